@@ -1,0 +1,12 @@
+"""B200-native implicit soil-column path of ClimaLand.jl (RichardsModel /
+EnergyHydrology implicit tendency, Jacobian, Newton linear solve, fused ARS111
+stage).  The product is `libclimaland_b200.so` (hand-written CUDA for sm_100a behind
+the C ABI of include/climaland_b200.h); this package is the host-side mirror of the
+reference's interface for that path.  There is no CPU fallback."""
+from . import _lib
+from ._lib import ClbError
+from .solver import (BOT_FLUX, BOT_FREE_DRAINAGE, BOT_MOISTURE_STATE, BROOKS_COREY, EARTH, ENERGY_HYDROLOGY,
+                     FIELDS, MATH_FAST, MATH_LIBM, RICHARDS, TOP_FLUX, TOP_MOISTURE_STATE, VAN_GENUCHTEN,
+                     VARIANT_AUTO, VARIANT_GENERIC, VARIANT_REGISTER_COLUMN, SoilColumnSolver)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

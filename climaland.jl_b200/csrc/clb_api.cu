@@ -1,0 +1,847 @@
+// clb_api.cu -- implementation of the C ABI declared in include/climaland_b200.h.
+// Host-side plumbing only: handle, device mirrors, layout transfers, kernel dispatch,
+// optional NCCL reductions.  All arithmetic is in the kernels (soil_*.cuh).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/climaland_b200.h"
+#include "layout_kernels.cuh"
+#include "soil_fused.cuh"
+#include "soil_hooks.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(CLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define TRY(expr)                  \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != CLB_OK) return rc__; \
+    } while (0)
+
+// ---- NCCL, loaded at run time (no link dependency; torch's or the system's copy) ----
+struct NcclUniqueId {
+    char internal[128];
+};
+typedef void *NcclComm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+int load_nccl()
+{
+    if (g_nccl.lib) return CLB_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(CLB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    NcclApi a;
+    a.lib = lib;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    a.AllReduce = (decltype(a.AllReduce))dlsym(lib, "ncclAllReduce");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString)
+        return fail(CLB_ERR_NCCL, "libnccl is missing a required symbol");
+    g_nccl = a;
+    return CLB_OK;
+}
+
+#define NCCL_TRY(expr)                                                                             \
+    do {                                                                                           \
+        int r__ = (expr);                                                                          \
+        if (r__ != 0) return fail(CLB_ERR_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+bool is_cell_field(int f) { return f >= 0 && f < CLB_F_NUM_CELL; }
+bool is_col_field(int f) { return f >= CLB_F_NUM_CELL && f < CLB_F_NUM; }
+
+constexpr int kBlock = 128;
+constexpr int kMaxLevels = 512;
+
+}  // namespace
+
+struct clb_handle_s {
+    clb_config cfg;
+    cudaStream_t stream = nullptr;
+    int64_t ld = 0;  // leading dimension of the mirrors (ncol rounded up to 32 doubles)
+    double *field[CLB_F_NUM] = {};
+    bool field_set[CLB_F_NUM] = {};
+    // grid
+    bool grid_set = false;
+    std::vector<double> z_c, z_f, dz_c, inv_dz_c, inv_dz_f;
+    double *d_grid = nullptr;  // z_c | dz_c | inv_dz_c | inv_dz_f, N each
+    // mask compaction
+    int64_t *d_idx = nullptr;
+    int64_t idx_max = -1;
+    // staging for host transfers
+    double *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    // scratch
+    double *work[6] = {};
+    double *carry = nullptr;
+    double *d_stats = nullptr;  // [0] dx^2, [1] non-finite count, [2] norm of the tolerance path, [3..6] balance
+    int32_t *d_flags = nullptr; // [0] converged, [1] iterations of the tolerance path
+    // multi-GPU
+    NcclComm comm = nullptr;
+    int32_t n_ranks = 1, rank = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int ensure_field(clb_handle h, int f)
+{
+    if (h->field[f]) return CLB_OK;
+    const size_t n = is_cell_field(f) ? (size_t)h->cfg.n_levels * h->ld : (size_t)h->ld;
+    CUDA_TRY(cudaMalloc(&h->field[f], n * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(h->field[f], 0, n * sizeof(double), h->stream));
+    return CLB_OK;
+}
+
+int ensure_work(clb_handle h, int count)
+{
+    const size_t n = (size_t)h->cfg.n_levels * h->ld;
+    for (int w = 0; w < count; ++w)
+        if (!h->work[w]) CUDA_TRY(cudaMalloc(&h->work[w], n * sizeof(double)));
+    if (!h->carry) CUDA_TRY(cudaMalloc(&h->carry, 4 * (size_t)h->ld * sizeof(double)));
+    return CLB_OK;
+}
+
+int ensure_stage(clb_handle h, size_t bytes)
+{
+    if (h->stage_bytes >= bytes) return CLB_OK;
+    if (h->d_stage) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaFree(h->d_stage));
+        h->d_stage = nullptr;
+        h->stage_bytes = 0;
+    }
+    CUDA_TRY(cudaMalloc(&h->d_stage, bytes));
+    h->stage_bytes = bytes;
+    return CLB_OK;
+}
+
+int require(clb_handle h, std::initializer_list<int> fields, const char *who)
+{
+    for (int f : fields)
+        if (!h->field_set[f]) return fail(CLB_ERR_UNSET, "%s: field %d was never set", who, f);
+    return CLB_OK;
+}
+
+int alloc_fields(clb_handle h, std::initializer_list<int> fields)
+{
+    for (int f : fields) {
+        TRY(ensure_field(h, f));
+        h->field_set[f] = true;
+    }
+    return CLB_OK;
+}
+
+clb::DevView make_view(clb_handle h)
+{
+    clb::DevView P;
+    std::memset(&P, 0, sizeof P);
+    const clb_config &c = h->cfg;
+    P.model = c.model; P.closure = c.closure; P.top_bc = c.top_bc; P.bottom_bc = c.bottom_bc;
+    P.topmodel = c.has_topmodel_source;
+    P.N = c.n_levels; P.ncol = c.n_columns; P.ld = h->ld;
+    P.earth = {c.rho_l, c.rho_i, c.cp_l, c.cp_i, c.T_ref, c.LH_f0};
+    const int N = c.n_levels;
+    P.z_c = h->d_grid; P.dz_c = h->d_grid + N; P.inv_dz_c = h->d_grid + 2 * N; P.inv_dz_f = h->d_grid + 3 * N;
+    if (h->grid_set) {
+        P.dz_top = h->dz_c[N - 1] / 2.0;
+        P.dz_bot = h->dz_c[0] / 2.0;
+    }
+    double *const *F = h->field;
+    P.nu = F[CLB_F_NU]; P.theta_r = F[CLB_F_THETA_R]; P.K_sat = F[CLB_F_K_SAT]; P.S_s = F[CLB_F_S_S];
+    P.hcm_a = F[CLB_F_HCM_A]; P.hcm_b = F[CLB_F_HCM_B]; P.hcm_m = F[CLB_F_HCM_M]; P.rho_c_ds = F[CLB_F_RHO_C_DS];
+    P.K_lag = F[CLB_F_K_LAG]; P.kappa_lag = F[CLB_F_KAPPA_LAG]; P.theta_l_lag = F[CLB_F_THETA_L_LAG];
+    P.is_sat = F[CLB_F_IS_SATURATED];
+    P.R_ss = F[CLB_F_R_SS]; P.R_ess = F[CLB_F_R_ESS]; P.h_grad = F[CLB_F_H_GRAD];
+    P.theta_bc_top = F[CLB_F_THETA_BC_TOP]; P.theta_bc_bot = F[CLB_F_THETA_BC_BOT];
+    P.Y_theta_l = F[CLB_F_Y_THETA_L]; P.Y_rho_e = F[CLB_F_Y_RHO_E_INT]; P.Y_theta_i = F[CLB_F_Y_THETA_I];
+    P.Y_intF_w = F[CLB_F_Y_INTF_W]; P.Y_intF_e = F[CLB_F_Y_INTF_E];
+    P.p_K = F[CLB_F_P_K]; P.p_psi = F[CLB_F_P_PSI]; P.p_T = F[CLB_F_P_T];
+    P.top_bc_w = F[CLB_F_TOP_BC_W]; P.bot_bc_w = F[CLB_F_BOT_BC_W];
+    P.top_bc_h = F[CLB_F_TOP_BC_H]; P.bot_bc_h = F[CLB_F_BOT_BC_H];
+    P.dfluxBCdY = F[CLB_F_DFLUXBCDY]; P.total_water = F[CLB_F_TOTAL_WATER];
+    P.dY_theta_l = F[CLB_F_DY_THETA_L]; P.dY_rho_e = F[CLB_F_DY_RHO_E_INT]; P.dY_theta_i = F[CLB_F_DY_THETA_I];
+    P.dY_intF_w = F[CLB_F_DY_INTF_W]; P.dY_intF_e = F[CLB_F_DY_INTF_E];
+    P.w11_lo = F[CLB_F_W11_LO]; P.w11_di = F[CLB_F_W11_DI]; P.w11_up = F[CLB_F_W11_UP];
+    P.w21_lo = F[CLB_F_W21_LO]; P.w21_di = F[CLB_F_W21_DI]; P.w21_up = F[CLB_F_W21_UP];
+    P.w22_lo = F[CLB_F_W22_LO]; P.w22_di = F[CLB_F_W22_DI]; P.w22_up = F[CLB_F_W22_UP];
+    P.b_theta_l = F[CLB_F_B_THETA_L]; P.b_rho_e = F[CLB_F_B_RHO_E_INT]; P.b_theta_i = F[CLB_F_B_THETA_I];
+    P.b_intF_w = F[CLB_F_B_INTF_W]; P.b_intF_e = F[CLB_F_B_INTF_E];
+    P.x_theta_l = F[CLB_F_X_THETA_L]; P.x_rho_e = F[CLB_F_X_RHO_E_INT]; P.x_theta_i = F[CLB_F_X_THETA_I];
+    P.x_intF_w = F[CLB_F_X_INTF_W]; P.x_intF_e = F[CLB_F_X_INTF_E];
+    for (int w = 0; w < 6; ++w) P.work[w] = h->work[w];
+    P.carry = h->carry;
+    P.stats = h->d_stats;
+    P.converged = nullptr;
+    return P;
+}
+
+inline unsigned grid_for(int64_t ncol) { return (unsigned)((ncol + kBlock - 1) / kBlock); }
+
+// closure x math dispatch for kernels templated <CLOSURE, MATH>
+#define DISPATCH_CM(h, KERNEL, grid, ...)                                                               \
+    do {                                                                                                \
+        const int cl__ = (h)->cfg.closure, ma__ = (h)->cfg.math_mode;                                   \
+        if (cl__ == 0 && ma__ == 0) KERNEL<0, 0><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);         \
+        else if (cl__ == 0 && ma__ == 1) KERNEL<0, 1><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);    \
+        else if (cl__ == 1 && ma__ == 0) KERNEL<1, 0><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);    \
+        else KERNEL<1, 1><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);                                \
+    } while (0)
+
+#define DISPATCH_CMN(h, KERNEL, NS, grid, ...)                                                             \
+    do {                                                                                                   \
+        const int cl__ = (h)->cfg.closure, ma__ = (h)->cfg.math_mode;                                      \
+        if (cl__ == 0 && ma__ == 0) KERNEL<0, 0, NS><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);        \
+        else if (cl__ == 0 && ma__ == 1) KERNEL<0, 1, NS><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);   \
+        else if (cl__ == 1 && ma__ == 0) KERNEL<1, 0, NS><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);   \
+        else KERNEL<1, 1, NS><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);                               \
+    } while (0)
+
+template <int NS>
+clb::GridConst<NS> make_grid_const(clb_handle h)
+{
+    clb::GridConst<NS> g;
+    for (int i = 0; i < NS; ++i) {
+        g.z_c[i] = h->z_c[i];
+        g.inv_dz_c[i] = h->inv_dz_c[i];
+        g.inv_dz_f[i] = h->inv_dz_f[i];
+    }
+    return g;
+}
+
+int step_inputs_ready(clb_handle h)
+{
+    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
+    TRY(require(h, {CLB_F_NU, CLB_F_THETA_R, CLB_F_K_SAT, CLB_F_S_S, CLB_F_HCM_A, CLB_F_HCM_B, CLB_F_Y_THETA_L},
+                "implicit path"));
+    if (h->cfg.closure == CLB_VAN_GENUCHTEN) TRY(require(h, {CLB_F_HCM_M}, "van Genuchten closure"));
+    if (h->cfg.model == CLB_ENERGY_HYDROLOGY)
+        TRY(require(h, {CLB_F_RHO_C_DS, CLB_F_K_LAG, CLB_F_KAPPA_LAG, CLB_F_THETA_L_LAG, CLB_F_Y_RHO_E_INT,
+                        CLB_F_Y_THETA_I},
+                    "EnergyHydrology"));
+    if (h->cfg.has_topmodel_source) {
+        TRY(require(h, {CLB_F_IS_SATURATED, CLB_F_R_SS, CLB_F_H_GRAD}, "TOPMODEL source"));
+        if (h->cfg.model == CLB_ENERGY_HYDROLOGY) TRY(require(h, {CLB_F_R_ESS}, "TOPMODEL source"));
+    }
+    if (h->cfg.top_bc == CLB_TOP_MOISTURE_STATE) TRY(require(h, {CLB_F_THETA_BC_TOP}, "MoistureStateBC top"));
+    if (h->cfg.bottom_bc == CLB_BOT_MOISTURE_STATE) TRY(require(h, {CLB_F_THETA_BC_BOT}, "MoistureStateBC bottom"));
+    // boundary fluxes and flux integrals default to zero when the host never set them
+    TRY(alloc_fields(h, {CLB_F_TOP_BC_W, CLB_F_BOT_BC_W, CLB_F_Y_INTF_W}));
+    if (h->cfg.model == CLB_ENERGY_HYDROLOGY) TRY(alloc_fields(h, {CLB_F_TOP_BC_H, CLB_F_BOT_BC_H, CLB_F_Y_INTF_E}));
+    if (h->cfg.model == CLB_RICHARDS && h->cfg.top_bc == CLB_TOP_MOISTURE_STATE) TRY(alloc_fields(h, {CLB_F_DFLUXBCDY}));
+    return CLB_OK;
+}
+
+int check_handle(clb_handle h)
+{
+    if (!h) return fail(CLB_ERR_INVALID, "null handle");
+    return CLB_OK;
+}
+
+int allreduce_doubles(clb_handle h, double *dptr, size_t n)
+{
+    if (!h->comm) return CLB_OK;
+    NCCL_TRY(g_nccl.AllReduce(dptr, dptr, n, kNcclFloat64, kNcclSum, h->comm, h->stream));
+    return CLB_OK;
+}
+
+// weighted per-column balance terms -> 4 atomically accumulated sums
+__global__ void __launch_bounds__(128) k_balance(const clb::DevView P, const double *w, double *out4)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v[4] = {0, 0, 0, 0};
+    if (c < P.ncol) {
+        const double wc = w ? w[c] : 1.0;
+        double water = 0.0, energy = 0.0;
+        for (int i = 0; i < P.N; ++i) {
+            const int64_t k = (int64_t)i * P.ld + c;
+            double vol = P.Y_theta_l[k];
+            if (P.model == 1) {
+                vol += P.Y_theta_i[k] * P.earth.rho_i / P.earth.rho_l;
+                energy += P.Y_rho_e[k] * P.dz_c[i];
+            }
+            water += vol * P.dz_c[i];
+        }
+        v[0] = wc * water;
+        v[1] = wc * P.Y_intF_w[c];
+        if (P.model == 1) {
+            v[2] = wc * energy;
+            v[3] = wc * P.Y_intF_e[c];
+        }
+    }
+    for (int j = 0; j < 4; ++j) {
+        double s = v[j];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(out4 + j, s);
+    }
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+int clb_abi_version(void) { return CLB_ABI_VERSION; }
+
+const char *clb_last_error(void) { return g_err.c_str(); }
+
+int clb_create(clb_handle *out, const clb_config *cfg)
+{
+    if (!out || !cfg) return fail(CLB_ERR_INVALID, "clb_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != CLB_ABI_VERSION)
+        return fail(CLB_ERR_INVALID, "clb_create: abi_version %d, library is %d", cfg->abi_version, CLB_ABI_VERSION);
+    if (cfg->model != CLB_RICHARDS && cfg->model != CLB_ENERGY_HYDROLOGY)
+        return fail(CLB_ERR_INVALID, "clb_create: unknown model %d", cfg->model);
+    if (cfg->closure != CLB_VAN_GENUCHTEN && cfg->closure != CLB_BROOKS_COREY)
+        return fail(CLB_ERR_INVALID, "clb_create: unknown closure %d", cfg->closure);
+    if (cfg->top_bc < 0 || cfg->top_bc > 1 || cfg->bottom_bc < 0 || cfg->bottom_bc > 2)
+        return fail(CLB_ERR_INVALID, "clb_create: unknown boundary condition kind");
+    if (cfg->math_mode != CLB_MATH_FAST && cfg->math_mode != CLB_MATH_LIBM)
+        return fail(CLB_ERR_INVALID, "clb_create: unknown math_mode %d", cfg->math_mode);
+    if (cfg->n_levels < 2 || cfg->n_levels > kMaxLevels)
+        return fail(CLB_ERR_INVALID, "clb_create: n_levels must be in [2, %d]", kMaxLevels);
+    if (cfg->n_columns < 1) return fail(CLB_ERR_INVALID, "clb_create: n_columns must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CLB_ERR_NO_DEVICE, "clb_create: no CUDA device available; this library has no CPU path");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(CLB_ERR_INVALID, "clb_create: device %d out of range (have %d)", cfg->device, ndev);
+    clb_handle h = new (std::nothrow) clb_handle_s();
+    if (!h) return fail(CLB_ERR_INVALID, "clb_create: out of host memory");
+    h->cfg = *cfg;
+    h->stream = (cudaStream_t)cfg->stream;
+    h->ld = (cfg->n_columns + 31) / 32 * 32;
+    DeviceGuard guard(cfg->device);
+    int rc = CLB_OK;
+    auto init = [&]() -> int {
+        CUDA_TRY(cudaMalloc(&h->d_grid, 4 * (size_t)cfg->n_levels * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->d_stats, 8 * sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(double), h->stream));
+        CUDA_TRY(cudaMalloc(&h->d_flags, 4 * sizeof(int32_t)));
+        CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int32_t), h->stream));
+        return CLB_OK;
+    };
+    rc = init();
+    if (rc != CLB_OK) {
+        clb_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return CLB_OK;
+}
+
+int clb_destroy(clb_handle h)
+{
+    if (!h) return CLB_OK;
+    DeviceGuard guard(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (auto &p : h->field) cudaFree(p);
+    for (auto &p : h->work) cudaFree(p);
+    cudaFree(h->carry);
+    cudaFree(h->d_grid);
+    cudaFree(h->d_idx);
+    cudaFree(h->d_stage);
+    cudaFree(h->d_stats);
+    cudaFree(h->d_flags);
+    delete h;
+    return CLB_OK;
+}
+
+int clb_sync(clb_handle h)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CLB_OK;
+}
+
+int clb_set_stream(clb_handle h, void *stream)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->stream = (cudaStream_t)stream;
+    return CLB_OK;
+}
+
+int clb_set_grid(clb_handle h, const double *z_c, const double *z_f)
+{
+    TRY(check_handle(h));
+    if (!z_c || !z_f) return fail(CLB_ERR_INVALID, "clb_set_grid: null pointer");
+    const int N = h->cfg.n_levels;
+    for (int i = 0; i < N; ++i)
+        if (!(z_f[i + 1] > z_f[i])) return fail(CLB_ERR_INVALID, "clb_set_grid: z_f must increase (bottom -> top)");
+    for (int i = 1; i < N; ++i)
+        if (!(z_c[i] > z_c[i - 1])) return fail(CLB_ERR_INVALID, "clb_set_grid: z_c must increase (bottom -> top)");
+    h->z_c.assign(z_c, z_c + N);
+    h->z_f.assign(z_f, z_f + N + 1);
+    h->dz_c.resize(N);
+    h->inv_dz_c.resize(N);
+    h->inv_dz_f.assign(N, 0.0);
+    for (int i = 0; i < N; ++i) {
+        h->dz_c[i] = z_f[i + 1] - z_f[i];
+        h->inv_dz_c[i] = 1.0 / h->dz_c[i];
+        if (i > 0) h->inv_dz_f[i] = 1.0 / (z_c[i] - z_c[i - 1]);
+    }
+    std::vector<double> pack;
+    pack.insert(pack.end(), h->z_c.begin(), h->z_c.end());
+    pack.insert(pack.end(), h->dz_c.begin(), h->dz_c.end());
+    pack.insert(pack.end(), h->inv_dz_c.begin(), h->inv_dz_c.end());
+    pack.insert(pack.end(), h->inv_dz_f.begin(), h->inv_dz_f.end());
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h->d_grid, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->grid_set = true;
+    return CLB_OK;
+}
+
+int clb_set_active_columns(clb_handle h, const int64_t *idx, int64_t n)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!idx) {
+        cudaFree(h->d_idx);
+        h->d_idx = nullptr;
+        h->idx_max = -1;
+        return CLB_OK;
+    }
+    if (n != h->cfg.n_columns)
+        return fail(CLB_ERR_INVALID, "clb_set_active_columns: n = %lld but the handle holds %lld columns", (long long)n,
+                    (long long)h->cfg.n_columns);
+    int64_t mx = -1;
+    for (int64_t j = 0; j < n; ++j) {
+        if (idx[j] < 0) return fail(CLB_ERR_INVALID, "clb_set_active_columns: negative index");
+        mx = std::max(mx, idx[j]);
+    }
+    if (!h->d_idx) CUDA_TRY(cudaMalloc(&h->d_idx, (size_t)n * sizeof(int64_t)));
+    CUDA_TRY(cudaMemcpy(h->d_idx, idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    h->idx_max = mx;
+    return CLB_OK;
+}
+
+static int transfer_geometry(clb_handle h, int32_t field, int64_t sl, int64_t sc, bool &cell, int64_t &extent,
+                             bool &dense)
+{
+    if (!is_cell_field(field) && !is_col_field(field)) return fail(CLB_ERR_INVALID, "unknown field id %d", field);
+    if (sl < 0 || sc < 0) return fail(CLB_ERR_INVALID, "strides must be >= 0");
+    cell = is_cell_field(field);
+    const int N = h->cfg.n_levels;
+    const int64_t maxcol = h->d_idx ? h->idx_max : h->cfg.n_columns - 1;
+    extent = maxcol * sc + (cell ? (int64_t)(N - 1) * sl : 0) + 1;
+    dense = !h->d_idx && (cell ? (sl == 1 && sc == N) : (sc == 1));
+    return CLB_OK;
+}
+
+int clb_set_field(clb_handle h, int32_t field, const double *src, int64_t stride_level, int64_t stride_column,
+                  int32_t mem)
+{
+    TRY(check_handle(h));
+    if (!src) return fail(CLB_ERR_INVALID, "clb_set_field: null source");
+    bool cell, dense;
+    int64_t extent;
+    TRY(transfer_geometry(h, field, stride_level, stride_column, cell, extent, dense));
+    DeviceGuard guard(h->cfg.device);
+    TRY(ensure_field(h, field));
+    const double *dsrc = src;
+    if (mem == CLB_HOST) {
+        TRY(ensure_stage(h, (size_t)extent * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_stage, src, (size_t)extent * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        dsrc = h->d_stage;
+    } else if (mem != CLB_DEVICE) {
+        return fail(CLB_ERR_INVALID, "clb_set_field: mem must be CLB_HOST or CLB_DEVICE");
+    }
+    const int N = h->cfg.n_levels;
+    const int64_t ncol = h->cfg.n_columns;
+    if (cell) {
+        const unsigned grid = (unsigned)((ncol + clb::kTileCols - 1) / clb::kTileCols);
+        const size_t smem = (size_t)N * (clb::kTileCols + 1) * sizeof(double);
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(clb::k_gather_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        clb::k_gather_cells<<<grid, 256, smem, h->stream>>>(h->field[field], h->ld, dsrc, stride_level, stride_column,
+                                                            h->d_idx, N, ncol);
+    } else {
+        clb::k_gather_cols<<<(unsigned)((ncol + 255) / 256), 256, 0, h->stream>>>(h->field[field], dsrc, stride_column,
+                                                                                  h->d_idx, ncol);
+    }
+    CUDA_TRY(cudaGetLastError());
+    h->field_set[field] = true;
+    return CLB_OK;
+}
+
+int clb_get_field(clb_handle h, int32_t field, double *dst, int64_t stride_level, int64_t stride_column, int32_t mem)
+{
+    TRY(check_handle(h));
+    if (!dst) return fail(CLB_ERR_INVALID, "clb_get_field: null destination");
+    bool cell, dense;
+    int64_t extent;
+    TRY(transfer_geometry(h, field, stride_level, stride_column, cell, extent, dense));
+    if (!h->field[field]) return fail(CLB_ERR_UNSET, "clb_get_field: field %d was never set or computed", field);
+    DeviceGuard guard(h->cfg.device);
+    double *ddst = dst;
+    if (mem == CLB_HOST) {
+        TRY(ensure_stage(h, (size_t)extent * sizeof(double)));
+        // a strided / masked destination keeps the elements the library does not own
+        if (!dense)
+            CUDA_TRY(cudaMemcpyAsync(h->d_stage, dst, (size_t)extent * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        ddst = h->d_stage;
+    } else if (mem != CLB_DEVICE) {
+        return fail(CLB_ERR_INVALID, "clb_get_field: mem must be CLB_HOST or CLB_DEVICE");
+    }
+    const int N = h->cfg.n_levels;
+    const int64_t ncol = h->cfg.n_columns;
+    if (cell) {
+        const unsigned grid = (unsigned)((ncol + clb::kTileCols - 1) / clb::kTileCols);
+        const size_t smem = (size_t)N * (clb::kTileCols + 1) * sizeof(double);
+        if (smem > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(clb::k_scatter_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        clb::k_scatter_cells<<<grid, 256, smem, h->stream>>>(h->field[field], h->ld, ddst, stride_level, stride_column,
+                                                             h->d_idx, N, ncol);
+    } else {
+        clb::k_scatter_cols<<<(unsigned)((ncol + 255) / 256), 256, 0, h->stream>>>(h->field[field], ddst,
+                                                                                   stride_column, h->d_idx, ncol);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (mem == CLB_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(dst, h->d_stage, (size_t)extent * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return CLB_OK;
+}
+
+int clb_fill_field(clb_handle h, int32_t field, double value)
+{
+    TRY(check_handle(h));
+    if (!is_cell_field(field) && !is_col_field(field)) return fail(CLB_ERR_INVALID, "unknown field id %d", field);
+    DeviceGuard guard(h->cfg.device);
+    TRY(ensure_field(h, field));
+    const int64_t n = is_cell_field(field) ? (int64_t)h->cfg.n_levels * h->ld : h->ld;
+    clb::k_fill<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->field[field], n, value);
+    CUDA_TRY(cudaGetLastError());
+    h->field_set[field] = true;
+    return CLB_OK;
+}
+
+int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *ld)
+{
+    TRY(check_handle(h));
+    if (!is_cell_field(field) && !is_col_field(field)) return fail(CLB_ERR_INVALID, "unknown field id %d", field);
+    if (!ptr) return fail(CLB_ERR_INVALID, "clb_field_device_ptr: null output");
+    DeviceGuard guard(h->cfg.device);
+    TRY(ensure_field(h, field));
+    h->field_set[field] = true;  // the caller fills it in place
+    *ptr = h->field[field];
+    if (ld) *ld = h->ld;
+    return CLB_OK;
+}
+
+int clb_update_implicit_cache(clb_handle h)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    TRY(step_inputs_ready(h));
+    TRY(alloc_fields(h, {CLB_F_P_PSI}));
+    if (h->cfg.model == CLB_RICHARDS)
+        TRY(alloc_fields(h, {CLB_F_P_K, CLB_F_TOTAL_WATER}));
+    else
+        TRY(alloc_fields(h, {CLB_F_P_T}));
+    nvtxRangePushA("update_implicit_cache!");
+    const clb::DevView P = make_view(h);
+    DISPATCH_CM(h, clb::k_update_implicit_cache, grid_for(P.ncol), P);
+    nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+int clb_update_boundary_fluxes(clb_handle h)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    TRY(step_inputs_ready(h));
+    TRY(require(h, {CLB_F_P_PSI}, "update_boundary_fluxes"));
+    if (h->cfg.model == CLB_RICHARDS) TRY(require(h, {CLB_F_P_K}, "update_boundary_fluxes"));
+    const clb::DevView P = make_view(h);
+    DISPATCH_CM(h, clb::k_update_boundary_fluxes, grid_for(P.ncol), P);
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+int clb_compute_imp_tendency(clb_handle h)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    TRY(step_inputs_ready(h));
+    TRY(require(h, {CLB_F_P_PSI}, "compute_imp_tendency (call update_implicit_cache first)"));
+    TRY(alloc_fields(h, {CLB_F_DY_THETA_L, CLB_F_DY_INTF_W}));
+    if (h->cfg.model == CLB_RICHARDS) {
+        TRY(require(h, {CLB_F_P_K}, "compute_imp_tendency"));
+    } else {
+        TRY(require(h, {CLB_F_P_T}, "compute_imp_tendency"));
+        TRY(alloc_fields(h, {CLB_F_DY_RHO_E_INT, CLB_F_DY_THETA_I, CLB_F_DY_INTF_E}));
+    }
+    nvtxRangePushA("compute_imp_tendency!");
+    const clb::DevView P = make_view(h);
+    clb::k_imp_tendency<<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P);
+    nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+int clb_compute_jacobian(clb_handle h, double dtgamma)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    TRY(step_inputs_ready(h));
+    TRY(alloc_fields(h, {CLB_F_W11_LO, CLB_F_W11_DI, CLB_F_W11_UP}));
+    if (h->cfg.model == CLB_RICHARDS) {
+        TRY(require(h, {CLB_F_P_K}, "compute_jacobian (call update_implicit_cache first)"));
+    } else {
+        TRY(require(h, {CLB_F_P_T}, "compute_jacobian (call update_implicit_cache first)"));
+        TRY(alloc_fields(h, {CLB_F_W21_LO, CLB_F_W21_DI, CLB_F_W21_UP, CLB_F_W22_LO, CLB_F_W22_DI, CLB_F_W22_UP}));
+    }
+    nvtxRangePushA("compute_jacobian!");
+    const clb::DevView P = make_view(h);
+    DISPATCH_CM(h, clb::k_jacobian, grid_for(P.ncol), P, dtgamma);
+    nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+int clb_ldiv(clb_handle h)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    TRY(require(h, {CLB_F_W11_LO, CLB_F_W11_DI, CLB_F_W11_UP, CLB_F_B_THETA_L}, "ldiv"));
+    TRY(alloc_fields(h, {CLB_F_X_THETA_L, CLB_F_X_INTF_W}));
+    TRY(ensure_field(h, CLB_F_B_INTF_W));
+    if (h->cfg.model == CLB_ENERGY_HYDROLOGY) {
+        TRY(require(h, {CLB_F_W21_LO, CLB_F_W21_DI, CLB_F_W21_UP, CLB_F_W22_LO, CLB_F_W22_DI, CLB_F_W22_UP,
+                        CLB_F_B_RHO_E_INT},
+                    "ldiv"));
+        TRY(alloc_fields(h, {CLB_F_X_RHO_E_INT, CLB_F_X_THETA_I, CLB_F_X_INTF_E}));
+        TRY(ensure_field(h, CLB_F_B_THETA_I));
+        TRY(ensure_field(h, CLB_F_B_INTF_E));
+    }
+    TRY(ensure_work(h, 2));
+    nvtxRangePushA("ldiv!");
+    const clb::DevView P = make_view(h);
+    clb::k_ldiv<<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P);
+    nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double tol, clb_stats *stats)
+{
+    TRY(check_handle(h));
+    if (max_iters < 1) return fail(CLB_ERR_INVALID, "clb_implicit_step: max_iters must be >= 1");
+    DeviceGuard guard(h->cfg.device);
+    TRY(step_inputs_ready(h));
+    const int N = h->cfg.n_levels;
+    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    const bool fixed = tol < 0.0;
+    int variant = h->cfg.kernel_variant;
+    const bool have_static = (N == 15);
+    if (variant == CLB_VARIANT_AUTO) variant = (fixed && have_static) ? CLB_VARIANT_REGISTER_COLUMN : CLB_VARIANT_GENERIC;
+    if (variant == CLB_VARIANT_REGISTER_COLUMN && !(fixed && have_static))
+        return fail(CLB_ERR_INVALID, "clb_implicit_step: the register-column variant needs N == 15 and tol < 0");
+    if (variant == CLB_VARIANT_GENERIC) TRY(ensure_work(h, eh ? 6 : 3));
+    CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(double), h->stream));
+    clb::DevView P = make_view(h);
+    const unsigned grid = grid_for(P.ncol);
+    nvtxRangePushA("implicit_step!");
+    int iters_done = max_iters;
+    if (fixed) {
+        if (variant == CLB_VARIANT_REGISTER_COLUMN) {
+            const clb::GridConst<15> gc = make_grid_const<15>(h);
+            if (eh)
+                DISPATCH_CMN(h, clb::k_eh_step_reg, 15, grid, P, gc, dtgamma, max_iters);
+            else
+                DISPATCH_CMN(h, clb::k_richards_step_reg, 15, grid, P, gc, dtgamma, max_iters);
+        } else {
+            if (eh)
+                DISPATCH_CM(h, clb::k_eh_step_generic, grid, P, dtgamma, 0, max_iters);
+            else
+                DISPATCH_CM(h, clb::k_richards_step_generic, grid, P, dtgamma, 0, max_iters);
+            clb::k_commit_state<<<grid, kBlock, 0, h->stream>>>(P);
+        }
+        CUDA_TRY(cudaGetLastError());
+        if (stats) TRY(allreduce_doubles(h, h->d_stats, 2));
+    } else {
+        // tolerance path: one launch per iteration; converged flag and norm stay on the device
+        CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int32_t), h->stream));
+        P.converged = h->d_flags;
+        for (int it = 0; it < max_iters; ++it) {
+            if (eh)
+                DISPATCH_CM(h, clb::k_eh_step_generic, grid, P, dtgamma, it, it + 1);
+            else
+                DISPATCH_CM(h, clb::k_richards_step_generic, grid, P, dtgamma, it, it + 1);
+            CUDA_TRY(cudaGetLastError());
+            TRY(allreduce_doubles(h, h->d_stats, 1));
+            clb::k_convergence_test<<<1, 32, 0, h->stream>>>(P, tol, h->d_stats + 2, h->d_flags + 1);
+        }
+        P.converged = nullptr;
+        clb::k_commit_state<<<grid, kBlock, 0, h->stream>>>(P);
+        CUDA_TRY(cudaGetLastError());
+        if (stats) TRY(allreduce_doubles(h, h->d_stats + 1, 1));
+    }
+    nvtxRangePop();
+    if (stats) {
+        double hs[3];
+        int32_t hf[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(hs, h->d_stats, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+        if (!fixed) CUDA_TRY(cudaMemcpyAsync(hf, h->d_flags, sizeof hf, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        stats->iterations = fixed ? iters_done : hf[1];
+        stats->converged = fixed ? 0 : hf[0];
+        stats->dx_norm = fixed ? std::sqrt(hs[0]) : hs[2];
+        stats->nan_count = (int64_t)std::llround(hs[1]);
+    }
+    return CLB_OK;
+}
+
+int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters, const int32_t *in_fields,
+                           const double *const *in_ptrs, int32_t n_in, const int32_t *out_fields,
+                           double *const *out_ptrs, int32_t n_out)
+{
+    TRY(check_handle(h));
+    const int N = h->cfg.n_levels;
+    for (int j = 0; j < n_in; ++j) {
+        const bool cell = is_cell_field(in_fields[j]);
+        TRY(clb_set_field(h, in_fields[j], in_ptrs[j], 1, cell ? N : 1, CLB_HOST));
+    }
+    TRY(clb_implicit_step(h, dtgamma, max_iters, -1.0, nullptr));
+    for (int j = 0; j < n_out; ++j) {
+        const bool cell = is_cell_field(out_fields[j]);
+        TRY(clb_get_field(h, out_fields[j], out_ptrs[j], 1, cell ? N : 1, CLB_HOST));
+    }
+    return clb_sync(h);
+}
+
+int clb_column_integral(clb_handle h, int32_t cell_field, int32_t col_field_out)
+{
+    TRY(check_handle(h));
+    if (!is_cell_field(cell_field) || !is_col_field(col_field_out))
+        return fail(CLB_ERR_INVALID, "clb_column_integral: (cell field, column field) expected");
+    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
+    if (!h->field[cell_field]) return fail(CLB_ERR_UNSET, "clb_column_integral: field %d was never set", cell_field);
+    DeviceGuard guard(h->cfg.device);
+    TRY(alloc_fields(h, {col_field_out}));
+    const clb::DevView P = make_view(h);
+    clb::k_column_integral<<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, h->field[cell_field], h->field[col_field_out]);
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+int clb_global_balance(clb_handle h, double *out4)
+{
+    TRY(check_handle(h));
+    if (!out4) return fail(CLB_ERR_INVALID, "clb_global_balance: null output");
+    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
+    TRY(require(h, {CLB_F_Y_THETA_L}, "clb_global_balance"));
+    DeviceGuard guard(h->cfg.device);
+    TRY(alloc_fields(h, {CLB_F_Y_INTF_W}));
+    if (h->cfg.model == CLB_ENERGY_HYDROLOGY) {
+        TRY(require(h, {CLB_F_Y_RHO_E_INT, CLB_F_Y_THETA_I}, "clb_global_balance"));
+        TRY(alloc_fields(h, {CLB_F_Y_INTF_E}));
+    }
+    double *acc = h->d_stats + 3;
+    CUDA_TRY(cudaMemsetAsync(acc, 0, 4 * sizeof(double), h->stream));
+    const clb::DevView P = make_view(h);
+    k_balance<<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, h->field_set[CLB_F_AREA_WEIGHT] ? h->field[CLB_F_AREA_WEIGHT] : nullptr,
+                                                        acc);
+    CUDA_TRY(cudaGetLastError());
+    TRY(allreduce_doubles(h, acc, 4));
+    CUDA_TRY(cudaMemcpyAsync(out4, acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CLB_OK;
+}
+
+int clb_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(CLB_ERR_INVALID, "clb_comm_unique_id: null output");
+    TRY(load_nccl());
+    NcclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof id);
+    return CLB_OK;
+}
+
+int clb_comm_init(clb_handle h, const void *id128, int32_t n_ranks, int32_t rank)
+{
+    TRY(check_handle(h));
+    if (!id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(CLB_ERR_INVALID, "clb_comm_init: bad arguments");
+    TRY(load_nccl());
+    DeviceGuard guard(h->cfg.device);
+    NcclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    NCCL_TRY(g_nccl.CommInitRank(&h->comm, n_ranks, id, rank));
+    h->n_ranks = n_ranks;
+    h->rank = rank;
+    return CLB_OK;
+}
+
+}  // extern "C"

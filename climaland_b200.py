@@ -1,0 +1,13 @@
+"""Import shim: the package directory is named `climaland.jl_b200/` (not a valid
+Python identifier), so `import climaland_b200` loads it under this name."""
+import importlib.util
+import os
+import sys
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_pkg = os.path.join(_here, "climaland.jl_b200")
+_spec = importlib.util.spec_from_file_location("climaland_b200", os.path.join(_pkg, "__init__.py"),
+                                               submodule_search_locations=[_pkg])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["climaland_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,235 @@
+/*
+ * climaland_b200.h -- C ABI of libclimaland_b200.so: the B200 (sm_100a, FP64)
+ * implementation of ClimaLand.jl's implicit soil-column path.
+ *
+ * This is the drop-in boundary.  ClimaLand's Julia hooks keep their
+ * names and call these entry points through `ccall` (binding shown in
+ * INTEGRATION.md and julia/ClimaLandB200.jl).  Each entry point cites the
+ * reference interface it replaces; paths are relative to the ClimaLand.jl tree.
+ *
+ *   make_update_implicit_cache  src/shared_utilities/models.jl:238-246
+ *   make_compute_imp_tendency   src/standalone/Soil/rre.jl:161-203,
+ *                               src/standalone/Soil/energy_hydrology.jl:363-425
+ *   make_compute_jacobian       rre.jl:391-458, energy_hydrology.jl:466-576
+ *   initialize_jacobian + ldiv! src/shared_utilities/implicit_timestepping.jl:63-172
+ *                               (ClimaCore MatrixFields.field_matrix_solve!)
+ *   Newton/ARS111 stage         src/simulations/Simulations.jl:127-135
+ *                               (ClimaTimeSteppers IMEXAlgorithm + NewtonsMethod)
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, strides; no C++ or torch types.
+ *   - every function returns CLB_OK (0) or a negative clb_status; the message is
+ *     available from clb_last_error().  Nothing throws or exits across the ABI.
+ *   - levels i = 0..N-1 run bottom -> top (Fields.level(.,1) is the bottom,
+ *     src/standalone/Soil/boundary_conditions.jl:351); z <= 0 increases upward;
+ *     fluxes are positive in +z.
+ *   - a handle is bound to one CUDA device and one stream; calls on a handle are
+ *     serialised by the caller (ClimaTimeSteppers drives the hooks from one task).
+ *     Work is enqueued asynchronously on the stream unless stated otherwise.
+ *   - the library keeps its own column-fastest (SoA over levels) device mirrors:
+ *     element (level i, column c) of a per-cell field lives at  base[i*ld + c].
+ *     Callers never see that layout: clb_set_field / clb_get_field take the
+ *     caller's own strides (ClimaCore `parent(field)` is level-fastest:
+ *     stride_level = 1, stride_column = N*Nf) and transpose on the device.
+ *   - there is no CPU fallback: without a CUDA device clb_create fails.
+ */
+#ifndef CLIMALAND_B200_H
+#define CLIMALAND_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define CLB_ABI_VERSION 1
+
+typedef struct clb_handle_s *clb_handle;
+
+typedef enum {
+    CLB_OK = 0,
+    CLB_ERR_INVALID = -1,      /* bad argument / configuration            */
+    CLB_ERR_CUDA = -2,         /* CUDA runtime error (see clb_last_error) */
+    CLB_ERR_UNSET = -3,        /* a field the hook needs was never set    */
+    CLB_ERR_NCCL = -4,         /* NCCL missing or failed                  */
+    CLB_ERR_NO_DEVICE = -5     /* no CUDA device: there is no CPU path    */
+} clb_status;
+
+/* model kinds: RichardsModel (rre.jl) / EnergyHydrology (energy_hydrology.jl) */
+enum { CLB_RICHARDS = 0, CLB_ENERGY_HYDROLOGY = 1 };
+/* retention closures: src/standalone/Soil/retention_models.jl:30-67 */
+enum { CLB_VAN_GENUCHTEN = 0, CLB_BROOKS_COREY = 1 };
+/* boundary conditions handled inside the implicit stage
+ * (src/standalone/Soil/boundary_conditions.jl:227-411); every other BC type is
+ * a flux computed by the host's explicit stage and passed in as a value. */
+enum { CLB_TOP_FLUX = 0, CLB_TOP_MOISTURE_STATE = 1 };
+enum { CLB_BOT_FLUX = 0, CLB_BOT_FREE_DRAINAGE = 1, CLB_BOT_MOISTURE_STATE = 2 };
+/* where a caller pointer lives */
+enum { CLB_HOST = 0, CLB_DEVICE = 1 };
+/* closure arithmetic: FAST shares log(S) between the powers (exp/log form,
+ * <= ~1e-14 relative from the pow form); LIBM evaluates the reference's pow
+ * expressions literally with CUDA libm. */
+enum { CLB_MATH_FAST = 0, CLB_MATH_LIBM = 1 };
+/* kernel variant of the fused step (0 = let the library choose) */
+enum { CLB_VARIANT_AUTO = 0, CLB_VARIANT_REGISTER_COLUMN = 1, CLB_VARIANT_GENERIC = 2 };
+
+/* Field ids.  "cell" fields are N x ncol, "col" fields are ncol. */
+typedef enum {
+    /* ---- time-invariant parameters (RichardsParameters rre.jl:22-47,
+     *      EnergyHydrologyParameters energy_hydrology.jl:60-170) -- cell */
+    CLB_F_NU = 0, CLB_F_THETA_R, CLB_F_K_SAT, CLB_F_S_S,
+    CLB_F_HCM_A,            /* vG alpha | BC c      */
+    CLB_F_HCM_B,            /* vG n     | BC psi_b  */
+    CLB_F_HCM_M,            /* vG m     | unused    */
+    CLB_F_RHO_C_DS,         /* EH: dry-soil volumetric heat capacity */
+    /* ---- lagged cache written by the host's explicit stage -- cell */
+    CLB_F_K_LAG, CLB_F_KAPPA_LAG, CLB_F_THETA_L_LAG,   /* EH: p.soil.{K,kappa,theta_l} */
+    CLB_F_IS_SATURATED,     /* TOPMODEL source mask, Runoff/Runoff.jl:321-359 */
+    /* ---- prognostic state Y -- cell */
+    CLB_F_Y_THETA_L, CLB_F_Y_RHO_E_INT, CLB_F_Y_THETA_I,
+    /* ---- implicit cache p.soil.{K,psi,T} -- cell */
+    CLB_F_P_K, CLB_F_P_PSI, CLB_F_P_T,
+    /* ---- implicit tendency dY -- cell */
+    CLB_F_DY_THETA_L, CLB_F_DY_RHO_E_INT, CLB_F_DY_THETA_I,
+    /* ---- Jacobian blocks, TridiagonalMatrixRow (lower, diag, upper) -- cell */
+    CLB_F_W11_LO, CLB_F_W11_DI, CLB_F_W11_UP,   /* (theta_l, theta_l)      */
+    CLB_F_W21_LO, CLB_F_W21_DI, CLB_F_W21_UP,   /* (rho_e_int, theta_l) EH */
+    CLB_F_W22_LO, CLB_F_W22_DI, CLB_F_W22_UP,   /* (rho_e_int, rho_e_int)  */
+    /* ---- linear solve right-hand side b and solution x -- cell */
+    CLB_F_B_THETA_L, CLB_F_B_RHO_E_INT, CLB_F_B_THETA_I,
+    CLB_F_X_THETA_L, CLB_F_X_RHO_E_INT, CLB_F_X_THETA_I,
+    CLB_F_NUM_CELL,
+    /* ---- per-column fields */
+    CLB_F_R_SS = CLB_F_NUM_CELL, CLB_F_R_ESS, CLB_F_H_GRAD,     /* lagged TOPMODEL */
+    CLB_F_THETA_BC_TOP, CLB_F_THETA_BC_BOT,                     /* MoistureStateBC values */
+    CLB_F_TOP_BC_W, CLB_F_BOT_BC_W, CLB_F_TOP_BC_H, CLB_F_BOT_BC_H, /* p.soil.top_bc/bottom_bc */
+    CLB_F_DFLUXBCDY, CLB_F_TOTAL_WATER,
+    CLB_F_Y_INTF_W, CLB_F_Y_INTF_E,          /* Y.soil.∫F_vol_liq_water_dt, ∫F_e_dt */
+    CLB_F_DY_INTF_W, CLB_F_DY_INTF_E,
+    CLB_F_B_INTF_W, CLB_F_B_INTF_E, CLB_F_X_INTF_W, CLB_F_X_INTF_E,
+    CLB_F_AREA_WEIGHT,                        /* weights of the global balance sums */
+    CLB_F_NUM
+} clb_field;
+
+typedef struct {
+    int32_t abi_version;          /* = CLB_ABI_VERSION */
+    int32_t model;                /* CLB_RICHARDS | CLB_ENERGY_HYDROLOGY */
+    int32_t closure;              /* CLB_VAN_GENUCHTEN | CLB_BROOKS_COREY */
+    int32_t top_bc, bottom_bc;
+    int32_t has_topmodel_source;  /* implicit TOPMODELSubsurfaceRunoff source present */
+    int32_t n_levels;             /* N */
+    int32_t device;               /* CUDA device ordinal */
+    int64_t n_columns;            /* active columns held by this handle (this rank's shard) */
+    void *stream;                 /* cudaStream_t; NULL = legacy default stream */
+    int32_t math_mode;            /* CLB_MATH_FAST | CLB_MATH_LIBM */
+    int32_t kernel_variant;       /* CLB_VARIANT_* */
+    /* LandParameters constants (src/shared_utilities/Parameters.jl:11-58) */
+    double rho_l, rho_i, cp_l, cp_i, T_ref, LH_f0;
+} clb_config;
+
+typedef struct {
+    int32_t iterations;     /* Newton iterations performed */
+    int32_t converged;      /* 1 if the tolerance test passed (always 0 for tol < 0) */
+    double dx_norm;         /* ||dx||_2 of the last iteration over all columns of all ranks */
+    int64_t nan_count;      /* non-finite entries of the new state (NaNCheckCallback, utils.jl:639-661) */
+} clb_stats;
+
+/* ---- lifetime ----------------------------------------------------------- */
+int clb_abi_version(void);
+/* Per-thread message of the last failure (also valid when handle creation failed). */
+const char *clb_last_error(void);
+/* Allocates the device mirrors.  Replaces: model construction + initialize(model)
+ * for the soil part of Y and p (src/shared_utilities/models.jl:493-499). */
+int clb_create(clb_handle *out, const clb_config *cfg);
+int clb_destroy(clb_handle h);
+/* Blocks until everything enqueued on the handle's stream has finished. */
+int clb_sync(clb_handle h);
+/* Switch the stream later calls are enqueued on (CUDA.jl task-local stream). */
+int clb_set_stream(clb_handle h, void *stream);
+
+/* ---- geometry and masks -------------------------------------------------- */
+/* Cell centres z_c[N] and faces z_f[N+1] (host pointers) as ClimaCore produced
+ * them (Domains.jl:636-667); thickness and spacings follow Domains.get_dz
+ * (Domains.jl:935-949). */
+int clb_set_grid(clb_handle h, const double *z_c, const double *z_f);
+/* Column j of the handle is column idx[j] of the caller's arrays (land-sea mask
+ * compaction; inactive columns are never read or written: test/standalone/Soil/
+ * mask_test.jl:53-61).  idx == NULL restores the identity.  Host pointer. */
+int clb_set_active_columns(clb_handle h, const int64_t *idx, int64_t n);
+
+/* ---- field transfer ------------------------------------------------------ */
+/* Copy a caller array into / out of the library mirror.  Element (i, c) of the
+ * caller array is at  ptr[i*stride_level + idx[c]*stride_column]  (strides in
+ * elements, >= 0; stride_level is ignored for per-column fields).  `mem` says
+ * whether ptr is a host or a device pointer. */
+int clb_set_field(clb_handle h, int32_t field, const double *src, int64_t stride_level,
+                  int64_t stride_column, int32_t mem);
+int clb_get_field(clb_handle h, int32_t field, double *dst, int64_t stride_level,
+                  int64_t stride_column, int32_t mem);
+/* Broadcast a scalar parameter (the reference accepts scalars or fields). */
+int clb_fill_field(clb_handle h, int32_t field, double value);
+/* Device pointer and leading dimension of the library mirror of a field, for
+ * callers that want to fill it in place (resident-SoA mode). */
+int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *ld);
+
+/* ---- the hooks, fine-grained (parity-checkable per call) ----------------- */
+/* update_implicit_cache!(p, Y, t): models.jl:238-246.  Richards: K, psi,
+ * total_water and, if the top BC is MoistureStateBC, the boundary fluxes and
+ * dfluxBCdY (rre.jl:368-380, 460-468).  EnergyHydrology: T and psi
+ * (energy_hydrology.jl:427-455). */
+int clb_update_implicit_cache(clb_handle h);
+/* Explicit-stage flavour: always evaluates state-type boundary fluxes (rre.jl:111-149). */
+int clb_update_boundary_fluxes(clb_handle h);
+/* compute_imp_tendency!(dY, Y, p, t): rre.jl:161-203, energy_hydrology.jl:363-425. */
+int clb_compute_imp_tendency(clb_handle h);
+/* compute_jacobian!(W, Y, p, dtgamma, t): rre.jl:391-458, energy_hydrology.jl:466-576. */
+int clb_compute_jacobian(clb_handle h, double dtgamma);
+/* ldiv!(x, W, b): BlockDiagonalSolve / BlockLowerTriangularSolve(theta_l),
+ * implicit_timestepping.jl:160-171; x = -b for the -I blocks. */
+int clb_ldiv(clb_handle h);
+
+/* ---- the fused implicit stage -------------------------------------------- */
+/* One implicit ARS111 stage on the resident state Y (in: U = temp, out: new U):
+ * cache_imp!, then max_iters x (Wfact, T_imp!, residual, ldiv!, update), all in
+ * one kernel when tol < 0 (the reference default: fixed iterations, no
+ * convergence checker, Simulations.jl:127-135).  With tol >= 0 the iterations
+ * are separate launches that stop -- without a host round trip -- once
+ * ||dx||_2 <= tol over all columns of all ranks.  stats may be NULL; when it is
+ * not, the call synchronises the stream to fill it. */
+int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double tol, clb_stats *stats);
+
+/* Host-buffer convenience for the end-to-end path: upload the per-step inputs
+ * (state and lagged cache, level-fastest host arrays with column stride N),
+ * run the fused stage, download the new state.  n_in / n_out fields. */
+int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters,
+                           const int32_t *in_fields, const double *const *in_ptrs, int32_t n_in,
+                           const int32_t *out_fields, double *const *out_ptrs, int32_t n_out);
+
+/* ---- diagnostics / reductions -------------------------------------------- */
+/* out[c] = sum_i field[i,c] * dz_c[i]  (ClimaCore column_integral_definite!,
+ * rre.jl:502-511).  out is a per-column field id. */
+int clb_column_integral(clb_handle h, int32_t cell_field, int32_t col_field_out);
+/* Weighted global sums for the water / energy balance (definition
+ * ext/land_sim_vis/plotting_utils.jl:160-178): out[0] = sum_c w_c * column
+ * water, out[1] = sum_c w_c * intF_w, out[2] = sum_c w_c * column energy,
+ * out[3] = sum_c w_c * intF_e.  All-reduced over ranks when a communicator is
+ * attached.  Synchronous; out is a host pointer to 4 doubles. */
+int clb_global_balance(clb_handle h, double *out4);
+
+/* ---- multi-GPU (one handle per rank; columns are sharded, no halo) -------- */
+/* NCCL is loaded at run time (libnccl.so.2).  Rank 0 creates the id, the host
+ * side broadcasts the 128 bytes (ClimaComms / torch.distributed), every rank
+ * calls clb_comm_init. */
+int clb_comm_unique_id(void *id128);
+int clb_comm_init(clb_handle h, const void *id128, int32_t n_ranks, int32_t rank);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIMALAND_B200_H */

@@ -1,0 +1,133 @@
+"""GPU parity of the fine-grained hooks (update_implicit_cache!, compute_imp_tendency!,
+compute_jacobian!, ldiv!) against the CPU oracle on identical seeded inputs, through the
+C ABI.  Tolerance: 1e-12 norm-wise relative per call (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, cuda_solver, oracle_problem
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+import os, sys  # noqa: E401,E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+
+def _workload(model, ncol, N, seed, topmodel=False):
+    import climaland_b200  # noqa: F401
+    from climaland_b200 import workloads
+    return workloads.make_workload(model, ncol, N=N, seed=seed, topmodel=topmodel)
+
+
+def _to_brooks_corey(w):
+    """Brooks-Corey parameters and a state consistent with them: hydrostatic above a water
+    table (psi = z_wt - z), S = (psi/psi_b)^(-c), so psi stays within tens of metres.  (Random
+    theta with random c gives psi ~ -1e16 m, a problem whose own conditioning is ~1e8.)"""
+    rng = np.random.default_rng(7)
+    w = dict(w)
+    shp = w["nu"].shape
+    c = rng.uniform(0.15, 0.6, shp)
+    psi_b = -rng.uniform(0.05, 0.5, shp)
+    z_wt = rng.uniform(-40.0, -10.0, (shp[0], 1))
+    psi = z_wt - w["z_c"][None, :]
+    S = np.where(psi < psi_b, (np.minimum(psi, psi_b) / psi_b) ** (-c), 1.0)
+    nu_eff = w["nu"] - w.get("y_theta_i", 0.0)
+    theta = w["theta_r"] + S * (nu_eff - w["theta_r"])
+    theta = theta * (1.0 + rng.uniform(-0.02, 0.02, shp))
+    w["y_theta_l"] = np.clip(theta, w["theta_r"] + 1e-3, nu_eff + 5e-3)
+    w["hcm_a"], w["hcm_b"] = c, psi_b
+    if "theta_l_lag" in w:
+        w["theta_l_lag"] = np.minimum(nu_eff, w["y_theta_l"])
+    if "is_saturated" in w:
+        w["is_saturated"] = (w["y_theta_l"] >= nu_eff).astype(np.float64)
+    return w
+
+
+CASES = [
+    # model, closure, top_bc, bottom_bc, topmodel, N, ncol
+    ("richards", 0, 0, 0, False, 15, 1000),
+    ("richards", 0, 1, 1, False, 15, 333),
+    ("richards", 0, 1, 2, True, 20, 130),
+    ("richards", 1, 0, 1, False, 15, 257),
+    ("richards", 1, 1, 2, True, 7, 65),
+    ("energy_hydrology", 0, 0, 0, False, 15, 1000),
+    ("energy_hydrology", 0, 0, 0, True, 15, 300),
+    ("energy_hydrology", 1, 0, 0, True, 50, 100),
+    ("energy_hydrology", 0, 1, 1, False, 15, 64),
+]
+
+
+@pytest.mark.parametrize("math_mode", [0, 1])
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-cl{c[1]}-t{c[2]}b{c[3]}-tm{int(c[4])}-N{c[5]}" for c in CASES])
+def test_hooks_match_oracle(case, math_mode):
+    model, closure, top_bc, bottom_bc, topmodel, N, ncol = case
+    w = _workload(model, ncol, N, seed=11, topmodel=topmodel)
+    if closure == 1:
+        w = _to_brooks_corey(w)
+    rng = np.random.default_rng(3)
+    if top_bc == 1:
+        w["theta_bc_top"] = w["nu"][:, -1] - rng.uniform(1e-3, 0.1, ncol)
+    if bottom_bc == 2:
+        w["theta_bc_bot"] = w["nu"][:, 0] - rng.uniform(1e-3, 0.1, ncol)
+    P, Y, p = oracle_problem(w, closure, top_bc, bottom_bc)
+    s = cuda_solver(w, closure, top_bc, bottom_bc, math_mode=math_mode)
+    eh = model == "energy_hydrology"
+
+    # update_implicit_cache!
+    P.update_implicit_cache(Y, p)
+    s.update_implicit_cache()
+    assert_close(s.get("p_psi"), p.psi, TOL, "psi")
+    if eh:
+        assert_close(s.get("p_t"), p.T, TOL, "T")
+    else:
+        assert_close(s.get("p_k"), p.K, TOL, "K")
+        assert_close(s.get("total_water"), p.total_water, TOL, "total_water")
+        if top_bc == 1:
+            assert_close(s.get("top_bc_w"), p.top_bc_w, TOL, "top_bc")
+            assert_close(s.get("bot_bc_w"), p.bot_bc_w, TOL, "bot_bc")
+            assert_close(s.get("dfluxbcdy"), p.dfluxBCdY, TOL, "dfluxBCdY")
+
+    # compute_imp_tendency!
+    dY = P.new_state()
+    P.compute_imp_tendency(dY, Y, p)
+    s.compute_imp_tendency()
+    assert_close(s.get("dy_theta_l"), dY.theta_l, TOL, "dY.theta_l")
+    assert_close(s.get("dy_intf_w"), dY.intF_w, TOL, "dY.intF_w")
+    if eh:
+        assert_close(s.get("dy_rho_e_int"), dY.rho_e_int, TOL, "dY.rho_e_int")
+        assert_close(s.get("dy_intf_e"), dY.intF_e, TOL, "dY.intF_e")
+        assert np.all(s.get("dy_theta_i") == 0.0)
+
+    # compute_jacobian!
+    dtg = 900.0
+    W = P.new_jacobian()
+    P.compute_jacobian(W, Y, p, dtg)
+    s.compute_jacobian(dtg)
+    blocks = ["w11"] + (["w21", "w22"] if eh else [])
+    for b in blocks:
+        for d in ("lo", "di", "up"):
+            assert_close(s.get(f"{b}_{d}"), getattr(W, f"{b}_{d}"), TOL, f"{b}_{d}")
+
+    # ldiv!
+    b = P.new_state()
+    b.theta_l[...] = rng.normal(0, 1e-3, b.theta_l.shape)
+    b.intF_w[...] = rng.normal(0, 1.0, ncol)
+    s.set("b_theta_l", b.theta_l)
+    s.set("b_intf_w", b.intF_w)
+    if eh:
+        b.rho_e_int[...] = rng.normal(0, 1e4, b.theta_l.shape)
+        b.theta_i[...] = rng.normal(0, 1e-3, b.theta_l.shape)
+        b.intF_e[...] = rng.normal(0, 1.0, ncol)
+        s.set("b_rho_e_int", b.rho_e_int)
+        s.set("b_theta_i", b.theta_i)
+        s.set("b_intf_e", b.intF_e)
+    x = P.new_state()
+    P.ldiv(x, W, b)
+    s.ldiv()
+    assert_close(s.get("x_theta_l"), x.theta_l, TOL, "x.theta_l")
+    assert_close(s.get("x_intf_w"), x.intF_w, TOL, "x.intF_w")
+    if eh:
+        assert_close(s.get("x_rho_e_int"), x.rho_e_int, TOL, "x.rho_e_int")
+        assert_close(s.get("x_theta_i"), x.theta_i, TOL, "x.theta_i")
+        assert_close(s.get("x_intf_e"), x.intF_e, TOL, "x.intF_e")
+    s.close()
