@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- column-steps/s of the fused implicit soil-column stage on B200.
+
+Workload (BASELINE.json configs[1]): EnergyHydrology, soil only, ~1 degree global land
+(61 206 columns = global_domain nelements (101, 15), 15 levels), van Genuchten closure,
+per-cell parameters, implicit TOPMODEL source, dt = 900 s, Newton max_iters = 3
+(experiments/benchmarks/soil.jl:47-73, src/simulations/Simulations.jl:127-135), FP64,
+synthetic fields.  One "step" = one implicit ARS111 stage of every column of
+the shard: update_implicit_cache! + 3 x (Jacobian, implicit tendency, residual, solve,
+update) = ONE fused kernel launch (clb_implicit_step).
+
+  value     column-steps/s with every input resident in HBM (library mirrors).
+  e2e       the same stage through the host-buffer C-ABI call (clb_implicit_step_host):
+            pinned host arrays in the reference layout, H2D of the per-step inputs, the
+            fused kernel, D2H of the new state, inside the timed region.
+  roofline  algorithmic bytes (2008 B per column-step) / kernel time against the
+            measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference: the CPU oracle (our C restatement of the reference path;
+            the reference itself is Julia and cannot run here) with OpenMP on the host cores.
+
+Multi-GPU: one process per GPU (torchrun), the columns are sharded, no data-path collective
+(columns are independent: rre.jl:106, utils.jl:183-188), weak scaling: every rank holds one
+~1 degree global domain.  Successive steps rotate over REPLICAS independent copies of the
+fields so the working set (REPLICAS x 123 MB) exceeds the 126 MB L2.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+NCOL = 61206
+NLEV = 15
+DT = 900.0
+MAX_ITERS = 3
+MODEL = "energy_hydrology"
+REPLICAS = 4
+METRIC = "column-steps/sec"
+UNIT = "column-steps/s"
+
+
+def workload_config(extra=None):
+    c = {"workload": f"EnergyHydrology soil-only ~1deg global ({NCOL} columns x {NLEV} levels per GPU), "
+                     f"van Genuchten per-cell params, TOPMODEL implicit source, dt={DT:.0f}s, Newton max_iters={MAX_ITERS}",
+         "columns_per_gpu": NCOL, "levels": NLEV, "dt_s": DT, "newton_iters": MAX_ITERS,
+         "l2_policy": f"steps rotate over {REPLICAS} independent field sets ({REPLICAS}x123 MB > 126 MB L2)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def make_inputs(seed):
+    import climaland_b200  # noqa: F401
+    from climaland_b200 import workloads
+    return workloads.make_workload(MODEL, NCOL, N=NLEV, seed=seed, topmodel=True)
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle on the host cores
+# --------------------------------------------------------------------------------------
+def run_oracle(steps, warmup, budget_s=None):
+    """Times the oracle's implicit stage on the full workload; returns (col-steps/s, ms/step, cores, n)."""
+    from helpers import oracle_problem
+    cores = os.cpu_count() or 1
+    w = make_inputs(0)
+    P, U, p = oracle_problem(w, nthreads=cores)
+    W = P.new_jacobian()
+    U0 = U.copy()
+
+    def one():
+        for k in ("theta_l", "rho_e_int", "theta_i", "intF_w", "intF_e"):
+            getattr(U, k)[...] = getattr(U0, k)
+        t = time.perf_counter()
+        P.implicit_step(U, DT, MAX_ITERS, p=p, W=W)
+        return time.perf_counter() - t
+
+    for _ in range(warmup):
+        one()
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        times.append(one())
+        if budget_s is not None and time.perf_counter() - t_start > budget_s:
+            break
+    ms = 1e3 * float(np.mean(times))
+    return NCOL / (ms * 1e-3), ms, cores, len(times)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, cores, n = run_oracle(args.steps, max(args.warmup, 1), budget_s=120.0)
+    sample = f"{n} steps of the full {NCOL}-column workload, OpenMP over columns"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is 100% Julia (no toolchain in the image): this arm times oracle/soil_oracle.c, "
+                    "our C restatement of the reference path, on the host cores"}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.window = index, [], False, [None, None]
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        nv = self.nv
+        while self.ok and not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                self.samples.append((time.perf_counter(), sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        nv = self.nv
+        t0, t1 = self.window
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1]
+        use = inside if len(inside) >= 3 else self.samples
+        bits = 0
+        for s in use:
+            bits |= s[2]
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        reasons = [k for k, v in names.items() if bits & v]
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.dev, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median([s[1] for s in use])), "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(use), "window": "timed region" if use is inside else "warm-up + timed region"}
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+PER_STEP_INPUTS = ("y_theta_l", "y_rho_e_int", "y_theta_i", "k_lag", "kappa_lag", "theta_l_lag", "is_saturated",
+                   "top_bc_w", "bot_bc_w", "top_bc_h", "bot_bc_h", "r_ss", "r_ess", "h_grad", "y_intf_w", "y_intf_e")
+PER_STEP_OUTPUTS = ("u_theta_l", "u_rho_e_int", "u_intf_w", "u_intf_e")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import climaland_b200 as cl
+    from climaland_b200 import workloads
+    from helpers import cuda_solver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    warmup = max(args.warmup, 3)
+    stream = torch.cuda.Stream()
+
+    # independent field sets (different seeds per rank and replica), resident in HBM
+    solvers, inputs = [], []
+    for r in range(REPLICAS):
+        w = make_inputs(seed=1000 * rank + r)
+        s = cuda_solver(w, device=local_rank, stream=stream.cuda_stream, out_of_place=True)
+        solvers.append(s)
+        inputs.append(w)
+
+    # the library's own communicator: used for the global balance sums (outside the timed region)
+    if world > 1:
+        uid = [cl.SoilColumnSolver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        solvers[0].comm_init(uid[0], world, rank)
+    balance0 = solvers[0].global_balance()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident throughput -------------------------------------------------
+    with torch.cuda.stream(stream):
+        for k in range(warmup):
+            solvers[k % REPLICAS].implicit_step(DT, MAX_ITERS)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.window[0] = time.perf_counter()
+        ev0.record(stream)
+        for k in range(args.steps):
+            solvers[k % REPLICAS].implicit_step(DT, MAX_ITERS)
+        ev1.record(stream)
+        barrier()
+        sampler.window[1] = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * NCOL / (ms_step * 1e-3)
+
+    # sanity: the stepped state is finite and the stage conserves water against the flux integral
+    st = solvers[0].implicit_step(DT, MAX_ITERS, want_stats=True)
+    assert st["nan_count"] == 0, "non-finite state after the timed steps"
+
+    # ---- end to end through the host-buffer call ------------------------------------------
+    def pinned(a):
+        tns = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        tns.numpy()[...] = a
+        return tns
+    e2e_sets = []
+    for w in inputs:
+        tin = {k: pinned(w[k]) for k in PER_STEP_INPUTS}
+        tout = {k: pinned(w[k.replace('u_', 'y_')]) for k in PER_STEP_OUTPUTS}
+        e2e_sets.append((tin, tout))
+    h2d = sum(v.numel() * 8 for v in e2e_sets[0][0].values())
+    d2h = sum(v.numel() * 8 for v in e2e_sets[0][1].values())
+
+    def e2e_step(k):
+        tin, tout = e2e_sets[k % REPLICAS]
+        solvers[k % REPLICAS].implicit_step_host(DT, MAX_ITERS, {a: b.numpy() for a, b in tin.items()},
+                                                 {a: b.numpy() for a, b in tout.items()})
+    with torch.cuda.stream(stream):
+        for k in range(3):
+            e2e_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(args.e2e_steps):
+            e2e_step(k)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+    ms_e2e = max(e0.elapsed_time(e1), wall * 1e3)  # the call synchronises: wall clock includes the host side
+    t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e_step = float(t.item()) / args.e2e_steps
+    e2e_value = world * NCOL / (ms_e2e_step * 1e-3)
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    balance1 = solvers[0].global_balance()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bytes_per_colstep = workloads.algorithmic_bytes(MODEL, NLEV, topmodel=True)
+        achieved = (value / world) * bytes_per_colstep / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config({"sypd_1deg_per_gpu": DT / (ms_step * 1e-3) / 365.0,
+                                       "kernel": "k_step_warp<vanGenuchten, fast, EnergyHydrology, 16 lanes/column> (one launch per step)",
+                                       "state": "out of place: Y (= temp) -> U, so every step does identical work"}),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e_step, "steps": args.e2e_steps,
+                    "api": "clb_implicit_step_host (pinned host buffers, reference layout)"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "bytes_per_column_step": bytes_per_colstep,
+                         "bytes_per_launch": bytes_per_colstep * NCOL, "peak_source": peak_src,
+                         "note": "FP64 pipe, not HBM, is expected to bind (DESIGN.md); frac is reported against HBM by contract"},
+            "clocks": sampler.summary(),
+            "balance": {"water_before": balance0[0], "water_after": balance1[0], "intF_w_after": balance1[1]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores, n = run_oracle(steps=1000, warmup=1, budget_s=12.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+                                    "sample": f"{n} steps of the full {NCOL}-column workload (oracle/soil_oracle.c, OpenMP over columns)"}
+        print(json.dumps(line))
+    for s in solvers:
+        s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,7 @@ class Config(C.Structure):
         ("stream", C.c_void_p), ("math_mode", C.c_int32), ("kernel_variant", C.c_int32),
         ("rho_l", C.c_double), ("rho_i", C.c_double), ("cp_l", C.c_double),
         ("cp_i", C.c_double), ("T_ref", C.c_double), ("LH_f0", C.c_double),
+        ("layout", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -83,7 +84,8 @@ def lib():
         "clb_set_field": [h, i32, C.c_void_p, i64, i64, i32],
         "clb_get_field": [h, i32, C.c_void_p, i64, i64, i32],
         "clb_fill_field": [h, i32, d],
-        "clb_field_device_ptr": [h, i32, C.POINTER(C.c_void_p), C.POINTER(i64)],
+        "clb_field_device_ptr": [h, i32, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(i64)],
+        "clb_set_option": [h, i32, i64],
         "clb_update_implicit_cache": [h], "clb_update_boundary_fluxes": [h],
         "clb_compute_imp_tendency": [h], "clb_compute_jacobian": [h, d], "clb_ldiv": [h],
         "clb_implicit_step": [h, d, i32, d, C.POINTER(Stats)],

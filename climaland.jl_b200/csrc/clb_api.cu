@@ -18,6 +18,7 @@
 #include "layout_kernels.cuh"
 #include "soil_fused.cuh"
 #include "soil_hooks.cuh"
+#include "soil_warp.cuh"
 
 namespace {
 
@@ -103,7 +104,10 @@ constexpr int kMaxLevels = 512;
 struct clb_handle_s {
     clb_config cfg;
     cudaStream_t stream = nullptr;
-    int64_t ld = 0;  // leading dimension of the mirrors (ncol rounded up to 32 doubles)
+    int64_t ld = 0;  // ncol rounded up to 32 doubles: length of per-column mirrors
+    int64_t sl = 0, sc = 0;    // strides of the per-cell mirrors: element (i, c) at i*sl + c*sc
+    size_t cell_elems = 0;     // allocation size of a per-cell mirror
+    bool out_of_place = false; // fused stage writes the U fields and leaves Y untouched
     double *field[CLB_F_NUM] = {};
     bool field_set[CLB_F_NUM] = {};
     // grid
@@ -146,7 +150,7 @@ struct DeviceGuard {
 int ensure_field(clb_handle h, int f)
 {
     if (h->field[f]) return CLB_OK;
-    const size_t n = is_cell_field(f) ? (size_t)h->cfg.n_levels * h->ld : (size_t)h->ld;
+    const size_t n = is_cell_field(f) ? h->cell_elems : (size_t)h->ld;
     CUDA_TRY(cudaMalloc(&h->field[f], n * sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(h->field[f], 0, n * sizeof(double), h->stream));
     return CLB_OK;
@@ -154,7 +158,7 @@ int ensure_field(clb_handle h, int f)
 
 int ensure_work(clb_handle h, int count)
 {
-    const size_t n = (size_t)h->cfg.n_levels * h->ld;
+    const size_t n = h->cell_elems;
     for (int w = 0; w < count; ++w)
         if (!h->work[w]) CUDA_TRY(cudaMalloc(&h->work[w], n * sizeof(double)));
     if (!h->carry) CUDA_TRY(cudaMalloc(&h->carry, 4 * (size_t)h->ld * sizeof(double)));
@@ -199,6 +203,7 @@ clb::DevView make_view(clb_handle h)
     P.model = c.model; P.closure = c.closure; P.top_bc = c.top_bc; P.bottom_bc = c.bottom_bc;
     P.topmodel = c.has_topmodel_source;
     P.N = c.n_levels; P.ncol = c.n_columns; P.ld = h->ld;
+    P.sl = h->sl; P.sc = h->sc;
     P.earth = {c.rho_l, c.rho_i, c.cp_l, c.cp_i, c.T_ref, c.LH_f0};
     const int N = c.n_levels;
     P.z_c = h->d_grid; P.dz_c = h->d_grid + N; P.inv_dz_c = h->d_grid + 2 * N; P.inv_dz_f = h->d_grid + 3 * N;
@@ -215,6 +220,12 @@ clb::DevView make_view(clb_handle h)
     P.theta_bc_top = F[CLB_F_THETA_BC_TOP]; P.theta_bc_bot = F[CLB_F_THETA_BC_BOT];
     P.Y_theta_l = F[CLB_F_Y_THETA_L]; P.Y_rho_e = F[CLB_F_Y_RHO_E_INT]; P.Y_theta_i = F[CLB_F_Y_THETA_I];
     P.Y_intF_w = F[CLB_F_Y_INTF_W]; P.Y_intF_e = F[CLB_F_Y_INTF_E];
+    if (h->out_of_place) {
+        P.out_theta_l = F[CLB_F_U_THETA_L]; P.out_rho_e = F[CLB_F_U_RHO_E_INT];
+        P.out_intF_w = F[CLB_F_U_INTF_W]; P.out_intF_e = F[CLB_F_U_INTF_E];
+    } else {
+        P.out_theta_l = P.Y_theta_l; P.out_rho_e = P.Y_rho_e; P.out_intF_w = P.Y_intF_w; P.out_intF_e = P.Y_intF_e;
+    }
     P.p_K = F[CLB_F_P_K]; P.p_psi = F[CLB_F_P_PSI]; P.p_T = F[CLB_F_P_T];
     P.top_bc_w = F[CLB_F_TOP_BC_W]; P.bot_bc_w = F[CLB_F_BOT_BC_W];
     P.top_bc_h = F[CLB_F_TOP_BC_H]; P.bot_bc_h = F[CLB_F_BOT_BC_H];
@@ -254,6 +265,15 @@ inline unsigned grid_for(int64_t ncol) { return (unsigned)((ncol + kBlock - 1) /
         else if (cl__ == 0 && ma__ == 1) KERNEL<0, 1, NS><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);   \
         else if (cl__ == 1 && ma__ == 0) KERNEL<1, 0, NS><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);   \
         else KERNEL<1, 1, NS><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);                               \
+    } while (0)
+
+#define DISPATCH_CMN2(h, KERNEL, A, B, grid, ...)                                                             \
+    do {                                                                                                      \
+        const int cl__ = (h)->cfg.closure, ma__ = (h)->cfg.math_mode;                                         \
+        if (cl__ == 0 && ma__ == 0) KERNEL<0, 0, A, B><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);         \
+        else if (cl__ == 0 && ma__ == 1) KERNEL<0, 1, A, B><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);    \
+        else if (cl__ == 1 && ma__ == 0) KERNEL<1, 0, A, B><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);    \
+        else KERNEL<1, 1, A, B><<<grid, kBlock, 0, (h)->stream>>>(__VA_ARGS__);                                \
     } while (0)
 
 template <int NS>
@@ -356,6 +376,10 @@ int clb_create(clb_handle *out, const clb_config *cfg)
         return fail(CLB_ERR_INVALID, "clb_create: unknown closure %d", cfg->closure);
     if (cfg->top_bc < 0 || cfg->top_bc > 1 || cfg->bottom_bc < 0 || cfg->bottom_bc > 2)
         return fail(CLB_ERR_INVALID, "clb_create: unknown boundary condition kind");
+    if (cfg->layout < CLB_LAYOUT_AUTO || cfg->layout > CLB_LAYOUT_LEVEL_FASTEST)
+        return fail(CLB_ERR_INVALID, "clb_create: unknown layout %d", cfg->layout);
+    if (cfg->kernel_variant < CLB_VARIANT_AUTO || cfg->kernel_variant > CLB_VARIANT_LANE_PER_CELL)
+        return fail(CLB_ERR_INVALID, "clb_create: unknown kernel_variant %d", cfg->kernel_variant);
     if (cfg->math_mode != CLB_MATH_FAST && cfg->math_mode != CLB_MATH_LIBM)
         return fail(CLB_ERR_INVALID, "clb_create: unknown math_mode %d", cfg->math_mode);
     if (cfg->n_levels < 2 || cfg->n_levels > kMaxLevels)
@@ -373,6 +397,17 @@ int clb_create(clb_handle *out, const clb_config *cfg)
     h->cfg = *cfg;
     h->stream = (cudaStream_t)cfg->stream;
     h->ld = (cfg->n_columns + 31) / 32 * 32;
+    int layout = cfg->layout;
+    if (layout == CLB_LAYOUT_AUTO) layout = (cfg->n_levels <= 32) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
+    h->cfg.layout = layout;
+    if (layout == CLB_LAYOUT_LEVEL_FASTEST) {
+        h->sl = 1;
+        h->sc = cfg->n_levels;
+    } else {
+        h->sl = h->ld;
+        h->sc = 1;
+    }
+    h->cell_elems = (size_t)cfg->n_levels * (size_t)h->ld;
     DeviceGuard guard(cfg->device);
     int rc = CLB_OK;
     auto init = [&]() -> int {
@@ -425,6 +460,18 @@ int clb_set_stream(clb_handle h, void *stream)
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->stream = (cudaStream_t)stream;
     return CLB_OK;
+}
+
+int clb_set_option(clb_handle h, int32_t option, int64_t value)
+{
+    TRY(check_handle(h));
+    switch (option) {
+    case CLB_OPT_OUT_OF_PLACE:
+        h->out_of_place = value != 0;
+        return CLB_OK;
+    default:
+        return fail(CLB_ERR_INVALID, "clb_set_option: unknown option %d", option);
+    }
 }
 
 int clb_set_grid(clb_handle h, const double *z_c, const double *z_f)
@@ -520,9 +567,9 @@ int clb_set_field(clb_handle h, int32_t field, const double *src, int64_t stride
         const unsigned grid = (unsigned)((ncol + clb::kTileCols - 1) / clb::kTileCols);
         const size_t smem = (size_t)N * (clb::kTileCols + 1) * sizeof(double);
         if (smem > 48 * 1024)
-            CUDA_TRY(cudaFuncSetAttribute(clb::k_gather_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        clb::k_gather_cells<<<grid, 256, smem, h->stream>>>(h->field[field], h->ld, dsrc, stride_level, stride_column,
-                                                            h->d_idx, N, ncol);
+            CUDA_TRY(cudaFuncSetAttribute(clb::k_relayout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        clb::k_relayout<<<grid, 256, smem, h->stream>>>(h->field[field], h->sl, h->sc, nullptr, dsrc, stride_level,
+                                                        stride_column, h->d_idx, N, ncol);
     } else {
         clb::k_gather_cols<<<(unsigned)((ncol + 255) / 256), 256, 0, h->stream>>>(h->field[field], dsrc, stride_column,
                                                                                   h->d_idx, ncol);
@@ -557,9 +604,9 @@ int clb_get_field(clb_handle h, int32_t field, double *dst, int64_t stride_level
         const unsigned grid = (unsigned)((ncol + clb::kTileCols - 1) / clb::kTileCols);
         const size_t smem = (size_t)N * (clb::kTileCols + 1) * sizeof(double);
         if (smem > 48 * 1024)
-            CUDA_TRY(cudaFuncSetAttribute(clb::k_scatter_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        clb::k_scatter_cells<<<grid, 256, smem, h->stream>>>(h->field[field], h->ld, ddst, stride_level, stride_column,
-                                                             h->d_idx, N, ncol);
+            CUDA_TRY(cudaFuncSetAttribute(clb::k_relayout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        clb::k_relayout<<<grid, 256, smem, h->stream>>>(ddst, stride_level, stride_column, h->d_idx, h->field[field],
+                                                        h->sl, h->sc, nullptr, N, ncol);
     } else {
         clb::k_scatter_cols<<<(unsigned)((ncol + 255) / 256), 256, 0, h->stream>>>(h->field[field], ddst,
                                                                                    stride_column, h->d_idx, ncol);
@@ -578,14 +625,14 @@ int clb_fill_field(clb_handle h, int32_t field, double value)
     if (!is_cell_field(field) && !is_col_field(field)) return fail(CLB_ERR_INVALID, "unknown field id %d", field);
     DeviceGuard guard(h->cfg.device);
     TRY(ensure_field(h, field));
-    const int64_t n = is_cell_field(field) ? (int64_t)h->cfg.n_levels * h->ld : h->ld;
+    const int64_t n = is_cell_field(field) ? (int64_t)h->cell_elems : h->ld;
     clb::k_fill<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->field[field], n, value);
     CUDA_TRY(cudaGetLastError());
     h->field_set[field] = true;
     return CLB_OK;
 }
 
-int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *ld)
+int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *stride_level, int64_t *stride_column)
 {
     TRY(check_handle(h));
     if (!is_cell_field(field) && !is_col_field(field)) return fail(CLB_ERR_INVALID, "unknown field id %d", field);
@@ -594,7 +641,8 @@ int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *ld)
     TRY(ensure_field(h, field));
     h->field_set[field] = true;  // the caller fills it in place
     *ptr = h->field[field];
-    if (ld) *ld = h->ld;
+    if (stride_level) *stride_level = is_cell_field(field) ? h->sl : 0;
+    if (stride_column) *stride_column = is_cell_field(field) ? h->sc : 1;
     return CLB_OK;
 }
 
@@ -704,18 +752,44 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
     const bool fixed = tol < 0.0;
     int variant = h->cfg.kernel_variant;
-    const bool have_static = (N == 15);
-    if (variant == CLB_VARIANT_AUTO) variant = (fixed && have_static) ? CLB_VARIANT_REGISTER_COLUMN : CLB_VARIANT_GENERIC;
-    if (variant == CLB_VARIANT_REGISTER_COLUMN && !(fixed && have_static))
-        return fail(CLB_ERR_INVALID, "clb_implicit_step: the register-column variant needs N == 15 and tol < 0");
+    const bool level_fast = h->cfg.layout == CLB_LAYOUT_LEVEL_FASTEST;
+    if (!fixed) {
+        variant = CLB_VARIANT_GENERIC;  // the tolerance path is one generic launch per iteration
+    } else if (variant == CLB_VARIANT_AUTO) {
+        if (level_fast && N <= 32)
+            variant = CLB_VARIANT_LANE_PER_CELL;
+        else if (N == 15)
+            variant = CLB_VARIANT_REGISTER_COLUMN;
+        else
+            variant = CLB_VARIANT_GENERIC;
+    }
+    if (variant == CLB_VARIANT_REGISTER_COLUMN && N != 15)
+        return fail(CLB_ERR_INVALID, "clb_implicit_step: the register-column variant is built for N == 15");
+    if (variant == CLB_VARIANT_LANE_PER_CELL && N > 32)
+        return fail(CLB_ERR_INVALID, "clb_implicit_step: the lane-per-cell variant needs N <= 32");
     if (variant == CLB_VARIANT_GENERIC) TRY(ensure_work(h, eh ? 6 : 3));
+    if (h->out_of_place) {
+        TRY(alloc_fields(h, {CLB_F_U_THETA_L, CLB_F_U_INTF_W}));
+        if (eh) TRY(alloc_fields(h, {CLB_F_U_RHO_E_INT, CLB_F_U_INTF_E}));
+    }
     CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(double), h->stream));
     clb::DevView P = make_view(h);
     const unsigned grid = grid_for(P.ncol);
     nvtxRangePushA("implicit_step!");
     int iters_done = max_iters;
     if (fixed) {
-        if (variant == CLB_VARIANT_REGISTER_COLUMN) {
+        if (variant == CLB_VARIANT_LANE_PER_CELL) {
+            const int cpw = (N <= 16) ? 2 : 1;  // columns per warp
+            const int64_t warps = (P.ncol + cpw - 1) / cpw;
+            const unsigned wgrid = (unsigned)((warps * 32 + kBlock - 1) / kBlock);
+            if (N <= 16) {
+                if (eh) DISPATCH_CMN2(h, clb::k_step_warp, 1, 16, wgrid, P, dtgamma, max_iters);
+                else DISPATCH_CMN2(h, clb::k_step_warp, 0, 16, wgrid, P, dtgamma, max_iters);
+            } else {
+                if (eh) DISPATCH_CMN2(h, clb::k_step_warp, 1, 32, wgrid, P, dtgamma, max_iters);
+                else DISPATCH_CMN2(h, clb::k_step_warp, 0, 32, wgrid, P, dtgamma, max_iters);
+            }
+        } else if (variant == CLB_VARIANT_REGISTER_COLUMN) {
             const clb::GridConst<15> gc = make_grid_const<15>(h);
             if (eh)
                 DISPATCH_CMN(h, clb::k_eh_step_reg, 15, grid, P, gc, dtgamma, max_iters);

@@ -9,12 +9,16 @@ namespace clb {
 constexpr int kMaxStaticLevels = 64;  // grid vectors of the register-column kernels travel as kernel parameters
 
 // Everything a kernel reads or writes.  Per-cell arrays: element (level i,
-// column c) at base[i*ld + c]; per-column arrays: base[c].  Pointers of fields
-// the configured model does not use are null.
+// column c) at base[i*sl + c*sc]; per-column arrays: base[c].  Two mirror layouts:
+//   column-fastest  sl = ld (ncol rounded up to 32), sc = 1   -- thread-per-column kernels
+//   level-fastest   sl = 1, sc = N (the reference's own layout) -- lane-per-cell kernels
+// Pointers of fields the configured model does not use are null.
 struct DevView {
     int32_t model, closure, top_bc, bottom_bc, topmodel;
     int32_t N;
     int64_t ncol, ld;
+    int64_t sl, sc;
+    __device__ __forceinline__ int64_t at(int i, int64_t c) const { return (int64_t)i * sl + c * sc; }
     EarthConst earth;
     // grid (device arrays, length N; inv_dz_f[i] belongs to the face between cells i-1 and i, i = 1..N-1)
     const double *z_c, *dz_c, *inv_dz_c, *inv_dz_f;
@@ -25,6 +29,8 @@ struct DevView {
     const double *R_ss, *R_ess, *h_grad, *theta_bc_top, *theta_bc_bot;
     // state, cache, tendency
     double *Y_theta_l, *Y_rho_e, *Y_theta_i, *Y_intF_w, *Y_intF_e;
+    // where the fused stage writes the new state: the Y fields (in place) or the U fields (out of place)
+    double *out_theta_l, *out_rho_e, *out_intF_w, *out_intF_e;
     double *p_K, *p_psi, *p_T;
     double *top_bc_w, *bot_bc_w, *top_bc_h, *bot_bc_h, *dfluxBCdY, *total_water;
     double *dY_theta_l, *dY_rho_e, *dY_theta_i, *dY_intF_w, *dY_intF_e;

@@ -24,7 +24,7 @@ struct RegCol {  // registers; requires fully unrolled level loops
     __device__ __forceinline__ double get(int i) const { return v[i]; }
     __device__ __forceinline__ void set(int i, double x) { v[i] = x; }
 };
-struct MemCol {  // column-fastest global scratch
+struct MemCol {  // global scratch with the mirrors' level stride
     double *p;
     int64_t ld;
     __device__ __forceinline__ double get(int i) const { return p[(int64_t)i * ld]; }
@@ -76,7 +76,7 @@ __device__ __forceinline__ double richards_newton_iteration(const DevView &P, co
         src_w = R_ss / fmax(P.h_grad[c], kEps);
     }
     // level 0
-    HydroCell cell = load_cell(P, c);
+    HydroCell cell = load_cell(P, P.at(0, c));
     double K0, psi0, d0;
     closure_eval<CLOSURE, MATH, true, true, true>(cell, U.get(0), cell.nu, K0, psi0, d0);
     if (bc_live) {
@@ -89,10 +89,10 @@ __device__ __forceinline__ double richards_newton_iteration(const DevView &P, co
     double cprev = 0.0, dprev = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const int64_t k = (int64_t)i * P.ld + c;
+        const int64_t k = P.at(i, c);
         double a_hi = 0.0, q_hi, K1 = 0.0, psi1 = 0.0, d1 = 0.0, top_dflux = 0.0;
         if (i < N - 1) {
-            cell = load_cell(P, k + P.ld);
+            cell = load_cell(P, k + P.sl);
             closure_eval<CLOSURE, MATH, true, true, true>(cell, U.get(i + 1), cell.nu, K1, psi1, d1);
             a_hi = ((K0 + K1) / 2.0) * G.idzf(i + 1);
             q_hi = -a_hi * ((psi1 + G.z(i + 1)) - (psi0 + G.z(i)));
@@ -145,10 +145,10 @@ __device__ __forceinline__ void richards_bc_constants(const DevView &P, int64_t 
     psi_bc_top = 0.0;
     psi_bc_bot = 0.0;
     if (P.top_bc == 1) {  // state BC values do not depend on the iterate: once per stage
-        const HydroCell ct = load_cell(P, (int64_t)(P.N - 1) * P.ld + c);
+        const HydroCell ct = load_cell(P, P.at(P.N - 1, c));
         psi_bc_top = pressure_head<CLOSURE, MATH>(ct, P.theta_bc_top[c], ct.nu);
         if (P.bottom_bc == 2) {
-            const HydroCell cb = load_cell(P, c);
+            const HydroCell cb = load_cell(P, P.at(0, c));
             psi_bc_bot = pressure_head<CLOSURE, MATH>(cb, P.theta_bc_bot[c], cb.nu);
         }
     }
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128) k_richards_step_reg(const DevView P, cons
         const GridS<NS> G{gc};
         RegCol<NS> U, cp, dp;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) U.set(i, P.Y_theta_l[(int64_t)i * P.ld + c]);
+        for (int i = 0; i < NS; ++i) U.set(i, P.Y_theta_l[P.at(i, c)]);
         double top_w = P.top_bc_w[c], bot_w = P.bot_bc_w[c];
         const double temp_int = P.Y_intF_w[c];
         double Uint = temp_int;
@@ -179,10 +179,10 @@ __global__ void __launch_bounds__(128) k_richards_step_reg(const DevView P, cons
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const double u = U.get(i);
-            P.Y_theta_l[(int64_t)i * P.ld + c] = u;
+            P.out_theta_l[P.at(i, c)] = u;
             if (!isfinite(u)) bad += 1.0;
         }
-        P.Y_intF_w[c] = Uint;
+        P.out_intF_w[c] = Uint;
         if (P.top_bc == 1) {  // the cache keeps the last evaluated boundary fluxes
             P.top_bc_w[c] = top_w;
             P.bot_bc_w[c] = bot_w;
@@ -205,12 +205,13 @@ __global__ void __launch_bounds__(128) k_richards_step_generic(const DevView P, 
     if (live) {
         const GridR G{P.z_c, P.inv_dz_c, P.inv_dz_f};
         const int N = P.N;
-        MemCol U{P.work[0] + c, P.ld}, cp{P.work[1] + c, P.ld}, dp{P.work[2] + c, P.ld};
+        const int64_t o = P.at(0, c);
+        MemCol U{P.work[0] + o, P.sl}, cp{P.work[1] + o, P.sl}, dp{P.work[2] + o, P.sl};
         double *carry = P.carry + c;  // per-column scalars carried between launches
         double top_w, bot_w, Uint;
         const double temp_int = P.Y_intF_w[c];
         if (iter_begin == 0) {
-            for (int i = 0; i < N; ++i) U.set(i, P.Y_theta_l[(int64_t)i * P.ld + c]);
+            for (int i = 0; i < N; ++i) U.set(i, P.Y_theta_l[P.at(i, c)]);
             top_w = P.top_bc_w[c];
             bot_w = P.bot_bc_w[c];
             Uint = temp_int;
@@ -239,26 +240,26 @@ __global__ void __launch_bounds__(128) k_commit_state(const DevView P)
     if (c < P.ncol) {
         const bool eh = (P.model == 1);
         for (int i = 0; i < P.N; ++i) {
-            const int64_t k = (int64_t)i * P.ld + c;
+            const int64_t k = P.at(i, c);
             const double u = P.work[0][k];
-            P.Y_theta_l[k] = u;
+            P.out_theta_l[k] = u;
             if (!isfinite(u)) bad += 1.0;
             if (eh) {
                 const double e = P.work[1][k];
-                P.Y_rho_e[k] = e;
+                P.out_rho_e[k] = e;
                 if (!isfinite(e)) bad += 1.0;
             }
         }
         const double *carry = P.carry + c;
         if (!eh) {
-            P.Y_intF_w[c] = carry[2 * P.ld];
+            P.out_intF_w[c] = carry[2 * P.ld];
             if (P.top_bc == 1) {
                 P.top_bc_w[c] = carry[0];
                 P.bot_bc_w[c] = carry[P.ld];
             }
         } else {
-            P.Y_intF_w[c] = carry[0];
-            P.Y_intF_e[c] = carry[P.ld];
+            P.out_intF_w[c] = carry[0];
+            P.out_intF_e[c] = carry[P.ld];
         }
     }
     accumulate_stats(P, 0.0, bad);
@@ -289,7 +290,7 @@ __device__ __forceinline__ double eh_newton_iteration(const DevView &P, const Gr
     }
     // ---- sweep 1: water rows + residuals, Thomas forward on W11; energy residual stored
     auto level = [&](int i, double &psi, double &dps, double &T, double &K, double &kap) {
-        const int64_t k = (int64_t)i * P.ld + c;
+        const int64_t k = P.at(i, c);
         const HydroCell cell = load_cell(P, k);
         const double theta_i = P.Y_theta_i[k];
         const double theta = U1.get(i);
@@ -306,7 +307,7 @@ __device__ __forceinline__ double eh_newton_iteration(const DevView &P, const Gr
     double cprev = 0.0, dprev = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const int64_t k = (int64_t)i * P.ld + c;
+        const int64_t k = P.at(i, c);
         double psi1 = 0, d1 = 0, T1 = 0, K1 = 0, kap1 = 0, eK1 = 0;
         double aK_hi = 0.0, qw_hi, qe_hi;
         if (i < N - 1) {
@@ -357,7 +358,7 @@ __device__ __forceinline__ double eh_newton_iteration(const DevView &P, const Gr
     }
     // ---- sweep 2: b2' = f2 - W21 x1, rows of W22, Thomas forward (c' -> cp, d' -> F2)
     auto level2 = [&](int i, double &eK, double &kap, double &rc) {
-        const int64_t k = (int64_t)i * P.ld + c;
+        const int64_t k = P.at(i, c);
         const double theta_i = P.Y_theta_i[k];
         const double nu = __ldg(P.nu + k), rcds = __ldg(P.rho_c_ds + k);
         const double T = eh_temperature(U1.get(i), U2.get(i), theta_i, nu, rcds, E);
@@ -432,8 +433,8 @@ __global__ void __launch_bounds__(128) k_eh_step_reg(const DevView P, const Grid
         RegCol<NS> U1, U2, cp, dp, D, F2;
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            U1.set(i, P.Y_theta_l[(int64_t)i * P.ld + c]);
-            U2.set(i, P.Y_rho_e[(int64_t)i * P.ld + c]);
+            U1.set(i, P.Y_theta_l[P.at(i, c)]);
+            U2.set(i, P.Y_rho_e[P.at(i, c)]);
         }
         const double tw = P.Y_intF_w[c], te = P.Y_intF_e[c];
         double Uw = tw, Ue = te;
@@ -443,13 +444,13 @@ __global__ void __launch_bounds__(128) k_eh_step_reg(const DevView P, const Grid
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const double a = U1.get(i), b = U2.get(i);
-            P.Y_theta_l[(int64_t)i * P.ld + c] = a;
-            P.Y_rho_e[(int64_t)i * P.ld + c] = b;
+            P.out_theta_l[P.at(i, c)] = a;
+            P.out_rho_e[P.at(i, c)] = b;
             if (!isfinite(a)) bad += 1.0;
             if (!isfinite(b)) bad += 1.0;
         }
-        P.Y_intF_w[c] = Uw;
-        P.Y_intF_e[c] = Ue;
+        P.out_intF_w[c] = Uw;
+        P.out_intF_e[c] = Ue;
     }
     accumulate_stats(P, dx2, bad);
 }
@@ -463,15 +464,16 @@ __global__ void __launch_bounds__(128) k_eh_step_generic(const DevView P, double
     if (live) {
         const GridR G{P.z_c, P.inv_dz_c, P.inv_dz_f};
         const int N = P.N;
-        MemCol U1{P.work[0] + c, P.ld}, U2{P.work[1] + c, P.ld}, cp{P.work[2] + c, P.ld}, dp{P.work[3] + c, P.ld};
-        MemCol D{P.work[4] + c, P.ld}, F2{P.work[5] + c, P.ld};
+        const int64_t o = P.at(0, c);
+        MemCol U1{P.work[0] + o, P.sl}, U2{P.work[1] + o, P.sl}, cp{P.work[2] + o, P.sl}, dp{P.work[3] + o, P.sl};
+        MemCol D{P.work[4] + o, P.sl}, F2{P.work[5] + o, P.sl};
         double *carry = P.carry + c;
         const double tw = P.Y_intF_w[c], te = P.Y_intF_e[c];
         double Uw, Ue;
         if (iter_begin == 0) {
             for (int i = 0; i < N; ++i) {
-                U1.set(i, P.Y_theta_l[(int64_t)i * P.ld + c]);
-                U2.set(i, P.Y_rho_e[(int64_t)i * P.ld + c]);
+                U1.set(i, P.Y_theta_l[P.at(i, c)]);
+                U2.set(i, P.Y_rho_e[P.at(i, c)]);
             }
             Uw = tw;
             Ue = te;

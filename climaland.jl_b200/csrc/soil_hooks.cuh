@@ -17,7 +17,7 @@ __device__ __forceinline__ void column_boundary_fluxes(const DevView &P, int64_t
 {
     const int N = P.N;
     if (P.top_bc == 1 /*MoistureStateBC*/) {
-        const int64_t k = (int64_t)(N - 1) * P.ld + c;
+        const int64_t k = P.at(N - 1, c);
         const HydroCell cell = load_cell(P, k);
         const double dz = P.dz_top;
         // boundary_flux! evaluates psi_bc with nu (not nu - theta_i) for either model
@@ -29,7 +29,7 @@ __device__ __forceinline__ void column_boundary_fluxes(const DevView &P, int64_t
     if (P.bottom_bc == 1 /*FreeDrainage*/) {
         P.bot_bc_w[c] = -1 * K_bot;
     } else if (P.bottom_bc == 2 /*MoistureStateBC*/) {
-        const HydroCell cell = load_cell(P, c);
+        const HydroCell cell = load_cell(P, P.at(0, c));
         const double dz = P.dz_bot;
         const double psi_bc = pressure_head<CLOSURE, MATH>(cell, P.theta_bc_bot[c], cell.nu);
         P.bot_bc_w[c] = -K_bot * ((psi_bot + dz) - psi_bc) / dz;
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) k_update_implicit_cache(const DevView P)
     if (P.model == 0) {
         double tw = 0.0, K_bot = 0.0, psi_bot = 0.0, K = 0.0, psi = 0.0, theta = 0.0;
         for (int i = 0; i < N; ++i) {
-            const int64_t k = (int64_t)i * P.ld + c;
+            const int64_t k = P.at(i, c);
             const HydroCell cell = load_cell(P, k);
             theta = P.Y_theta_l[k];
             double d;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) k_update_implicit_cache(const DevView P)
         if (P.top_bc == 1) column_boundary_fluxes<CLOSURE, MATH>(P, c, K_bot, psi_bot, K, psi, theta);
     } else {
         for (int i = 0; i < N; ++i) {
-            const int64_t k = (int64_t)i * P.ld + c;
+            const int64_t k = P.at(i, c);
             const HydroCell cell = load_cell(P, k);
             const double theta_i = P.Y_theta_i[k];
             const double theta = P.Y_theta_l[k];
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(128) k_update_boundary_fluxes(const DevView P)
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.ncol) return;
     const double *K = (P.model == 1) ? P.K_lag : P.p_K;
-    const int64_t kt = (int64_t)(P.N - 1) * P.ld + c;
-    column_boundary_fluxes<CLOSURE, MATH>(P, c, K[c], P.p_psi[c], K[kt], P.p_psi[kt], P.Y_theta_l[kt]);
+    const int64_t kb = P.at(0, c), kt = P.at(P.N - 1, c);
+    column_boundary_fluxes<CLOSURE, MATH>(P, c, K[kb], P.p_psi[kb], K[kt], P.p_psi[kt], P.Y_theta_l[kt]);
 }
 
 // compute_imp_tendency!: rre.jl:161-203, energy_hydrology.jl:363-425.
@@ -118,20 +118,21 @@ __global__ void __launch_bounds__(128) k_imp_tendency(const DevView P)
     P.dY_intF_w[c] = dintw;
     if (eh) P.dY_intF_e[c] = dinte;
 
-    double K0 = Kf[c], h0 = P.p_psi[c] + P.z_c[0];
+    const int64_t k00 = P.at(0, c);
+    double K0 = Kf[k00], h0 = P.p_psi[k00] + P.z_c[0];
     double T0 = 0.0, eK0 = 0.0, kap0 = 0.0;
     if (eh) {
-        T0 = P.p_T[c];
+        T0 = P.p_T[k00];
         eK0 = volumetric_internal_energy_liq(T0, P.earth) * K0;
-        kap0 = P.kappa_lag[c];
+        kap0 = P.kappa_lag[k00];
     }
     double qw_lo = bot_w, qe_lo = bot_h;
     for (int i = 0; i < N; ++i) {
-        const int64_t k = (int64_t)i * P.ld + c;
+        const int64_t k = P.at(i, c);
         double qw_hi, qe_hi = 0.0;
         double K1 = 0, h1 = 0, T1 = 0, eK1 = 0, kap1 = 0;
         if (i < N - 1) {
-            const int64_t k1 = k + P.ld;
+            const int64_t k1 = k + P.sl;
             const double idzf = P.inv_dz_f[i + 1];
             K1 = Kf[k1];
             h1 = P.p_psi[k1] + P.z_c[i + 1];
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const DevView P, double dtg)
     double rc_m = 0, rc_0 = 0, rc_p = 0;      // 1 / rho_c_s(lagged theta_l, theta_i)
 
     auto level = [&](int i, double &dps, double &K, double &eK, double &kp, double &rc) {
-        const int64_t k = (int64_t)i * P.ld + c;
+        const int64_t k = P.at(i, c);
         const HydroCell cell = load_cell(P, k);
         const double theta_i = eh ? P.Y_theta_i[k] : 0.0;
         dps = dpsidtheta<CLOSURE, MATH>(cell, P.Y_theta_l[k], eh ? cell.nu - theta_i : cell.nu);
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const DevView P, double dtg)
     level(0, dps_0, K_0, eK_0, kp_0, rc_0);
     double aK_lo = 0, aE_lo = 0, aC_lo = 0;
     for (int i = 0; i < N; ++i) {
-        const int64_t k = (int64_t)i * P.ld + c;
+        const int64_t k = P.at(i, c);
         double aK_hi = 0, aE_hi = 0, aC_hi = 0;
         if (i < N - 1) {
             level(i + 1, dps_p, K_p, eK_p, kp_p, rc_p);
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(128) k_jacobian(const DevView P, double dtg)
 }
 
 // Thomas sweep in the normalised (c', d') form; x doubles as d'.
-__device__ __forceinline__ void thomas_column(int N, int64_t ld, const double *lo, const double *di, const double *up,
+__device__ __forceinline__ void thomas_column(int N, int64_t ld /* level stride */, const double *lo, const double *di, const double *up,
                                               const double *b, double *x, double *cp)
 {
     double den = 1.0 / di[0];
@@ -279,23 +280,23 @@ __global__ void __launch_bounds__(128) k_ldiv(const DevView P)
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.ncol) return;
     const int N = P.N;
-    const int64_t ld = P.ld;
-    double *cp = P.work[0] + c;
-    thomas_column(N, ld, P.w11_lo + c, P.w11_di + c, P.w11_up + c, P.b_theta_l + c, P.x_theta_l + c, cp);
+    const int64_t ld = P.sl, o = P.at(0, c);
+    double *cp = P.work[0] + o;
+    thomas_column(N, ld, P.w11_lo + o, P.w11_di + o, P.w11_up + o, P.b_theta_l + o, P.x_theta_l + o, cp);
     P.x_intF_w[c] = -P.b_intF_w[c];
     if (P.model == 1) {
-        double *b2 = P.work[1] + c;
-        const double *x1 = P.x_theta_l + c;
+        double *b2 = P.work[1] + o;
+        const double *x1 = P.x_theta_l + o;
         for (int i = 0; i < N; ++i) {
             const int64_t k = (int64_t)i * ld;
-            double s = P.w21_di[k + c] * x1[k];
-            if (i > 0) s = P.w21_lo[k + c] * x1[k - ld] + s;
-            if (i < N - 1) s = s + P.w21_up[k + c] * x1[k + ld];
-            b2[k] = P.b_rho_e[k + c] - s;
+            double s = P.w21_di[k + o] * x1[k];
+            if (i > 0) s = P.w21_lo[k + o] * x1[k - ld] + s;
+            if (i < N - 1) s = s + P.w21_up[k + o] * x1[k + ld];
+            b2[k] = P.b_rho_e[k + o] - s;
         }
-        thomas_column(N, ld, P.w22_lo + c, P.w22_di + c, P.w22_up + c, b2, P.x_rho_e + c, cp);
+        thomas_column(N, ld, P.w22_lo + o, P.w22_di + o, P.w22_up + o, b2, P.x_rho_e + o, cp);
         for (int i = 0; i < N; ++i) {
-            const int64_t k = (int64_t)i * ld + c;
+            const int64_t k = P.at(i, c);
             P.x_theta_i[k] = -P.b_theta_i[k];
         }
         P.x_intF_e[c] = -P.b_intF_e[c];
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(128) k_column_integral(const DevView P, const 
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.ncol) return;
     double s = 0.0;
-    for (int i = 0; i < P.N; ++i) s += field[(int64_t)i * P.ld + c] * P.dz_c[i];
+    for (int i = 0; i < P.N; ++i) s += field[P.at(i, c)] * P.dz_c[i];
     out[c] = s;
 }
 

@@ -22,8 +22,10 @@ TOP_FLUX, TOP_MOISTURE_STATE = K["CLB_TOP_FLUX"], K["CLB_TOP_MOISTURE_STATE"]
 BOT_FLUX, BOT_FREE_DRAINAGE, BOT_MOISTURE_STATE = (K["CLB_BOT_FLUX"], K["CLB_BOT_FREE_DRAINAGE"],
                                                    K["CLB_BOT_MOISTURE_STATE"])
 MATH_FAST, MATH_LIBM = K["CLB_MATH_FAST"], K["CLB_MATH_LIBM"]
-VARIANT_AUTO, VARIANT_REGISTER_COLUMN, VARIANT_GENERIC = (K["CLB_VARIANT_AUTO"], K["CLB_VARIANT_REGISTER_COLUMN"],
-                                                          K["CLB_VARIANT_GENERIC"])
+VARIANT_AUTO, VARIANT_REGISTER_COLUMN, VARIANT_GENERIC, VARIANT_LANE_PER_CELL = (
+    K["CLB_VARIANT_AUTO"], K["CLB_VARIANT_REGISTER_COLUMN"], K["CLB_VARIANT_GENERIC"], K["CLB_VARIANT_LANE_PER_CELL"])
+LAYOUT_AUTO, LAYOUT_COLUMN_FASTEST, LAYOUT_LEVEL_FASTEST = (K["CLB_LAYOUT_AUTO"], K["CLB_LAYOUT_COLUMN_FASTEST"],
+                                                            K["CLB_LAYOUT_LEVEL_FASTEST"])
 
 FIELDS = {k[len("CLB_F_"):].lower(): v for k, v in K.items()
           if k.startswith("CLB_F_") and k not in ("CLB_F_NUM", "CLB_F_NUM_CELL")}
@@ -44,7 +46,8 @@ def _is_torch(a):
 class SoilColumnSolver:
     def __init__(self, *, model, n_columns, z_f, z_c=None, closure=VAN_GENUCHTEN, top_bc=TOP_FLUX,
                  bottom_bc=BOT_FLUX, has_topmodel_source=False, device=0, stream=None, math_mode=MATH_FAST,
-                 kernel_variant=VARIANT_AUTO, earth=None, active_columns=None, n_columns_total=None):
+                 kernel_variant=VARIANT_AUTO, layout=LAYOUT_AUTO, earth=None, active_columns=None,
+                 n_columns_total=None, out_of_place=False):
         self.L = _lib.lib()
         z_f = np.ascontiguousarray(z_f, dtype=np.float64)
         self.N = int(z_f.size - 1)
@@ -57,11 +60,13 @@ class SoilColumnSolver:
         cfg = Config(abi_version=K["CLB_ABI_VERSION"], model=model, closure=closure, top_bc=top_bc,
                      bottom_bc=bottom_bc, has_topmodel_source=int(bool(has_topmodel_source)), n_levels=self.N,
                      device=int(device), n_columns=self.ncol, stream=stream, math_mode=math_mode,
-                     kernel_variant=kernel_variant, **e)
+                     kernel_variant=kernel_variant, layout=layout, **e)
         self.cfg = cfg
         self.h = C.c_void_p()
         check(self.L.clb_create(C.byref(self.h), C.byref(cfg)))
         check(self.L.clb_set_grid(self.h, z_c.ctypes.data_as(_lib._dp), z_f.ctypes.data_as(_lib._dp)))
+        if out_of_place:
+            check(self.L.clb_set_option(self.h, K["CLB_OPT_OUT_OF_PLACE"], 1))
         if active_columns is not None:
             idx = np.ascontiguousarray(active_columns, dtype=np.int64)
             check(self.L.clb_set_active_columns(self.h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
@@ -121,9 +126,9 @@ class SoilColumnSolver:
         return out
 
     def device_ptr(self, name):
-        p, ld = C.c_void_p(), C.c_int64()
-        check(self.L.clb_field_device_ptr(self.h, field_id(name), C.byref(p), C.byref(ld)))
-        return p.value, ld.value
+        p, sl, sc = C.c_void_p(), C.c_int64(), C.c_int64()
+        check(self.L.clb_field_device_ptr(self.h, field_id(name), C.byref(p), C.byref(sl), C.byref(sc)))
+        return p.value, sl.value, sc.value
 
     # ---- hooks ---------------------------------------------------------------
     def update_implicit_cache(self):

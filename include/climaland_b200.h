@@ -74,7 +74,16 @@ enum { CLB_HOST = 0, CLB_DEVICE = 1 };
  * expressions literally with CUDA libm. */
 enum { CLB_MATH_FAST = 0, CLB_MATH_LIBM = 1 };
 /* kernel variant of the fused step (0 = let the library choose) */
-enum { CLB_VARIANT_AUTO = 0, CLB_VARIANT_REGISTER_COLUMN = 1, CLB_VARIANT_GENERIC = 2 };
+enum { CLB_VARIANT_AUTO = 0,
+       CLB_VARIANT_REGISTER_COLUMN = 1, /* one thread per column, N = 15 in registers          */
+       CLB_VARIANT_GENERIC = 2,         /* one thread per column, any N, scratch in HBM/L2      */
+       CLB_VARIANT_LANE_PER_CELL = 3    /* one lane per cell, shuffle stencil + cyclic reduction, N <= 32 */ };
+/* layout of the library's per-cell mirrors (0 = let the library choose) */
+enum { CLB_LAYOUT_AUTO = 0,
+       CLB_LAYOUT_COLUMN_FASTEST = 1,   /* element (i, c) at i*ld + c                              */
+       CLB_LAYOUT_LEVEL_FASTEST = 2     /* element (i, c) at c*N + i: the reference's own layout    */ };
+/* clb_set_option */
+enum { CLB_OPT_OUT_OF_PLACE = 1 };      /* fused stage reads Y (= temp) and writes the U fields */
 
 /* Field ids.  "cell" fields are N x ncol, "col" fields are ncol. */
 typedef enum {
@@ -101,6 +110,8 @@ typedef enum {
     /* ---- linear solve right-hand side b and solution x -- cell */
     CLB_F_B_THETA_L, CLB_F_B_RHO_E_INT, CLB_F_B_THETA_I,
     CLB_F_X_THETA_L, CLB_F_X_RHO_E_INT, CLB_F_X_THETA_I,
+    /* ---- new state of the fused stage in out-of-place mode -- cell */
+    CLB_F_U_THETA_L, CLB_F_U_RHO_E_INT,
     CLB_F_NUM_CELL,
     /* ---- per-column fields */
     CLB_F_R_SS = CLB_F_NUM_CELL, CLB_F_R_ESS, CLB_F_H_GRAD,     /* lagged TOPMODEL */
@@ -111,6 +122,7 @@ typedef enum {
     CLB_F_DY_INTF_W, CLB_F_DY_INTF_E,
     CLB_F_B_INTF_W, CLB_F_B_INTF_E, CLB_F_X_INTF_W, CLB_F_X_INTF_E,
     CLB_F_AREA_WEIGHT,                        /* weights of the global balance sums */
+    CLB_F_U_INTF_W, CLB_F_U_INTF_E,           /* out-of-place new flux integrals */
     CLB_F_NUM
 } clb_field;
 
@@ -128,6 +140,8 @@ typedef struct {
     int32_t kernel_variant;       /* CLB_VARIANT_* */
     /* LandParameters constants (src/shared_utilities/Parameters.jl:11-58) */
     double rho_l, rho_i, cp_l, cp_i, T_ref, LH_f0;
+    int32_t layout;               /* CLB_LAYOUT_* */
+    int32_t reserved;
 } clb_config;
 
 typedef struct {
@@ -149,6 +163,9 @@ int clb_destroy(clb_handle h);
 int clb_sync(clb_handle h);
 /* Switch the stream later calls are enqueued on (CUDA.jl task-local stream). */
 int clb_set_stream(clb_handle h, void *stream);
+/* CLB_OPT_OUT_OF_PLACE: clb_implicit_step keeps Y (ClimaTimeSteppers' `temp`) and
+ * writes the new stage value into the CLB_F_U_* fields. */
+int clb_set_option(clb_handle h, int32_t option, int64_t value);
 
 /* ---- geometry and masks -------------------------------------------------- */
 /* Cell centres z_c[N] and faces z_f[N+1] (host pointers) as ClimaCore produced
@@ -171,9 +188,10 @@ int clb_get_field(clb_handle h, int32_t field, double *dst, int64_t stride_level
                   int64_t stride_column, int32_t mem);
 /* Broadcast a scalar parameter (the reference accepts scalars or fields). */
 int clb_fill_field(clb_handle h, int32_t field, double value);
-/* Device pointer and leading dimension of the library mirror of a field, for
- * callers that want to fill it in place (resident-SoA mode). */
-int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *ld);
+/* Device pointer and strides of the library mirror of a field, for callers that
+ * want to fill it in place (resident mode). */
+int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *stride_level,
+                         int64_t *stride_column);
 
 /* ---- the hooks, fine-grained (parity-checkable per call) ----------------- */
 /* update_implicit_cache!(p, Y, t): models.jl:238-246.  Richards: K, psi,

@@ -21,7 +21,15 @@ CASES = [
     ("energy_hydrology", 0, 0, 0, False, 15, 300, 900.0, 1),
     ("energy_hydrology", 1, 0, 0, True, 15, 100, 900.0, 3),
     ("energy_hydrology", 0, 0, 0, True, 50, 100, 900.0, 3),
+    ("richards", 0, 1, 1, True, 24, 77, 1800.0, 2),
+    ("energy_hydrology", 0, 0, 0, True, 30, 90, 900.0, 3),
+    ("energy_hydrology", 1, 0, 0, False, 9, 45, 900.0, 2),
 ]
+
+# (kernel_variant, layout): lane-per-cell on level-fastest mirrors, register-column and generic on
+# column-fastest mirrors, generic on level-fastest mirrors
+VARIANTS = {"lane_per_cell": (3, 2), "register_column": (1, 1), "generic_cf": (2, 1), "generic_lf": (2, 2),
+            "auto": (0, 0)}
 
 
 def _setup(case):
@@ -49,14 +57,19 @@ def _compare_state(s, U, eh, tol=TOL):
         assert_close(s.get("y_theta_i"), U.theta_i, 0.0, "theta_i")
 
 
-@pytest.mark.parametrize("variant", [0, 2], ids=["auto", "generic"])
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("math_mode", [0, 1], ids=["fast", "libm"])
 @pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-cl{c[1]}-t{c[2]}b{c[3]}-tm{int(c[4])}-N{c[5]}-it{c[8]}" for c in CASES])
 def test_fused_step_matches_oracle(case, math_mode, variant):
     model, closure, top_bc, bottom_bc, topmodel, N, ncol, dt, iters = case
+    kv, layout = VARIANTS[variant]
+    if variant == "lane_per_cell" and N > 32:
+        pytest.skip("lane-per-cell needs N <= 32")
+    if variant == "register_column" and N != 15:
+        pytest.skip("register-column is built for N = 15")
     w = _setup(case)
     P, U, p = oracle_problem(w, closure, top_bc, bottom_bc)
-    s = cuda_solver(w, closure, top_bc, bottom_bc, math_mode=math_mode, kernel_variant=variant)
+    s = cuda_solver(w, closure, top_bc, bottom_bc, math_mode=math_mode, kernel_variant=kv, layout=layout)
     it, nrm = P.implicit_step(U, dt, iters, tol=-1.0, p=p)
     st = s.implicit_step(dt, iters, want_stats=True)
     assert st["iterations"] == iters and st["nan_count"] == 0
@@ -89,6 +102,26 @@ def test_tolerance_path_matches_oracle(model):
     assert st["iterations"] == it and st["converged"]
     assert abs(st["dx_norm"] - nrm) <= 1e-6 * nrm
     _compare_state(s, U, model == "energy_hydrology", tol=1e-11)
+    s.close()
+
+
+@pytest.mark.parametrize("model", ["richards", "energy_hydrology"])
+def test_out_of_place_leaves_temp_untouched(model):
+    """CLB_OPT_OUT_OF_PLACE: Y keeps ClimaTimeSteppers' `temp`, the new stage value goes to U."""
+    case = (model, 0, 0, 0, True, 15, 300, 900.0, 3)
+    w = _setup(case)
+    P, U, p = oracle_problem(w)
+    P.implicit_step(U, 900.0, 3, p=p)
+    s = cuda_solver(w, out_of_place=True)
+    for _ in range(2):  # idempotent: the second call repeats the first
+        s.implicit_step(900.0, 3)
+        assert np.array_equal(s.get("y_theta_l"), w["y_theta_l"])
+        assert_close(s.get("u_theta_l"), U.theta_l, TOL, "u_theta_l")
+        assert_close(s.get("u_intf_w"), U.intF_w, TOL, "u_intf_w")
+        if model == "energy_hydrology":
+            assert np.array_equal(s.get("y_rho_e_int"), w["y_rho_e_int"])
+            assert_close(s.get("u_rho_e_int"), U.rho_e_int, TOL, "u_rho_e_int")
+            assert_close(s.get("u_intf_e"), U.intF_e, TOL, "u_intf_e")
     s.close()
 
 

@@ -57,9 +57,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("layout", [1, 2], ids=["colfast", "levfast"])
 @pytest.mark.parametrize("math_mode", [0, 1])
 @pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-cl{c[1]}-t{c[2]}b{c[3]}-tm{int(c[4])}-N{c[5]}" for c in CASES])
-def test_hooks_match_oracle(case, math_mode):
+def test_hooks_match_oracle(case, math_mode, layout):
     model, closure, top_bc, bottom_bc, topmodel, N, ncol = case
     w = _workload(model, ncol, N, seed=11, topmodel=topmodel)
     if closure == 1:
@@ -70,7 +71,7 @@ def test_hooks_match_oracle(case, math_mode):
     if bottom_bc == 2:
         w["theta_bc_bot"] = w["nu"][:, 0] - rng.uniform(1e-3, 0.1, ncol)
     P, Y, p = oracle_problem(w, closure, top_bc, bottom_bc)
-    s = cuda_solver(w, closure, top_bc, bottom_bc, math_mode=math_mode)
+    s = cuda_solver(w, closure, top_bc, bottom_bc, math_mode=math_mode, layout=layout)
     eh = model == "energy_hydrology"
 
     # update_implicit_cache!
