@@ -70,7 +70,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    # CLB_LIBRARY_PATH: load an alternative build of the same ABI (kernel tuning experiments)
+    path = os.environ.get("CLB_LIBRARY_PATH") or _build.build()
     L = C.CDLL(path)
     h = C.c_void_p
     i32, i64, d = C.c_int32, C.c_int64, C.c_double
@@ -93,6 +94,7 @@ def lib():
                                    C.POINTER(i32), C.POINTER(C.c_void_p), i32],
         "clb_column_integral": [h, i32, i32],
         "clb_global_balance": [h, _dp],
+        "clb_test_math": [i32, _dp, _dp, _dp, i64],
         "clb_comm_unique_id": [C.c_void_p],
         "clb_comm_init": [h, C.c_void_p, i32, i32],
     }

@@ -123,6 +123,7 @@ struct clb_handle_s {
     // scratch
     double *work[6] = {};
     double *carry = nullptr;
+    double *zeros_cell = nullptr, *zeros_col = nullptr;  // stand-ins for fields the configuration does not use
     double *d_stats = nullptr;  // [0] dx^2, [1] non-finite count, [2] norm of the tolerance path, [3..6] balance
     int32_t *d_flags = nullptr; // [0] converged, [1] iterations of the tolerance path
     // multi-GPU
@@ -217,6 +218,12 @@ clb::DevView make_view(clb_handle h)
     P.K_lag = F[CLB_F_K_LAG]; P.kappa_lag = F[CLB_F_KAPPA_LAG]; P.theta_l_lag = F[CLB_F_THETA_L_LAG];
     P.is_sat = F[CLB_F_IS_SATURATED];
     P.R_ss = F[CLB_F_R_SS]; P.R_ess = F[CLB_F_R_ESS]; P.h_grad = F[CLB_F_H_GRAD];
+    if (!c.has_topmodel_source) {  // the lane-per-cell kernel loads these unconditionally
+        P.is_sat = h->zeros_cell;
+        P.R_ss = P.R_ess = P.h_grad = h->zeros_col;
+    } else if (!P.R_ess) {
+        P.R_ess = h->zeros_col;
+    }
     P.theta_bc_top = F[CLB_F_THETA_BC_TOP]; P.theta_bc_bot = F[CLB_F_THETA_BC_BOT];
     P.Y_theta_l = F[CLB_F_Y_THETA_L]; P.Y_rho_e = F[CLB_F_Y_RHO_E_INT]; P.Y_theta_i = F[CLB_F_Y_THETA_I];
     P.Y_intF_w = F[CLB_F_Y_INTF_W]; P.Y_intF_e = F[CLB_F_Y_INTF_E];
@@ -355,10 +362,45 @@ __global__ void __launch_bounds__(128) k_balance(const clb::DevView P, const dou
     }
 }
 
+// device-side evaluation of the soil_math.cuh functions, for the accuracy tests
+__global__ void k_test_math(int kind, const double *x, const double *y, double *out, int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double r = 0.0;
+    switch (kind) {
+    case 0: r = clb::fm::rcp(x[k]); break;
+    case 1: r = clb::fm::div(x[k], y[k]); break;
+    case 2: r = clb::fm::log(x[k]); break;
+    case 3: r = clb::fm::exp(x[k]); break;
+    case 4: r = clb::fm::sqrt(x[k]); break;
+    case 5: r = clb::fm::rcp_seed(x[k]); break;
+    default: r = NAN;
+    }
+    out[k] = r;
+}
+
 }  // namespace
 
 // =============================================================================
 extern "C" {
+
+int clb_test_math(int32_t kind, const double *x, const double *y, double *out, int64_t n)
+{
+    if (!x || !out || n < 1) return fail(CLB_ERR_INVALID, "clb_test_math: bad arguments");
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc(&dx, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&dy, n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&dout, n * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dy, y ? y : x, n * sizeof(double), cudaMemcpyHostToDevice));
+    k_test_math<<<(unsigned)((n + 255) / 256), 256>>>(kind, dx, dy, dout, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return CLB_OK;
+}
+
 
 int clb_abi_version(void) { return CLB_ABI_VERSION; }
 
@@ -412,6 +454,10 @@ int clb_create(clb_handle *out, const clb_config *cfg)
     int rc = CLB_OK;
     auto init = [&]() -> int {
         CUDA_TRY(cudaMalloc(&h->d_grid, 4 * (size_t)cfg->n_levels * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->zeros_cell, h->cell_elems * sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(h->zeros_cell, 0, h->cell_elems * sizeof(double), h->stream));
+        CUDA_TRY(cudaMalloc(&h->zeros_col, (size_t)h->ld * sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(h->zeros_col, 0, (size_t)h->ld * sizeof(double), h->stream));
         CUDA_TRY(cudaMalloc(&h->d_stats, 8 * sizeof(double)));
         CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(double), h->stream));
         CUDA_TRY(cudaMalloc(&h->d_flags, 4 * sizeof(int32_t)));
@@ -436,6 +482,8 @@ int clb_destroy(clb_handle h)
     for (auto &p : h->field) cudaFree(p);
     for (auto &p : h->work) cudaFree(p);
     cudaFree(h->carry);
+    cudaFree(h->zeros_cell);
+    cudaFree(h->zeros_col);
     cudaFree(h->d_grid);
     cudaFree(h->d_idx);
     cudaFree(h->d_stage);

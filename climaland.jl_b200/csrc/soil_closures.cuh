@@ -22,6 +22,8 @@
 #pragma once
 #include <math.h>
 
+#include "soil_math.cuh"
+
 namespace clb {
 
 constexpr double kSqrtEps = 1.4901161193847656e-8;  // sqrt(eps(Float64))
@@ -139,11 +141,120 @@ __device__ __forceinline__ void closure_eval(const HydroCell &p, double theta, d
     }
 }
 
+// Per-cell evaluator of one implicit stage.  nu_eff (nu, or nu - theta_i for
+// EnergyHydrology) is constant during the Newton loop, so everything that does not
+// depend on the iterate is prepared once: clips, 1/m, 1/n, 1/alpha, the dpsi prefactor.
+//   LIBM mode: holds the raw parameters and evaluates the reference's pow expressions.
+//   FAST mode: one log(S) shared by all powers, soil_math.cuh functions, no division by a
+//              stage constant inside the loop.  S itself is an exactly rounded-or-exact
+//              quotient (fm::div reproduces exact quotients), so the S < 1 / S <= 1 branches
+//              agree with the reference.
+template <int CLOSURE, int MATH>
+struct CellEval;
+
+template <int CLOSURE>
+struct CellEval<CLOSURE, kMathLibm> {
+    HydroCell p;
+    double nu_eff;
+    __device__ __forceinline__ CellEval(const HydroCell &c, double nu_eff_) : p(c), nu_eff(nu_eff_) {}
+    template <bool WK, bool WP, bool WD>
+    __device__ __forceinline__ void eval(double theta, double &K, double &psi, double &dpsi) const
+    {
+        closure_eval<CLOSURE, kMathLibm, WK, WP, WD>(p, theta, nu_eff, K, psi, dpsi);
+    }
+};
+
+template <>
+struct CellEval<kVanGenuchten, kMathFast> {
+    double theta_r, theta_lo, nu_safe, range, K_sat, inv_Ss, m, inv_m, inv_n, inv_alpha, c_dpsi;
+    __device__ __forceinline__ CellEval(const HydroCell &c, double nu_eff)
+    {
+        theta_r = c.theta_r;
+        theta_lo = c.theta_r + kSqrtEps;
+        nu_safe = fmax(nu_eff, theta_lo);
+        range = nu_safe - c.theta_r;
+        K_sat = c.K_sat;
+        inv_Ss = fm::rcp(c.S_s);
+        m = c.m;
+        inv_m = fm::rcp(c.m);
+        inv_n = fm::rcp(c.b);
+        inv_alpha = fm::rcp(c.a);
+        c_dpsi = fm::rcp((c.a * c.m * c.b) * range);
+    }
+    template <bool WK, bool WP, bool WD>
+    __device__ __forceinline__ void eval(double theta, double &K, double &psi, double &dpsi) const
+    {
+        const double theta_safe = fmax(theta, theta_lo);
+        const double S = fm::div(theta_safe - theta_r, range);
+        if (S < 1.0) {
+            const double L = fm::log(S);
+            const double E = L * inv_m;
+            const double A = fm::exp(E);  // S^(1/m)
+            const double l1 = fm::log(1.0 - A);
+            if (WK) {
+                const double t = 1.0 - fm::exp(m * l1);
+                K = (fm::sqrt(S) * (t * t)) * K_sat;
+            }
+            if (WP || WD) {
+                const double B = fm::rcp(A);  // S^(-1/m)
+                const double x = B - 1.0;
+                const double q = fm::exp((l1 - E) * inv_n);  // x^(1/n)
+                if (WP) psi = -(q * inv_alpha);
+                if (WD) {
+                    const double d = ((q * B) * c_dpsi) * fm::rcp(x * S);
+                    dpsi = (x == 0.0) ? INFINITY : d;
+                }
+            }
+        } else {
+            if (WK) K = K_sat;
+            if (WP) psi = (S == 1.0) ? -0.0 : (theta_safe - nu_safe) * inv_Ss;
+            if (WD) dpsi = inv_Ss;
+        }
+    }
+};
+
+template <>
+struct CellEval<kBrooksCorey, kMathFast> {
+    double theta_r, theta_lo, nu_safe, range, K_sat, inv_Ss, psi_b, neg_inv_c, k_exp, c_dpsi;
+    __device__ __forceinline__ CellEval(const HydroCell &c, double nu_eff)
+    {
+        theta_r = c.theta_r;
+        theta_lo = c.theta_r + kSqrtEps;
+        nu_safe = fmax(nu_eff, theta_lo);
+        range = nu_safe - c.theta_r;
+        K_sat = c.K_sat;
+        inv_Ss = fm::rcp(c.S_s);
+        psi_b = c.b;
+        neg_inv_c = -fm::rcp(c.a);
+        k_exp = fma(-2.0, neg_inv_c, 3.0);
+        c_dpsi = -fm::div(c.b, c.a * range);
+    }
+    template <bool WK, bool WP, bool WD>
+    __device__ __forceinline__ void eval(double theta, double &K, double &psi, double &dpsi) const
+    {
+        const double theta_safe = fmax(theta, theta_lo);
+        const double S = fm::div(theta_safe - theta_r, range);
+        if (S < 1.0) {
+            const double L = fm::log(S);
+            if (WK) K = fm::exp(k_exp * L) * K_sat;
+            if (WP || WD) {
+                const double pw = fm::exp(L * neg_inv_c);  // S^(-1/c)
+                if (WP) psi = psi_b * pw;
+                if (WD) dpsi = (c_dpsi * pw) * fm::rcp(S);
+            }
+        } else {
+            if (WK) K = K_sat;
+            if (WP) psi = (S == 1.0) ? psi_b : (theta_safe - nu_safe) * inv_Ss + psi_b;
+            if (WD) dpsi = inv_Ss;
+        }
+    }
+};
+
 template <int CLOSURE, int MATH>
 __device__ __forceinline__ double pressure_head(const HydroCell &p, double theta, double nu_eff)
 {
     double K, psi, d;
-    closure_eval<CLOSURE, MATH, false, true, false>(p, theta, nu_eff, K, psi, d);
+    CellEval<CLOSURE, MATH>(p, nu_eff).template eval<false, true, false>(theta, K, psi, d);
     return psi;
 }
 
@@ -151,7 +262,7 @@ template <int CLOSURE, int MATH>
 __device__ __forceinline__ double dpsidtheta(const HydroCell &p, double theta, double nu_eff)
 {
     double K, psi, d;
-    closure_eval<CLOSURE, MATH, false, false, true>(p, theta, nu_eff, K, psi, d);
+    CellEval<CLOSURE, MATH>(p, nu_eff).template eval<false, false, true>(theta, K, psi, d);
     return d;
 }
 
@@ -183,6 +294,17 @@ __device__ __forceinline__ double eh_temperature(double theta_l, double rho_e_in
     const double tl = fmin(nu - theta_i, theta_l);
     const double rho_c_s = volumetric_heat_capacity(tl, theta_i, rho_c_ds, e);
     return temperature_from_rho_e_int(rho_e_int, theta_i, rho_c_s, e);
+}
+
+// The same with the branch-free division of soil_math.cuh (FAST mode of the fused kernels).
+template <int MATH>
+__device__ __forceinline__ double eh_temperature_m(double theta_l, double rho_e_int, double theta_i, double nu,
+                                                   double rho_c_ds, const EarthConst &e)
+{
+    if (MATH == kMathLibm) return eh_temperature(theta_l, rho_e_int, theta_i, nu, rho_c_ds, e);
+    const double tl = fmin(nu - theta_i, theta_l);
+    const double rho_c_s = volumetric_heat_capacity(tl, theta_i, rho_c_ds, e);
+    return e.T_ref + fm::div(rho_e_int + theta_i * e.rho_i * e.LH_f0, rho_c_s);
 }
 
 }  // namespace clb

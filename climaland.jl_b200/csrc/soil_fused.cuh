@@ -78,7 +78,7 @@ __device__ __forceinline__ double richards_newton_iteration(const DevView &P, co
     // level 0
     HydroCell cell = load_cell(P, P.at(0, c));
     double K0, psi0, d0;
-    closure_eval<CLOSURE, MATH, true, true, true>(cell, U.get(0), cell.nu, K0, psi0, d0);
+    CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, true, true>(U.get(0), K0, psi0, d0);
     if (bc_live) {
         if (P.bottom_bc == 1)
             bot_w = -1 * K0;
@@ -93,7 +93,7 @@ __device__ __forceinline__ double richards_newton_iteration(const DevView &P, co
         double a_hi = 0.0, q_hi, K1 = 0.0, psi1 = 0.0, d1 = 0.0, top_dflux = 0.0;
         if (i < N - 1) {
             cell = load_cell(P, k + P.sl);
-            closure_eval<CLOSURE, MATH, true, true, true>(cell, U.get(i + 1), cell.nu, K1, psi1, d1);
+            CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, true, true>(U.get(i + 1), K1, psi1, d1);
             a_hi = ((K0 + K1) / 2.0) * G.idzf(i + 1);
             q_hi = -a_hi * ((psi1 + G.z(i + 1)) - (psi0 + G.z(i)));
         } else {
@@ -295,7 +295,7 @@ __device__ __forceinline__ double eh_newton_iteration(const DevView &P, const Gr
         const double theta_i = P.Y_theta_i[k];
         const double theta = U1.get(i);
         double Kdummy;
-        closure_eval<CLOSURE, MATH, false, true, true>(cell, theta, cell.nu - theta_i, Kdummy, psi, dps);
+        CellEval<CLOSURE, MATH>(cell, cell.nu - theta_i).template eval<false, true, true>(theta, Kdummy, psi, dps);
         T = eh_temperature(theta, U2.get(i), theta_i, cell.nu, __ldg(P.rho_c_ds + k), E);
         K = __ldg(P.K_lag + k);
         kap = __ldg(P.kappa_lag + k);

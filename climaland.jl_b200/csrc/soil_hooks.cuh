@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) k_update_implicit_cache(const DevView P)
             const HydroCell cell = load_cell(P, k);
             theta = P.Y_theta_l[k];
             double d;
-            closure_eval<CLOSURE, MATH, true, true, false>(cell, theta, cell.nu, K, psi, d);
+            CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, true, false>(theta, K, psi, d);
             P.p_K[k] = K;
             P.p_psi[k] = psi;
             tw += theta * P.dz_c[i];

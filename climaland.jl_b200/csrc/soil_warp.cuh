@@ -25,6 +25,9 @@
 
 namespace clb {
 
+#ifndef CLB_WARP_MIN_BLOCKS
+#define CLB_WARP_MIN_BLOCKS 4
+#endif
 constexpr unsigned kFull = 0xffffffffu;
 
 template <int SEG>
@@ -36,51 +39,56 @@ __device__ __forceinline__ double from_below(double v, int d = 1) { return __shf
 // row l is (a, b, c | d) = (lower, diag, upper | rhs).  Rows outside the column are
 // identity rows.  Out-of-range shuffles return the lane's own (finite) value and are
 // multiplied by a coupling that is exactly zero there.
+// Rows are kept normalised (diagonal = 1), so a step needs three values from each
+// neighbour (a, c, d) and one reciprocal.
 template <int SEG>
 __device__ __forceinline__ double pcr_solve(double a, double b, double c, double d)
 {
+    double r = fm::rcp(b);
+    a *= r; c *= r; d *= r;
 #pragma unroll
     for (int s = 1; s < SEG; s <<= 1) {
-        const double r = 1.0 / b;
-        const double al = -a * from_below<SEG>(r, s);
-        const double ga = -c * from_above<SEG>(r, s);
         const double a_m = from_below<SEG>(a, s), c_m = from_below<SEG>(c, s), d_m = from_below<SEG>(d, s);
         const double a_p = from_above<SEG>(a, s), c_p = from_above<SEG>(c, s), d_p = from_above<SEG>(d, s);
-        b = b + al * c_m + ga * a_p;
-        d = d + al * d_m + ga * d_p;
-        a = al * a_m;
-        c = ga * c_p;
+        r = fm::rcp(fma(-a, c_m, fma(-c, a_p, 1.0)));
+        d = fma(-a, d_m, fma(-c, d_p, d)) * r;
+        a = -(a * a_m) * r;
+        c = -(c * c_p) * r;
     }
-    return d / b;
+    return d;
 }
 
 // The same reduction split into a matrix part (once) and a right-hand-side part (per solve).
 template <int SEG>
 struct PcrFactor {
     static constexpr int kSteps = (SEG == 32) ? 5 : 4;
-    double al[kSteps], ga[kSteps], inv_b;
+    double a_s[kSteps], c_s[kSteps], r_s[kSteps + 1];
     __device__ __forceinline__ void factor(double a, double b, double c)
     {
+        double r = fm::rcp(b);
+        r_s[0] = r;
+        a *= r; c *= r;
         int k = 0;
 #pragma unroll
         for (int s = 1; s < SEG; s <<= 1, ++k) {
-            const double r = 1.0 / b;
-            al[k] = -a * from_below<SEG>(r, s);
-            ga[k] = -c * from_above<SEG>(r, s);
             const double a_m = from_below<SEG>(a, s), c_m = from_below<SEG>(c, s);
             const double a_p = from_above<SEG>(a, s), c_p = from_above<SEG>(c, s);
-            b = b + al[k] * c_m + ga[k] * a_p;
-            a = al[k] * a_m;
-            c = ga[k] * c_p;
+            a_s[k] = a;
+            c_s[k] = c;
+            r = fm::rcp(fma(-a, c_m, fma(-c, a_p, 1.0)));
+            r_s[k + 1] = r;
+            a = -(a * a_m) * r;
+            c = -(c * c_p) * r;
         }
-        inv_b = 1.0 / b;
     }
     __device__ __forceinline__ double solve(double d) const
     {
+        d *= r_s[0];
         int k = 0;
 #pragma unroll
-        for (int s = 1; s < SEG; s <<= 1, ++k) d = d + al[k] * from_below<SEG>(d, s) + ga[k] * from_above<SEG>(d, s);
-        return d * inv_b;
+        for (int s = 1; s < SEG; s <<= 1, ++k)
+            d = fma(-a_s[k], from_below<SEG>(d, s), fma(-c_s[k], from_above<SEG>(d, s), d)) * r_s[k + 1];
+        return d;
     }
 };
 
@@ -92,8 +100,14 @@ __device__ __forceinline__ HydroCell dummy_cell()
     return h;
 }
 
+// IEEE operations in LIBM mode, the branch-free ones of soil_math.cuh in FAST mode
+template <int MATH>
+__device__ __forceinline__ double m_rcp(double x) { return MATH == kMathLibm ? 1.0 / x : fm::rcp(x); }
+template <int MATH>
+__device__ __forceinline__ double m_div(double a, double b) { return MATH == kMathLibm ? a / b : fm::div(a, b); }
+
 template <int CLOSURE, int MATH, int MODEL, int SEG>
-__global__ void __launch_bounds__(128) k_step_warp(const DevView P, double dtg, int max_iters)
+__global__ void __launch_bounds__(128, CLB_WARP_MIN_BLOCKS) k_step_warp(const DevView P, double dtg, int max_iters)
 {
     constexpr int CPW = 32 / SEG;  // columns per warp
     const int lane = threadIdx.x & 31;
@@ -105,61 +119,85 @@ __global__ void __launch_bounds__(128) k_step_warp(const DevView P, double dtg, 
     const bool cell = col_ok && l < N;
     const bool is_bot = (l == 0), is_top = (l == N - 1);
     const bool interior = cell && l < N - 1;  // has a face above shared with level l+1
-    const int64_t k = cell ? P.at(l, c) : 0;
-    const int64_t cs = col_ok ? c : 0;
     const EarthConst &E = P.earth;
+    // pad lanes read a valid cell (clamped indices) and are neutralised by selects afterwards
+    const int ls = min(l, N - 1);
+    const int64_t cs = col_ok ? c : P.ncol - 1;
+    const int64_t k = P.at(ls, cs);
 
-    // ---- per-lane constants of the stage ------------------------------------------------
-    const HydroCell hc = cell ? load_cell(P, k) : dummy_cell();
-    const double z = cell ? __ldg(P.z_c + l) : 0.0;
-    const double idzc = cell ? __ldg(P.inv_dz_c + l) : 1.0;
-    const double idzf_hi = interior ? __ldg(P.inv_dz_f + l + 1) : 0.0;
-    double sat = 0.0, src_w = 0.0, src_e = 0.0, R_ss = 0.0, R_ess = 0.0;
-    if (P.topmodel) {
-        const double hg = fmax(P.h_grad[cs], kEps);
-        R_ss = P.R_ss[cs];
-        src_w = R_ss / hg;
-        if (MODEL == 1) {
-            R_ess = P.R_ess[cs];
-            src_e = R_ess / hg;
-        }
-        sat = cell ? P.is_sat[k] : 0.0;
-    }
+    // ---- every global load of the stage, issued back to back (one DRAM round trip) -------
+    HydroCell hc = load_cell(P, k);
+    const double z = __ldg(P.z_c + ls);
+    double idzc = __ldg(P.inv_dz_c + ls);
+    double idzf_hi = __ldg(P.inv_dz_f + min(ls + 1, N - 1));
+    const double ld_theta = P.Y_theta_l[k];
+    // (fields the configuration does not use point at zero-filled dummies: no branches here)
+    const double ld_sat = P.is_sat[k];
+    const double ld_Rss = P.R_ss[cs];
+    const double ld_hg = P.h_grad[cs];
     double top_w = P.top_bc_w[cs], bot_w = P.bot_bc_w[cs];
-    const double temp1 = cell ? P.Y_theta_l[k] : 0.3;
-    double U1 = temp1;
-    const double tiw = P.Y_intF_w[cs];
-    double Uiw = tiw;
-
-    // EnergyHydrology: lagged fields, constant face coefficients, factored W22
-    double theta_i = 0.0, rcds = 0.0, K_lag = 0.0, temp2 = 0.0, U2 = 0.0, nu_eff = hc.nu;
-    double aK_hi = 0.0, aK_lo = 0.0, aC_hi = 0.0, aC_lo = 0.0, top_h = 0.0, bot_h = 0.0, tie = 0.0, Uie = 0.0;
-    PcrFactor<SEG> W22;
+    double ld_theta_i = 0.0, ld_rcds = 1e6, ld_K = 0.0, ld_kap = 0.0, ld_tl = 0.0, ld_rho_e = 0.0, ld_Ress = 0.0;
+    double top_h = 0.0, bot_h = 0.0;
     if (MODEL == 1) {
-        theta_i = cell ? P.Y_theta_i[k] : 0.0;
-        rcds = cell ? __ldg(P.rho_c_ds + k) : 1e6;
-        K_lag = cell ? __ldg(P.K_lag + k) : 0.0;
-        const double kap = cell ? __ldg(P.kappa_lag + k) : 0.0;
-        const double tl_lag = cell ? __ldg(P.theta_l_lag + k) : 0.0;
-        temp2 = cell ? P.Y_rho_e[k] : 0.0;
-        U2 = temp2;
-        nu_eff = hc.nu - theta_i;
+        ld_theta_i = P.Y_theta_i[k];
+        ld_rcds = __ldg(P.rho_c_ds + k);
+        ld_K = __ldg(P.K_lag + k);
+        ld_kap = __ldg(P.kappa_lag + k);
+        ld_tl = __ldg(P.theta_l_lag + k);
+        ld_rho_e = P.Y_rho_e[k];
+        ld_Ress = P.R_ess[cs];
         top_h = P.top_bc_h[cs];
         bot_h = P.bot_bc_h[cs];
-        tie = P.Y_intF_e[cs];
-        Uie = tie;
+    }
+    const bool bc_live = (MODEL == 0) && (P.top_bc == 1);  // cache holds dfluxBCdY (rre.jl:460-468)
+    double ld_thbc = hc.nu;
+    if (bc_live) {
+        if (is_top) ld_thbc = P.theta_bc_top[cs];
+        if (is_bot && P.bottom_bc == 2) ld_thbc = P.theta_bc_bot[cs];
+    }
+    const double tiw = P.Y_intF_w[cs];
+    double Uiw = tiw;
+    const double tie = (MODEL == 1) ? P.Y_intF_e[cs] : 0.0;
+
+    // ---- per-lane constants of the stage ------------------------------------------------
+    if (!cell) {
+        hc = dummy_cell();
+        idzc = 1.0;
+    }
+    if (!interior) idzf_hi = 0.0;
+    const double temp1 = cell ? ld_theta : 0.3;
+    double U1 = temp1;
+    // implicit TOPMODEL source (Runoff/Runoff.jl:321-359): per-cell constants src * is_saturated
+    const double inv_hg = m_rcp<MATH>(fmax(ld_hg, kEps));
+    const double sw = cell ? (ld_Rss * inv_hg) * ld_sat : 0.0;
+    const double se = (MODEL == 1 && cell) ? (ld_Ress * inv_hg) * ld_sat : 0.0;
+    // boundary face flux seen by this lane: top lane -> top_bc, bottom lane -> bottom_bc
+    double qw_bc = is_top ? top_w : bot_w;
+    const double qe_bc = is_top ? top_h : bot_h;
+
+    // EnergyHydrology: lagged fields, constant face coefficients, factored W22
+    const double theta_i = (MODEL == 1 && cell) ? ld_theta_i : 0.0;
+    const double rcds = ld_rcds;
+    const double K_lag = cell ? ld_K : 0.0;
+    const double temp2 = cell ? ld_rho_e : 0.0;
+    double U2 = temp2;
+    const double nu_eff = hc.nu - theta_i;  // nu for Richards
+    double aK_hi = 0.0, aK_lo = 0.0, aC_hi = 0.0;
+    PcrFactor<SEG> W22;
+    if (MODEL == 1) {
+        const double kap = cell ? ld_kap : 0.0;
         // (shuffles are always executed by the whole warp, then selected)
         const double K_p = from_above<SEG>(K_lag), kap_p = from_above<SEG>(kap);
         aK_hi = interior ? ((K_lag + K_p) / 2.0) * idzf_hi : 0.0;
         aC_hi = interior ? ((kap + kap_p) / 2.0) * idzf_hi : 0.0;
         aK_lo = from_below<SEG>(aK_hi);
-        aC_lo = from_below<SEG>(aC_hi);
+        double aC_lo = from_below<SEG>(aC_hi);
         if (is_bot) {
             aK_lo = 0.0;
             aC_lo = 0.0;
         }
         // Jacobian uses the LAGGED theta_l for rho_c_s (energy_hydrology.jl:561-566)
-        const double rc = 1 / volumetric_heat_capacity(tl_lag, theta_i, rcds, E);
+        const double rc = m_rcp<MATH>(volumetric_heat_capacity(ld_tl, theta_i, rcds, E));
         double rc_p = from_above<SEG>(rc);
         if (!interior) rc_p = 0.0;
         double rc_m = from_below<SEG>(rc);
@@ -172,25 +210,39 @@ __global__ void __launch_bounds__(128) k_step_warp(const DevView P, double dtg, 
         W22.factor(lo, di, up);
     }
 
-    // Richards with a MoistureStateBC top: boundary values do not depend on the iterate
-    const bool bc_live = (MODEL == 0) && (P.top_bc == 1);
-    double psi_bc = 0.0;
-    if (bc_live) {
-        double th = hc.nu;
-        if (cell && is_top) th = P.theta_bc_top[cs];
-        if (cell && is_bot && P.bottom_bc == 2) th = P.theta_bc_bot[cs];
-        psi_bc = pressure_head<CLOSURE, MATH>(hc, th, hc.nu);  // used by lanes 0 / N-1 only
+    double dx2_int = 0.0;
+    if (MODEL == 1) {
+        // flux integrals (W = -I) with lagged boundary fluxes do not depend on the iterate: run the
+        // same Newton recurrence here, off the hot loop, so its operands die before it
+        const double Tiw = -(top_w - bot_w) - ld_Rss, Tie = -(top_h - bot_h) - ld_Ress;
+        double Ue = tie, dxw = 0.0, dxe = 0.0;
+        for (int it = 0; it < max_iters; ++it) {
+            dxw = -(tiw + dtg * Tiw - Uiw);
+            Uiw -= dxw;
+            dxe = -(tie + dtg * Tie - Ue);
+            Ue -= dxe;
+        }
+        if (is_bot && col_ok) {
+            dx2_int = dxw * dxw + dxe * dxe;
+            P.out_intF_w[c] = Uiw;
+            P.out_intF_e[c] = Ue;
+        }
     }
 
+    // Richards with a MoistureStateBC top: boundary heads do not depend on the iterate
+    double psi_bc = 0.0;
+    if (bc_live) psi_bc = pressure_head<CLOSURE, MATH>(hc, ld_thbc, hc.nu);  // used by lanes 0 / N-1 only
+
+    const CellEval<CLOSURE, MATH> ce(hc, nu_eff);
     double dx2 = 0.0;
 #pragma unroll 1
     for (int it = 0; it < max_iters; ++it) {
         // ---- cache_imp!: closures at the iterate --------------------------------------------
         double K = K_lag, psi, dps;
         if (MODEL == 0)
-            closure_eval<CLOSURE, MATH, true, true, true>(hc, U1, hc.nu, K, psi, dps);
+            ce.template eval<true, true, true>(U1, K, psi, dps);
         else
-            closure_eval<CLOSURE, MATH, false, true, true>(hc, U1, nu_eff, K, psi, dps);
+            ce.template eval<false, true, true>(U1, K, psi, dps);
         const double h = psi + z;
         const double h_p = from_above<SEG>(h);
         double dps_p = from_above<SEG>(dps);
@@ -205,26 +257,25 @@ __global__ void __launch_bounds__(128) k_step_warp(const DevView P, double dtg, 
             if (is_bot) aK_lo = 0.0;
             if (bc_live) {
                 if (is_top) {
-                    top_w = -K * ((psi_bc + P.dz_top) - psi) / P.dz_top;
+                    qw_bc = -K * ((psi_bc + P.dz_top) - psi) / P.dz_top;
                     top_dflux = K * dps / P.dz_top;
                 }
                 if (is_bot) {
                     if (P.bottom_bc == 1)
-                        bot_w = -1 * K;
+                        qw_bc = -1 * K;
                     else if (P.bottom_bc == 2)
-                        bot_w = -K * ((psi + P.dz_bot) - psi_bc) / P.dz_bot;
+                        qw_bc = -K * ((psi + P.dz_bot) - psi_bc) / P.dz_bot;
                 }
-                top_w = __shfl_sync(kFull, top_w, N - 1, SEG);
-                bot_w = __shfl_sync(kFull, bot_w, 0, SEG);
+                top_w = __shfl_sync(kFull, qw_bc, N - 1, SEG);
+                bot_w = __shfl_sync(kFull, qw_bc, 0, SEG);
             }
         }
         // ---- T_imp!: face fluxes (owned by the lane below the face) ---------------------------
         const double dh = h_p - h;
-        const double qw_hi = interior ? -aK_hi * dh : top_w;
+        const double qw_hi = interior ? -aK_hi * dh : qw_bc;
         double qw_lo = from_below<SEG>(qw_hi);
-        if (is_bot) qw_lo = bot_w;
-        double Tw = -((qw_hi - qw_lo) * idzc);
-        if (P.topmodel) Tw -= src_w * sat;
+        if (is_bot) qw_lo = qw_bc;
+        const double Tw = -((qw_hi - qw_lo) * idzc) - sw;
         double f1 = temp1 + dtg * Tw - U1;
         // ---- Wfact: (theta_l, theta_l) -------------------------------------------------------
         double lo, di, up;
@@ -234,18 +285,17 @@ __global__ void __launch_bounds__(128) k_step_warp(const DevView P, double dtg, 
         }
         double f2 = 0.0, aE_hi = 0.0, aE_lo = 0.0;
         if (MODEL == 1) {
-            const double T = eh_temperature(U1, U2, theta_i, hc.nu, rcds, E);
+            const double T = eh_temperature_m<MATH>(U1, U2, theta_i, hc.nu, rcds, E);
             const double eK = volumetric_internal_energy_liq(T, E) * K_lag;
             const double eK_p = from_above<SEG>(eK);
             aE_hi = interior ? ((eK + eK_p) / 2.0) * idzf_hi : 0.0;
             aE_lo = from_below<SEG>(aE_hi);
             if (is_bot) aE_lo = 0.0;
             const double T_p = from_above<SEG>(T);
-            const double qe_hi = interior ? -aC_hi * (T_p - T) - aE_hi * dh : top_h;
+            const double qe_hi = interior ? -aC_hi * (T_p - T) - aE_hi * dh : qe_bc;
             double qe_lo = from_below<SEG>(qe_hi);
-            if (is_bot) qe_lo = bot_h;
-            double Te = -((qe_hi - qe_lo) * idzc);
-            if (P.topmodel) Te -= src_e * sat;
+            if (is_bot) qe_lo = qe_bc;
+            const double Te = -((qe_hi - qe_lo) * idzc) - se;
             f2 = cell ? temp2 + dtg * Te - U2 : 0.0;
         }
         // ---- ldiv!: BlockDiagonalSolve / BlockLowerTriangularSolve(theta_l) --------------------
@@ -261,18 +311,12 @@ __global__ void __launch_bounds__(128) k_step_warp(const DevView P, double dtg, 
             U2 -= x2;
             if (cell) dx2 += x2 * x2;
         }
-        // ---- flux integrals (W = -I): lane 0 of the segment keeps them -------------------------
-        double Tiw = -(top_w - bot_w);
-        if (P.topmodel) Tiw -= R_ss;
-        const double dxw = -(tiw + dtg * Tiw - Uiw);
-        Uiw -= dxw;
-        if (is_bot && col_ok) dx2 += dxw * dxw;
-        if (MODEL == 1) {
-            double Tie = -(top_h - bot_h);
-            if (P.topmodel) Tie -= R_ess;
-            const double dxe = -(tie + dtg * Tie - Uie);
-            Uie -= dxe;
-            if (is_bot && col_ok) dx2 += dxe * dxe;
+        if (MODEL == 0) {
+            // flux integral (W = -I); the boundary fluxes may follow the iterate (MoistureStateBC)
+            const double Tiw = -(top_w - bot_w) - ld_Rss;
+            const double dxw = -(tiw + dtg * Tiw - Uiw);
+            Uiw -= dxw;
+            if (is_bot && col_ok) dx2 += dxw * dxw;
         }
     }
 
@@ -285,15 +329,15 @@ __global__ void __launch_bounds__(128) k_step_warp(const DevView P, double dtg, 
             P.out_rho_e[k] = U2;
             if (!isfinite(U2)) bad += 1.0;
         }
-        if (is_bot) {
+        if (is_bot && MODEL == 0) {
             P.out_intF_w[c] = Uiw;
-            if (MODEL == 1) P.out_intF_e[c] = Uie;
             if (bc_live) {
                 P.top_bc_w[c] = top_w;
                 P.bot_bc_w[c] = bot_w;
             }
         }
     }
+    dx2 += dx2_int;
     accumulate_stats(P, dx2, bad);
 }
 

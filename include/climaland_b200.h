@@ -237,6 +237,12 @@ int clb_column_integral(clb_handle h, int32_t cell_field, int32_t col_field_out)
  * attached.  Synchronous; out is a host pointer to 4 doubles. */
 int clb_global_balance(clb_handle h, double *out4);
 
+/* ---- testing ------------------------------------------------------------- */
+/* Evaluates one of the library's device math functions (csrc/soil_math.cuh) on host
+ * arrays: kind 0 rcp(x), 1 div(x, y), 2 log(x), 3 exp(x), 4 sqrt(x), 5 rcp seed.
+ * Used by tests/test_cuda_math.py only. */
+int clb_test_math(int32_t kind, const double *x, const double *y, double *out, int64_t n);
+
 /* ---- multi-GPU (one handle per rank; columns are sharded, no halo) -------- */
 /* NCCL is loaded at run time (libnccl.so.2).  Rank 0 creates the id, the host
  * side broadcasts the 128 bytes (ClimaComms / torch.distributed), every rank
