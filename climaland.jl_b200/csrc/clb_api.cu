@@ -804,7 +804,7 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     if (!fixed) {
         variant = CLB_VARIANT_GENERIC;  // the tolerance path is one generic launch per iteration
     } else if (variant == CLB_VARIANT_AUTO) {
-        if (level_fast && N <= 32)
+        if (level_fast && N <= 31)
             variant = CLB_VARIANT_LANE_PER_CELL;
         else if (N == 15)
             variant = CLB_VARIANT_REGISTER_COLUMN;
@@ -813,8 +813,8 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     }
     if (variant == CLB_VARIANT_REGISTER_COLUMN && N != 15)
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the register-column variant is built for N == 15");
-    if (variant == CLB_VARIANT_LANE_PER_CELL && N > 32)
-        return fail(CLB_ERR_INVALID, "clb_implicit_step: the lane-per-cell variant needs N <= 32");
+    if (variant == CLB_VARIANT_LANE_PER_CELL && N > 31)
+        return fail(CLB_ERR_INVALID, "clb_implicit_step: the lane-per-cell variant needs N <= 31");
     if (variant == CLB_VARIANT_GENERIC) TRY(ensure_work(h, eh ? 6 : 3));
     if (h->out_of_place) {
         TRY(alloc_fields(h, {CLB_F_U_THETA_L, CLB_F_U_INTF_W}));
@@ -827,10 +827,10 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     int iters_done = max_iters;
     if (fixed) {
         if (variant == CLB_VARIANT_LANE_PER_CELL) {
-            const int cpw = (N <= 16) ? 2 : 1;  // columns per warp
+            const int cpw = (N <= 15) ? 2 : 1;  // columns per warp (one lane of each segment is a ghost)
             const int64_t warps = (P.ncol + cpw - 1) / cpw;
             const unsigned wgrid = (unsigned)((warps * 32 + kBlock - 1) / kBlock);
-            if (N <= 16) {
+            if (N <= 15) {
                 if (eh) DISPATCH_CMN2(h, clb::k_step_warp, 1, 16, wgrid, P, dtgamma, max_iters);
                 else DISPATCH_CMN2(h, clb::k_step_warp, 0, 16, wgrid, P, dtgamma, max_iters);
             } else {

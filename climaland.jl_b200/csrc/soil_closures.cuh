@@ -187,18 +187,20 @@ struct CellEval<kVanGenuchten, kMathFast> {
         const double theta_safe = fmax(theta, theta_lo);
         const double S = fm::div(theta_safe - theta_r, range);
         if (S < 1.0) {
-            const double L = fm::log(S);
+            const double L = fm::log_pos(S);      // S in [~1e-8, 1)
             const double E = L * inv_m;
-            const double A = fm::exp(E);  // S^(1/m)
-            const double l1 = fm::log(1.0 - A);
+            const double A = fm::exp_clamped(E);  // S^(1/m) in (0, 1]
+            // 1 - A is 0 only when S^(1/m) rounds to 1; a floor keeps log finite (the limits
+            // K -> K_sat, psi -> 0 are reached either way, dpsi is selected below)
+            const double l1 = fm::log_pos(fmax(1.0 - A, 1e-300));
             if (WK) {
-                const double t = 1.0 - fm::exp(m * l1);
+                const double t = 1.0 - fm::exp_clamped(m * l1);
                 K = (fm::sqrt(S) * (t * t)) * K_sat;
             }
             if (WP || WD) {
                 const double B = fm::rcp(A);  // S^(-1/m)
                 const double x = B - 1.0;
-                const double q = fm::exp((l1 - E) * inv_n);  // x^(1/n)
+                const double q = fm::exp_clamped((l1 - E) * inv_n);  // x^(1/n)
                 if (WP) psi = -(q * inv_alpha);
                 if (WD) {
                     const double d = ((q * B) * c_dpsi) * fm::rcp(x * S);
@@ -235,10 +237,10 @@ struct CellEval<kBrooksCorey, kMathFast> {
         const double theta_safe = fmax(theta, theta_lo);
         const double S = fm::div(theta_safe - theta_r, range);
         if (S < 1.0) {
-            const double L = fm::log(S);
-            if (WK) K = fm::exp(k_exp * L) * K_sat;
+            const double L = fm::log_pos(S);
+            if (WK) K = fm::exp_clamped(k_exp * L) * K_sat;
             if (WP || WD) {
-                const double pw = fm::exp(L * neg_inv_c);  // S^(-1/c)
+                const double pw = fm::exp_clamped(L * neg_inv_c);  // S^(-1/c)
                 if (WP) psi = psi_b * pw;
                 if (WD) dpsi = (c_dpsi * pw) * fm::rcp(S);
             }

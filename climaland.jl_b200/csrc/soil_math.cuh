@@ -129,5 +129,59 @@ __device__ __forceinline__ double exp(double x)
     return (x != x) ? x : out;
 }
 
+// Variants for arguments known to be in range (the closures: S in (0, 1), exponents within
+// +-700 for every admissible parameter set).  log_pos: x normal and > 0, no special cases.
+// exp_clamped: no special cases either; the power of two is clamped to the normal range, so
+// an out-of-range argument gives a tiny / huge finite number instead of 0 / inf, never garbage.
+__device__ __forceinline__ double log_pos(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;
+    hx |= (i ^ 0x3ff00000);
+    k += (i >> 20);
+    const double m = __hiloint2double(hx, lx);
+    const double f = m - 1.0;
+    const double s = f * rcp(2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
+    const double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dk = __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;
+    return dk * ln2_hi - ((hfsq - fma(s, hfsq + R, dk * ln2_lo)) - f);
+}
+
+__device__ __forceinline__ double exp_clamped(double x)
+{
+    const double L2E = 1.4426950408889634074, ln2_hi = 6.93147180369123816490e-01,
+                 ln2_lo = 1.90821492927058770002e-10, MAGIC = 6755399441055744.0;
+    const double t = fma(x, L2E, MAGIC);
+    const int k = __double2loint(t);
+    const double kd = t - MAGIC;
+    double r = fma(kd, -ln2_hi, x);
+    r = fma(kd, -ln2_lo, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p01 = fma(r, 1.0, 1.0);
+    const double p23 = fma(r, 0.1666666666666668, 0.5000000000000019);
+    const double p45 = fma(r, 0.008333333333319589, 0.04166666666648795);
+    const double p67 = fma(r, 0.00019841269890076403, 0.0013888888952352863);
+    const double p89 = fma(r, 2.755724088722987e-06, 2.4801485441561313e-05);
+    const double pab = fma(r, 2.5110049204818658e-08, 2.763265472252779e-07);
+    const double q0 = fma(r2, p23, p01);
+    const double q1 = fma(r2, p67, p45);
+    const double q2 = fma(r2, pab, p89);
+    const double p = fma(r8, q2, fma(r4, q1, q0));
+    const int kc = min(max(k, -1021), 1022);
+    return __hiloint2double(__double2hiint(p) + (kc << 20), __double2loint(p));
+}
+
 }  // namespace fm
 }  // namespace clb

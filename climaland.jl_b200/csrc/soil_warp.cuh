@@ -106,32 +106,41 @@ __device__ __forceinline__ double m_rcp(double x) { return MATH == kMathLibm ? 1
 template <int MATH>
 __device__ __forceinline__ double m_div(double a, double b) { return MATH == kMathLibm ? a / b : fm::div(a, b); }
 
+// Neighbour exchange by rotation within the segment: the last lane of a segment (SEG - 1)
+// is a GHOST lane -- the host dispatches SEG > N -- that holds the column's bottom boundary
+// values, so lane 0's "below" neighbour is the ghost and no boundary select is needed.
+template <int SEG>
+__device__ __forceinline__ double rot_above(double v, int l) { return __shfl_sync(kFull, v, (l + 1) & (SEG - 1), SEG); }
+template <int SEG>
+__device__ __forceinline__ double rot_below(double v, int l) { return __shfl_sync(kFull, v, (l - 1) & (SEG - 1), SEG); }
+
 template <int CLOSURE, int MATH, int MODEL, int SEG>
 __global__ void __launch_bounds__(128, CLB_WARP_MIN_BLOCKS) k_step_warp(const DevView P, double dtg, int max_iters)
 {
     constexpr int CPW = 32 / SEG;  // columns per warp
+    constexpr int G = SEG - 1;     // ghost lane
     const int lane = threadIdx.x & 31;
     const int l = lane & (SEG - 1);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t c = warp * CPW + lane / SEG;
-    const int N = P.N;
+    const int N = P.N;  // N <= SEG - 1
     const bool col_ok = c < P.ncol;
     const bool cell = col_ok && l < N;
-    const bool is_bot = (l == 0), is_top = (l == N - 1);
+    const bool is_bot = (l == 0), is_top = (l == N - 1), is_ghost = (l == G);
     const bool interior = cell && l < N - 1;  // has a face above shared with level l+1
     const EarthConst &E = P.earth;
-    // pad lanes read a valid cell (clamped indices) and are neutralised by selects afterwards
+    // pad lanes read a valid cell (clamped indices) and are neutralised below
     const int ls = min(l, N - 1);
     const int64_t cs = col_ok ? c : P.ncol - 1;
     const int64_t k = P.at(ls, cs);
 
-    // ---- every global load of the stage, issued back to back (one DRAM round trip) -------
+    // ---- every global load of the stage, issued back to back (one DRAM round trip);
+    //      fields the configuration does not use point at zero-filled dummies ----------------
     HydroCell hc = load_cell(P, k);
     const double z = __ldg(P.z_c + ls);
     double idzc = __ldg(P.inv_dz_c + ls);
     double idzf_hi = __ldg(P.inv_dz_f + min(ls + 1, N - 1));
     const double ld_theta = P.Y_theta_l[k];
-    // (fields the configuration does not use point at zero-filled dummies: no branches here)
     const double ld_sat = P.is_sat[k];
     const double ld_Rss = P.R_ss[cs];
     const double ld_hg = P.h_grad[cs];
@@ -159,10 +168,11 @@ __global__ void __launch_bounds__(128, CLB_WARP_MIN_BLOCKS) k_step_warp(const De
     double Uiw = tiw;
     const double tie = (MODEL == 1) ? P.Y_intF_e[cs] : 0.0;
 
-    // ---- per-lane constants of the stage ------------------------------------------------
+    // ---- per-lane constants of the stage.  Pad and ghost lanes get idzc = 0, no source and a
+    //      zero face coefficient: their rows are identity rows and their update is exactly 0 ----
     if (!cell) {
         hc = dummy_cell();
-        idzc = 1.0;
+        idzc = 0.0;
     }
     if (!interior) idzf_hi = 0.0;
     const double temp1 = cell ? ld_theta : 0.3;
@@ -171,9 +181,11 @@ __global__ void __launch_bounds__(128, CLB_WARP_MIN_BLOCKS) k_step_warp(const De
     const double inv_hg = m_rcp<MATH>(fmax(ld_hg, kEps));
     const double sw = cell ? (ld_Rss * inv_hg) * ld_sat : 0.0;
     const double se = (MODEL == 1 && cell) ? (ld_Ress * inv_hg) * ld_sat : 0.0;
-    // boundary face flux seen by this lane: top lane -> top_bc, bottom lane -> bottom_bc
-    double qw_bc = is_top ? top_w : bot_w;
-    const double qe_bc = is_top ? top_h : bot_h;
+    // boundary face fluxes enter as an additive constant of the face above: the top lane owns
+    // the top boundary face, the ghost lane "owns" the bottom boundary face
+    double qadd_w = 0.0, qadd_e = 0.0;
+    if (col_ok && is_top) { qadd_w = top_w; qadd_e = top_h; }
+    if (col_ok && is_ghost) { qadd_w = bot_w; qadd_e = bot_h; }
 
     // EnergyHydrology: lagged fields, constant face coefficients, factored W22
     const double theta_i = (MODEL == 1 && cell) ? ld_theta_i : 0.0;
@@ -186,30 +198,17 @@ __global__ void __launch_bounds__(128, CLB_WARP_MIN_BLOCKS) k_step_warp(const De
     PcrFactor<SEG> W22;
     if (MODEL == 1) {
         const double kap = cell ? ld_kap : 0.0;
-        // (shuffles are always executed by the whole warp, then selected)
-        const double K_p = from_above<SEG>(K_lag), kap_p = from_above<SEG>(kap);
-        aK_hi = interior ? ((K_lag + K_p) / 2.0) * idzf_hi : 0.0;
-        aC_hi = interior ? ((kap + kap_p) / 2.0) * idzf_hi : 0.0;
-        aK_lo = from_below<SEG>(aK_hi);
-        double aC_lo = from_below<SEG>(aC_hi);
-        if (is_bot) {
-            aK_lo = 0.0;
-            aC_lo = 0.0;
-        }
+        aK_hi = ((K_lag + rot_above<SEG>(K_lag, l)) / 2.0) * idzf_hi;
+        aC_hi = ((kap + rot_above<SEG>(kap, l)) / 2.0) * idzf_hi;
+        aK_lo = rot_below<SEG>(aK_hi, l);
+        const double aC_lo = rot_below<SEG>(aC_hi, l);
         // Jacobian uses the LAGGED theta_l for rho_c_s (energy_hydrology.jl:561-566)
         const double rc = m_rcp<MATH>(volumetric_heat_capacity(ld_tl, theta_i, rcds, E));
-        double rc_p = from_above<SEG>(rc);
-        if (!interior) rc_p = 0.0;
-        double rc_m = from_below<SEG>(rc);
-        if (is_bot) rc_m = 0.0;
+        const double rc_p = rot_above<SEG>(rc, l), rc_m = rot_below<SEG>(rc, l);
         double lo, di, up;
         tridiag_row(dtg, aC_lo, aC_hi, rc_m, rc, rc_p, idzc, 0.0, lo, di, up);
-        if (!cell) {
-            lo = 0.0; up = 0.0; di = -1.0;
-        }
         W22.factor(lo, di, up);
     }
-
     double dx2_int = 0.0;
     if (MODEL == 1) {
         // flux integrals (W = -I) with lagged boundary fluxes do not depend on the iterate: run the
@@ -244,72 +243,62 @@ __global__ void __launch_bounds__(128, CLB_WARP_MIN_BLOCKS) k_step_warp(const De
         else
             ce.template eval<false, true, true>(U1, K, psi, dps);
         const double h = psi + z;
-        const double h_p = from_above<SEG>(h);
-        double dps_p = from_above<SEG>(dps);
-        if (!interior) dps_p = 0.0;
-        double dps_m = from_below<SEG>(dps);
-        if (is_bot) dps_m = 0.0;
+        const double dh = rot_above<SEG>(h, l) - h;
+        const double dps_p = rot_above<SEG>(dps, l), dps_m = rot_below<SEG>(dps, l);
         double top_dflux = 0.0;
         if (MODEL == 0) {
-            const double K_p = from_above<SEG>(K);
-            aK_hi = interior ? ((K + K_p) / 2.0) * idzf_hi : 0.0;
-            aK_lo = from_below<SEG>(aK_hi);
-            if (is_bot) aK_lo = 0.0;
+            aK_hi = ((K + rot_above<SEG>(K, l)) / 2.0) * idzf_hi;
+            aK_lo = rot_below<SEG>(aK_hi, l);
             if (bc_live) {
-                if (is_top) {
-                    qw_bc = -K * ((psi_bc + P.dz_top) - psi) / P.dz_top;
+                double qb = 0.0;  // bottom boundary flux, evaluated by lane 0, owned by the ghost
+                if (P.bottom_bc == 1)
+                    qb = -1 * K;
+                else if (P.bottom_bc == 2)
+                    qb = -K * ((psi + P.dz_bot) - psi_bc) / P.dz_bot;
+                else
+                    qb = bot_w;
+                qb = rot_above<SEG>(qb, l);
+                if (col_ok && is_ghost) qadd_w = qb;
+                if (col_ok && is_top) {
+                    qadd_w = -K * ((psi_bc + P.dz_top) - psi) / P.dz_top;
                     top_dflux = K * dps / P.dz_top;
                 }
-                if (is_bot) {
-                    if (P.bottom_bc == 1)
-                        qw_bc = -1 * K;
-                    else if (P.bottom_bc == 2)
-                        qw_bc = -K * ((psi + P.dz_bot) - psi_bc) / P.dz_bot;
-                }
-                top_w = __shfl_sync(kFull, qw_bc, N - 1, SEG);
-                bot_w = __shfl_sync(kFull, qw_bc, 0, SEG);
+                top_w = __shfl_sync(kFull, qadd_w, N - 1, SEG);
+                bot_w = __shfl_sync(kFull, qadd_w, G, SEG);
             }
         }
         // ---- T_imp!: face fluxes (owned by the lane below the face) ---------------------------
-        const double dh = h_p - h;
-        const double qw_hi = interior ? -aK_hi * dh : qw_bc;
-        double qw_lo = from_below<SEG>(qw_hi);
-        if (is_bot) qw_lo = qw_bc;
+        const double qw_hi = fma(-aK_hi, dh, qadd_w);
+        const double qw_lo = rot_below<SEG>(qw_hi, l);
         const double Tw = -((qw_hi - qw_lo) * idzc) - sw;
-        double f1 = temp1 + dtg * Tw - U1;
+        const double f1 = temp1 + dtg * Tw - U1;
         // ---- Wfact: (theta_l, theta_l) -------------------------------------------------------
         double lo, di, up;
         tridiag_row(dtg, aK_lo, aK_hi, dps_m, dps, dps_p, idzc, top_dflux, lo, di, up);
-        if (!cell) {
-            lo = 0.0; up = 0.0; di = -1.0; f1 = 0.0;
-        }
         double f2 = 0.0, aE_hi = 0.0, aE_lo = 0.0;
         if (MODEL == 1) {
             const double T = eh_temperature_m<MATH>(U1, U2, theta_i, hc.nu, rcds, E);
             const double eK = volumetric_internal_energy_liq(T, E) * K_lag;
-            const double eK_p = from_above<SEG>(eK);
-            aE_hi = interior ? ((eK + eK_p) / 2.0) * idzf_hi : 0.0;
-            aE_lo = from_below<SEG>(aE_hi);
-            if (is_bot) aE_lo = 0.0;
-            const double T_p = from_above<SEG>(T);
-            const double qe_hi = interior ? -aC_hi * (T_p - T) - aE_hi * dh : qe_bc;
-            double qe_lo = from_below<SEG>(qe_hi);
-            if (is_bot) qe_lo = qe_bc;
+            aE_hi = ((eK + rot_above<SEG>(eK, l)) / 2.0) * idzf_hi;
+            aE_lo = rot_below<SEG>(aE_hi, l);
+            const double dT = rot_above<SEG>(T, l) - T;
+            const double qe_hi = fma(-aC_hi, dT, fma(-aE_hi, dh, qadd_e));
+            const double qe_lo = rot_below<SEG>(qe_hi, l);
             const double Te = -((qe_hi - qe_lo) * idzc) - se;
-            f2 = cell ? temp2 + dtg * Te - U2 : 0.0;
+            f2 = temp2 + dtg * Te - U2;
         }
         // ---- ldiv!: BlockDiagonalSolve / BlockLowerTriangularSolve(theta_l) --------------------
         const double x1 = pcr_solve<SEG>(lo, di, up, f1);
         U1 -= x1;
-        dx2 = cell ? x1 * x1 : 0.0;
+        dx2 = x1 * x1;
         if (MODEL == 1) {
-            const double y = cell ? dps * x1 : 0.0;
-            const double y_p = from_above<SEG>(y), y_m = from_below<SEG>(y);
+            const double y = dps * x1;
+            const double y_p = rot_above<SEG>(y, l), y_m = rot_below<SEG>(y, l);
             // (W21 x1) with W21 = -dtg*(D . Diag(interp(-eK)) . G . Diag(dpsi)) - I  (energy_hydrology.jl:545-556)
             const double s = dtg * ((aE_lo * (y_m - y) + aE_hi * (y_p - y)) * idzc) - x1;
-            const double x2 = W22.solve(cell ? f2 - s : 0.0);
+            const double x2 = W22.solve(f2 - s);
             U2 -= x2;
-            if (cell) dx2 += x2 * x2;
+            dx2 += x2 * x2;
         }
         if (MODEL == 0) {
             // flux integral (W = -I); the boundary fluxes may follow the iterate (MoistureStateBC)

@@ -77,7 +77,7 @@ enum { CLB_MATH_FAST = 0, CLB_MATH_LIBM = 1 };
 enum { CLB_VARIANT_AUTO = 0,
        CLB_VARIANT_REGISTER_COLUMN = 1, /* one thread per column, N = 15 in registers          */
        CLB_VARIANT_GENERIC = 2,         /* one thread per column, any N, scratch in HBM/L2      */
-       CLB_VARIANT_LANE_PER_CELL = 3    /* one lane per cell, shuffle stencil + cyclic reduction, N <= 32 */ };
+       CLB_VARIANT_LANE_PER_CELL = 3    /* one lane per cell, shuffle stencil + cyclic reduction, N <= 31 */ };
 /* layout of the library's per-cell mirrors (0 = let the library choose) */
 enum { CLB_LAYOUT_AUTO = 0,
        CLB_LAYOUT_COLUMN_FASTEST = 1,   /* element (i, c) at i*ld + c                              */

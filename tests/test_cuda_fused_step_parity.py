@@ -63,8 +63,8 @@ def _compare_state(s, U, eh, tol=TOL):
 def test_fused_step_matches_oracle(case, math_mode, variant):
     model, closure, top_bc, bottom_bc, topmodel, N, ncol, dt, iters = case
     kv, layout = VARIANTS[variant]
-    if variant == "lane_per_cell" and N > 32:
-        pytest.skip("lane-per-cell needs N <= 32")
+    if variant == "lane_per_cell" and N > 31:
+        pytest.skip("lane-per-cell needs N <= 31")
     if variant == "register_column" and N != 15:
         pytest.skip("register-column is built for N = 15")
     w = _setup(case)
