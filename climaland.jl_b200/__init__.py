@@ -10,4 +10,10 @@ from .solver import (BOT_FLUX, BOT_FREE_DRAINAGE, BOT_MOISTURE_STATE, BROOKS_COR
                      VARIANT_AUTO, VARIANT_GENERIC, VARIANT_LANE_PER_CELL, VARIANT_REGISTER_COLUMN, LAYOUT_AUTO,
                      LAYOUT_COLUMN_FASTEST, LAYOUT_LEVEL_FASTEST, SoilColumnSolver)
 
+from .soil import (B200SoilJacobian, BrooksCorey, Column, EnergyHydrology, EnergyHydrologyParameters, FreeDrainage,
+                   FusedSoilNewton, HeatFluxBC, IMEXAlgorithm, LandSimulation, MoistureStateBC, NewtonsMethod,
+                   RichardsModel, RichardsParameters, TOPMODELSubsurfaceRunoff, WaterFluxBC, WaterHeatBC,
+                   initialize, initialize_jacobian, ldiv, make_compute_imp_tendency, make_compute_jacobian,
+                   make_update_boundary_fluxes, make_update_implicit_cache, vanGenuchten)
+
 __all__ = [n for n in dir() if not n.startswith("_")]

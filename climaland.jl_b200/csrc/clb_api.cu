@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(128) k_balance(const clb::DevView P, const dou
         const double wc = w ? w[c] : 1.0;
         double water = 0.0, energy = 0.0;
         for (int i = 0; i < P.N; ++i) {
-            const int64_t k = (int64_t)i * P.ld + c;
+            const int64_t k = P.at(i, c);
             double vol = P.Y_theta_l[k];
             if (P.model == 1) {
                 vol += P.Y_theta_i[k] * P.earth.rho_i / P.earth.rho_l;
