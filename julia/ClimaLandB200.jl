@@ -1,0 +1,377 @@
+# ClimaLandB200.jl -- the reference-side binding of libclimaland_b200.so.
+#
+# STATUS: written against ClimaLand.jl v1.11.2 / ClimaCore 0.15 / ClimaTimeSteppers 0.10 sources;
+# NOT executed -- the build image has no Julia toolchain (DESIGN.md "Boundary").  The C ABI it
+# binds (include/climaland_b200.h) is exercised by the same call sequence from Python/ctypes
+# (climaland.jl_b200/solver.py, soil.py) in tests/.
+#
+# What a ClimaLand maintainer does with it (INTEGRATION.md has the walk-through):
+#
+#     using ClimaLand, ClimaLandB200
+#     soil = ClimaLand.Soil.EnergyHydrology{FT}(...)                  # unchanged
+#     sim  = ClimaLandB200.LandSimulationB200(t0, tf, Δt, soil; ...)   # swaps the implicit hooks
+#     ClimaLand.Simulations.solve!(sim)
+#
+# Two drop-in levels (SURVEY 8b):
+#   fine-grained  make_compute_imp_tendency / make_compute_jacobian / make_update_implicit_cache
+#                 return closures that `ccall` one entry point each; `jac_prototype` is a
+#                 B200SoilJacobian whose `ldiv!` is clb_ldiv.  ClimaTimeSteppers' own Newton loop
+#                 drives them (src/simulations/Simulations.jl:177-199).
+#   fused         FusedSoilNewton <: ClimaTimeSteppers.NewtonsMethod-like object whose
+#                 `solve_newton!` ignores the closures and calls clb_implicit_step once per stage.
+module ClimaLandB200
+
+using LinearAlgebra
+import ClimaLand
+import ClimaLand: Soil
+import ClimaCore: Fields, Spaces
+import ClimaTimeSteppers
+import CUDA
+
+const libclb = get(ENV, "CLIMALAND_B200_LIB", "libclimaland_b200.so")
+
+# ---- enums of include/climaland_b200.h ------------------------------------------------------
+const CLB_ABI_VERSION = Int32(1)
+const CLB_RICHARDS, CLB_ENERGY_HYDROLOGY = Int32(0), Int32(1)
+const CLB_VAN_GENUCHTEN, CLB_BROOKS_COREY = Int32(0), Int32(1)
+const CLB_TOP_FLUX, CLB_TOP_MOISTURE_STATE = Int32(0), Int32(1)
+const CLB_BOT_FLUX, CLB_BOT_FREE_DRAINAGE, CLB_BOT_MOISTURE_STATE = Int32(0), Int32(1), Int32(2)
+const CLB_HOST, CLB_DEVICE = Int32(0), Int32(1)
+
+# clb_field ids, in header order
+@enum ClbField::Int32 begin
+    F_NU = 0; F_THETA_R; F_K_SAT; F_S_S; F_HCM_A; F_HCM_B; F_HCM_M; F_RHO_C_DS
+    F_K_LAG; F_KAPPA_LAG; F_THETA_L_LAG; F_IS_SATURATED
+    F_Y_THETA_L; F_Y_RHO_E_INT; F_Y_THETA_I
+    F_P_K; F_P_PSI; F_P_T
+    F_DY_THETA_L; F_DY_RHO_E_INT; F_DY_THETA_I
+    F_W11_LO; F_W11_DI; F_W11_UP; F_W21_LO; F_W21_DI; F_W21_UP; F_W22_LO; F_W22_DI; F_W22_UP
+    F_B_THETA_L; F_B_RHO_E_INT; F_B_THETA_I; F_X_THETA_L; F_X_RHO_E_INT; F_X_THETA_I
+    F_U_THETA_L; F_U_RHO_E_INT
+    F_R_SS; F_R_ESS; F_H_GRAD; F_THETA_BC_TOP; F_THETA_BC_BOT
+    F_TOP_BC_W; F_BOT_BC_W; F_TOP_BC_H; F_BOT_BC_H; F_DFLUXBCDY; F_TOTAL_WATER
+    F_Y_INTF_W; F_Y_INTF_E; F_DY_INTF_W; F_DY_INTF_E; F_B_INTF_W; F_B_INTF_E; F_X_INTF_W; F_X_INTF_E
+    F_AREA_WEIGHT; F_U_INTF_W; F_U_INTF_E
+end
+
+# struct clb_config (same field order and widths as the header)
+struct ClbConfig
+    abi_version::Int32
+    model::Int32
+    closure::Int32
+    top_bc::Int32
+    bottom_bc::Int32
+    has_topmodel_source::Int32
+    n_levels::Int32
+    device::Int32
+    n_columns::Int64
+    stream::Ptr{Cvoid}
+    math_mode::Int32
+    kernel_variant::Int32
+    rho_l::Float64
+    rho_i::Float64
+    cp_l::Float64
+    cp_i::Float64
+    T_ref::Float64
+    LH_f0::Float64
+    layout::Int32
+    reserved::Int32
+end
+
+struct ClbStats
+    iterations::Int32
+    converged::Int32
+    dx_norm::Float64
+    nan_count::Int64
+end
+
+struct ClbError <: Exception
+    code::Int32
+    msg::String
+end
+Base.showerror(io::IO, e::ClbError) = print(io, "libclimaland_b200 error ", e.code, ": ", e.msg)
+
+# The library never throws across the ABI: a negative status becomes a Julia exception here,
+# which is how the reference's hooks report errors.
+function check(rc::Cint)
+    rc == 0 && return nothing
+    throw(ClbError(rc, unsafe_string(ccall((:clb_last_error, libclb), Cstring, ()))))
+end
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    N::Int
+    ncol::Int
+    function Handle(cfg::ClbConfig)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:clb_create, libclb), Cint, (Ref{Ptr{Cvoid}}, Ref{ClbConfig}), out, cfg))
+        h = new(out[], cfg.n_levels, cfg.n_columns)
+        finalizer(x -> ccall((:clb_destroy, libclb), Cint, (Ptr{Cvoid},), x.ptr), h)
+        return h
+    end
+end
+
+# ---- field transfer -------------------------------------------------------------------------
+# ClimaCore stores a scalar 3-D field as parent(field)::CuArray{FT,5} of size (Nv, Ni, Nj, 1, Nh):
+# level fastest, the Ni*Nj*Nh columns follow with stride Nv (test/standalone/Soil/mask_test.jl:61).
+# A 2-D (surface) field is (Ni, Nj, 1, Nh): stride 1 per column.
+strides_of(f::Fields.Field) = ndims(parent(f)) == 5 ? (1, size(parent(f), 1)) : (0, 1)
+
+function set_field!(h::Handle, id::ClbField, f::Fields.Field)
+    sl, sc = strides_of(f)
+    A = parent(f)
+    GC.@preserve A check(ccall((:clb_set_field, libclb), Cint,
+        (Ptr{Cvoid}, Int32, CUDA.CuPtr{Float64}, Int64, Int64, Int32),
+        h.ptr, Int32(id), pointer(A), sl, sc, CLB_DEVICE))
+end
+set_field!(h::Handle, id::ClbField, v::Real) =
+    check(ccall((:clb_fill_field, libclb), Cint, (Ptr{Cvoid}, Int32, Float64), h.ptr, Int32(id), Float64(v)))
+
+function get_field!(f::Fields.Field, h::Handle, id::ClbField)
+    sl, sc = strides_of(f)
+    A = parent(f)
+    GC.@preserve A check(ccall((:clb_get_field, libclb), Cint,
+        (Ptr{Cvoid}, Int32, CUDA.CuPtr{Float64}, Int64, Int64, Int32),
+        h.ptr, Int32(id), pointer(A), sl, sc, CLB_DEVICE))
+end
+
+# ---- model -> handle --------------------------------------------------------------------------
+water_bc(bc) = bc isa Soil.WaterHeatBC ? bc.water : bc
+closure_id(::Soil.vanGenuchten) = CLB_VAN_GENUCHTEN
+closure_id(::Soil.BrooksCorey) = CLB_BROOKS_COREY
+closure_id(f::Fields.Field) = closure_id(first(Array(parent(f)))) # per-cell closures share a type
+top_id(bc) = water_bc(bc) isa Soil.MoistureStateBC ? CLB_TOP_MOISTURE_STATE : CLB_TOP_FLUX
+bot_id(bc) = water_bc(bc) isa Soil.MoistureStateBC ? CLB_BOT_MOISTURE_STATE :
+             water_bc(bc) isa Soil.FreeDrainage ? CLB_BOT_FREE_DRAINAGE : CLB_BOT_FLUX
+has_topmodel(model) = any(s -> s isa ClimaLand.Soil.Runoff.TOPMODELSubsurfaceRunoff || (
+    hasproperty(s, :runoff) && s.runoff isa ClimaLand.Soil.Runoff.TOPMODELRunoff), model.sources)
+
+"""
+    B200Soil(model, Y, p)
+
+The handle plus what the hooks need to find their fields.  Built once, next to
+`initialize(model)` (src/shared_utilities/models.jl:493-499); uploads the time-invariant
+parameters (RichardsParameters rre.jl:22-47 / EnergyHydrologyParameters energy_hydrology.jl:60-170),
+the vertical grid as ClimaCore produced it (Domains.jl:636-667) and the land-sea mask as the
+active-column list (inactive columns are never read or written: mask_test.jl:53-61).
+"""
+struct B200Soil{M}
+    model::M
+    h::Handle
+    energy::Bool
+end
+
+function B200Soil(model::Union{Soil.RichardsModel, Soil.EnergyHydrology}, Y, p)
+    FT = eltype(Y)
+    FT === Float64 || error("libclimaland_b200 is FP64 only")
+    energy = model isa Soil.EnergyHydrology
+    prm = model.parameters
+    ϑ = Y.soil.ϑ_l
+    Nv = size(parent(ϑ), 1)
+    ncol_total = length(parent(ϑ)) ÷ Nv
+    mask = ClimaLand.Domains.landsea_mask(ClimaLand.get_domain(model))
+    active = isnothing(mask) ? nothing : Int64.(findall(>(0.5), vec(Array(parent(mask)))) .- 1)
+    ncol = isnothing(active) ? ncol_total : length(active)
+    earth = energy ? prm.earth_param_set : nothing
+    LP = ClimaLand.Parameters
+    cfg = ClbConfig(CLB_ABI_VERSION, energy ? CLB_ENERGY_HYDROLOGY : CLB_RICHARDS,
+        closure_id(prm.hydrology_cm), top_id(model.boundary_conditions.top),
+        bot_id(model.boundary_conditions.bottom), Int32(has_topmodel(model)), Int32(Nv),
+        Int32(CUDA.deviceid(CUDA.device())), Int64(ncol), Ptr{Cvoid}(CUDA.stream().handle),
+        Int32(0), Int32(0),
+        energy ? LP.ρ_cloud_liq(earth) : 1000.0, energy ? LP.ρ_cloud_ice(earth) : 917.0,
+        energy ? LP.cp_l(earth) : 4181.0, energy ? LP.cp_i(earth) : 2100.0,
+        energy ? LP.T_0(earth) : 273.16, energy ? LP.LH_f0(earth) : 333600.0, Int32(0), Int32(0))
+    h = Handle(cfg)
+    # vertical grid: one column of z (cell centres) and the face heights
+    z_c = Array(parent(Fields.coordinate_field(axes(ϑ)).z))[:, 1, 1, 1, 1]
+    z_f = Array(parent(Fields.coordinate_field(Spaces.face_space(axes(ϑ))).z))[:, 1, 1, 1, 1]
+    check(ccall((:clb_set_grid, libclb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h.ptr, z_c, z_f))
+    isnothing(active) || check(ccall((:clb_set_active_columns, libclb), Cint,
+        (Ptr{Cvoid}, Ptr{Int64}, Int64), h.ptr, active, length(active)))
+    # parameters: scalars are broadcast, fields are transposed on the device.  Struct-valued
+    # closure fields (Nf = 4) are split into component fields first, so every upload is a scalar field.
+    up(id, v::Real) = set_field!(h, id, v)
+    up(id, v::Fields.Field) = set_field!(h, id, v)
+    up(F_NU, prm.ν); up(F_THETA_R, prm.θ_r); up(F_K_SAT, prm.K_sat); up(F_S_S, prm.S_s)
+    cm = prm.hydrology_cm
+    comp(name) = cm isa Fields.Field ? (@. getproperty(cm, name)) : getproperty(cm, name)
+    if closure_id(cm) == CLB_VAN_GENUCHTEN
+        up(F_HCM_A, comp(:α)); up(F_HCM_B, comp(:n)); up(F_HCM_M, comp(:m))
+    else
+        up(F_HCM_A, comp(:c)); up(F_HCM_B, comp(:ψb))
+    end
+    energy && up(F_RHO_C_DS, prm.ρc_ds)
+    return B200Soil(model, h, energy)
+end
+
+# state / lagged cache -> library mirrors (device-to-device transposes on the handle's stream)
+function push_state!(b::B200Soil, Y)
+    set_field!(b.h, F_Y_THETA_L, Y.soil.ϑ_l)
+    set_field!(b.h, F_Y_INTF_W, Y.soil.∫F_vol_liq_water_dt)
+    if b.energy
+        set_field!(b.h, F_Y_RHO_E_INT, Y.soil.ρe_int)
+        set_field!(b.h, F_Y_THETA_I, Y.soil.θ_i)
+        set_field!(b.h, F_Y_INTF_E, Y.soil.∫F_e_dt)
+    end
+end
+
+function push_lagged!(b::B200Soil, p, t)
+    h, m = b.h, b.model
+    top, bot = water_bc(m.boundary_conditions.top), water_bc(m.boundary_conditions.bottom)
+    if b.energy
+        set_field!(h, F_TOP_BC_W, p.soil.top_bc.water); set_field!(h, F_BOT_BC_W, p.soil.bottom_bc.water)
+        set_field!(h, F_TOP_BC_H, p.soil.top_bc.heat);  set_field!(h, F_BOT_BC_H, p.soil.bottom_bc.heat)
+        set_field!(h, F_K_LAG, p.soil.K); set_field!(h, F_KAPPA_LAG, p.soil.κ); set_field!(h, F_THETA_L_LAG, p.soil.θ_l)
+    else
+        set_field!(h, F_TOP_BC_W, p.soil.top_bc); set_field!(h, F_BOT_BC_W, p.soil.bottom_bc)
+    end
+    top isa Soil.MoistureStateBC && set_field!(h, F_THETA_BC_TOP, top.bc(p, t))
+    bot isa Soil.MoistureStateBC && set_field!(h, F_THETA_BC_BOT, bot.bc(p, t))
+    if has_topmodel(m)
+        set_field!(h, F_R_SS, p.soil.R_ss); set_field!(h, F_H_GRAD, p.soil.h∇)
+        set_field!(h, F_IS_SATURATED, p.soil.is_saturated)
+        b.energy && set_field!(h, F_R_ESS, p.soil.R_ess)
+    end
+end
+
+# ---- the hooks (same names and argument order as the reference) ---------------------------------
+"update_implicit_cache!(p, Y, t): src/shared_utilities/models.jl:238-246"
+function make_update_implicit_cache(b::B200Soil)
+    function update_implicit_cache!(p, Y, t)
+        push_state!(b, Y); push_lagged!(b, p, t)
+        check(ccall((:clb_update_implicit_cache, libclb), Cint, (Ptr{Cvoid},), b.h.ptr))
+        get_field!(p.soil.ψ, b.h, F_P_PSI)
+        if b.energy
+            get_field!(p.soil.T, b.h, F_P_T)
+        else
+            get_field!(p.soil.K, b.h, F_P_K)
+            get_field!(p.soil.total_water, b.h, F_TOTAL_WATER)
+            if haskey(p.soil, :dfluxBCdY)   # rre.jl:460-468
+                get_field!(p.soil.top_bc, b.h, F_TOP_BC_W); get_field!(p.soil.bottom_bc, b.h, F_BOT_BC_W)
+            end
+        end
+        return nothing
+    end
+end
+
+"compute_imp_tendency!(dY, Y, p, t): rre.jl:161-203, energy_hydrology.jl:363-425"
+function make_compute_imp_tendency(b::B200Soil)
+    function compute_imp_tendency!(dY, Y, p, t)
+        # the mirrors already hold Y and p from the cache_imp! call that precedes T_imp! in
+        # every Newton iteration (SURVEY 3.2); only the outputs move
+        check(ccall((:clb_compute_imp_tendency, libclb), Cint, (Ptr{Cvoid},), b.h.ptr))
+        get_field!(dY.soil.ϑ_l, b.h, F_DY_THETA_L)
+        get_field!(dY.soil.∫F_vol_liq_water_dt, b.h, F_DY_INTF_W)
+        if b.energy
+            get_field!(dY.soil.ρe_int, b.h, F_DY_RHO_E_INT)
+            get_field!(dY.soil.θ_i, b.h, F_DY_THETA_I)
+            get_field!(dY.soil.∫F_e_dt, b.h, F_DY_INTF_E)
+        end
+        return nothing
+    end
+end
+
+"""
+    B200SoilJacobian
+
+`jac_prototype` replacing `initialize_jacobian(Y)`'s FieldMatrixWithSolver
+(src/shared_utilities/implicit_timestepping.jl:63-172): the tridiagonal blocks live in the library,
+`ldiv!` is BlockDiagonalSolve (Richards) / BlockLowerTriangularSolve(@name(soil.ϑ_l)) (EnergyHydrology).
+"""
+struct B200SoilJacobian{B}
+    b::B
+end
+Base.similar(w::B200SoilJacobian) = w
+initialize_jacobian(b::B200Soil) = B200SoilJacobian(b)
+
+"compute_jacobian!(W, Y, p, dtγ, t): rre.jl:391-458, energy_hydrology.jl:466-576"
+function make_compute_jacobian(b::B200Soil)
+    function compute_jacobian!(W::B200SoilJacobian, Y, p, dtγ, t)
+        check(ccall((:clb_compute_jacobian, libclb), Cint, (Ptr{Cvoid}, Float64), b.h.ptr, float(dtγ)))
+        return nothing
+    end
+end
+
+function LinearAlgebra.ldiv!(x::Fields.FieldVector, W::B200SoilJacobian, rhs::Fields.FieldVector)
+    b = W.b
+    set_field!(b.h, F_B_THETA_L, rhs.soil.ϑ_l); set_field!(b.h, F_B_INTF_W, rhs.soil.∫F_vol_liq_water_dt)
+    if b.energy
+        set_field!(b.h, F_B_RHO_E_INT, rhs.soil.ρe_int); set_field!(b.h, F_B_THETA_I, rhs.soil.θ_i)
+        set_field!(b.h, F_B_INTF_E, rhs.soil.∫F_e_dt)
+    end
+    check(ccall((:clb_ldiv, libclb), Cint, (Ptr{Cvoid},), b.h.ptr))
+    get_field!(x.soil.ϑ_l, b.h, F_X_THETA_L); get_field!(x.soil.∫F_vol_liq_water_dt, b.h, F_X_INTF_W)
+    if b.energy
+        get_field!(x.soil.ρe_int, b.h, F_X_RHO_E_INT); get_field!(x.soil.θ_i, b.h, F_X_THETA_I)
+        get_field!(x.soil.∫F_e_dt, b.h, F_X_INTF_E)
+    end
+    return x
+end
+
+# ---- fused level: one call per implicit stage ---------------------------------------------------
+"""
+    FusedSoilNewton(; max_iters = 3, tol = nothing)
+
+Passed as `IMEXAlgorithm(ARS111(), FusedSoilNewton(...))`.  ClimaTimeSteppers calls
+`solve_newton!(alg, cache, x, f!, j!, pre_iteration!, post_implicit!)` once per implicit stage with
+x = U (initialised to temp); this method ignores the closures and runs the whole loop
+(cache_imp!, max_iters x (Wfact, T_imp!, residual, ldiv!, update)) as ONE kernel.
+`dtγ` reaches us through `set_dtγ!`, called from the Wfact wrapper below.
+"""
+mutable struct FusedSoilNewton{B}
+    b::B
+    max_iters::Int
+    tol::Float64       # < 0: fixed iteration count (the reference default, Simulations.jl:127-135)
+    dtγ::Float64
+    t::Any
+    p::Any
+end
+FusedSoilNewton(b; max_iters = 3, tol = nothing) =
+    FusedSoilNewton(b, max_iters, isnothing(tol) ? -1.0 : Float64(tol), NaN, nothing, nothing)
+ClimaTimeSteppers.allocate_cache(::FusedSoilNewton, x_prototype, j_prototype) = (;)
+
+function ClimaTimeSteppers.solve_newton!(alg::FusedSoilNewton, cache, x, f!, j!, pre_iteration!, post_implicit!)
+    b = alg.b
+    push_state!(b, x); push_lagged!(b, alg.p, alg.t)
+    stats = Ref(ClbStats(0, 0, 0.0, 0))
+    check(ccall((:clb_implicit_step, libclb), Cint, (Ptr{Cvoid}, Float64, Int32, Float64, Ref{ClbStats}),
+        b.h.ptr, alg.dtγ, alg.max_iters, alg.tol, alg.tol < 0 ? C_NULL : stats))
+    get_field!(x.soil.ϑ_l, b.h, F_Y_THETA_L); get_field!(x.soil.∫F_vol_liq_water_dt, b.h, F_Y_INTF_W)
+    if b.energy
+        get_field!(x.soil.ρe_int, b.h, F_Y_RHO_E_INT); get_field!(x.soil.∫F_e_dt, b.h, F_Y_INTF_E)
+    end
+    return nothing
+end
+
+"""
+    LandSimulationB200(t0, tf, Δt, model; fused = true, kwargs...)
+
+`ClimaLand.Simulations.LandSimulation` (src/simulations/Simulations.jl:115-245) with the implicit
+hooks of the soil model replaced; everything else (set_ic!, exp_tendency!, drivers, diagnostics,
+callbacks, ClimaTimeSteppers.init) is the reference's own code.
+"""
+function LandSimulationB200(t0, tf, Δt, model; fused = true, max_iters = 3, kwargs...)
+    Y, p, _ = ClimaLand.initialize(model)
+    b = B200Soil(model, Y, p)
+    newton = fused ? FusedSoilNewton(b; max_iters) :
+             ClimaTimeSteppers.NewtonsMethod(; max_iters,
+                 update_j = ClimaTimeSteppers.UpdateEvery(ClimaTimeSteppers.NewNewtonIteration))
+    ts = ClimaTimeSteppers.IMEXAlgorithm(ClimaTimeSteppers.ARS111(), newton)
+    sim = ClimaLand.Simulations.LandSimulation(t0, tf, Δt, model; timestepper = ts, kwargs...)
+    # swap the implicit side of the ClimaODEFunction the reference built (Simulations.jl:177-199)
+    imp! = make_compute_imp_tendency(b)
+    jac! = make_compute_jacobian(b)
+    cache! = make_update_implicit_cache(b)
+    Wfact = fused ? ((W, Y, p, dtγ, t) -> (newton.dtγ = float(dtγ); newton.t = t; newton.p = p; nothing)) : jac!
+    f = sim._integrator.sol.prob.f
+    T_imp! = ClimaTimeSteppers.ODEFunction(imp!; jac_prototype = initialize_jacobian(b), Wfact)
+    newf = ClimaTimeSteppers.ClimaODEFunction(; T_exp! = f.T_exp!, T_imp!, dss! = f.dss!,
+        cache_imp! = (Y, p, t) -> cache!(p, Y, t))
+    prob = ClimaTimeSteppers.ODEProblem(newf, sim._integrator.u, (t0, tf), sim._integrator.p)
+    integ = ClimaTimeSteppers.init(prob, ts; dt = Δt, callback = sim.callbacks, adaptive = false)
+    return ClimaLand.Simulations.LandSimulation(sim.model, ts, sim.start_date, sim.user_callbacks,
+        sim.diagnostics, sim.required_callbacks, sim.callbacks, integ)
+end
+
+end # module
