@@ -170,6 +170,14 @@ PER_STEP_INPUTS = ("y_theta_l", "y_rho_e_int", "y_theta_i", "k_lag", "kappa_lag"
 PER_STEP_OUTPUTS = ("u_theta_l", "u_rho_e_int", "u_intf_w", "u_intf_e")
 
 
+KERNEL_NAMES = {
+    1: "k_eh_step_reg<vanGenuchten, fast, 15> (thread per column)",
+    2: "k_eh_step_generic<vanGenuchten, fast> (thread per column, scratch in HBM)",
+    3: "k_step_warp<vanGenuchten, fast, EnergyHydrology, 16 lanes/column>",
+    4: "k_step_pair<vanGenuchten, EnergyHydrology, 15> (2 lanes/column, twisted Thomas, constants in shared memory)",
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,6 +186,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="CLB_VARIANT_* (0 = the library's choice)")
+    ap.add_argument("--layout", type=int, default=0, help="CLB_LAYOUT_* (0 = the library's choice)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -205,7 +215,8 @@ def main():
     solvers, inputs = [], []
     for r in range(REPLICAS):
         w = make_inputs(seed=1000 * rank + r)
-        s = cuda_solver(w, device=local_rank, stream=stream.cuda_stream, out_of_place=True)
+        s = cuda_solver(w, device=local_rank, stream=stream.cuda_stream, out_of_place=True,
+                        kernel_variant=args.variant, layout=args.layout)
         solvers.append(s)
         inputs.append(w)
 
@@ -305,7 +316,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config({"sypd_1deg_per_gpu": DT / (ms_step * 1e-3) / 365.0,
-                                       "kernel": "k_step_warp<vanGenuchten, fast, EnergyHydrology, 16 lanes/column> (one launch per step)",
+                                       "kernel": KERNEL_NAMES.get(solvers[0].last_variant(), "?") + " (one launch per step)",
                                        "state": "out of place: Y (= temp) -> U, so every step does identical work"}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e_step, "steps": args.e2e_steps,

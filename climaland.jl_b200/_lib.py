@@ -95,6 +95,7 @@ def lib():
         "clb_column_integral": [h, i32, i32],
         "clb_global_balance": [h, _dp],
         "clb_test_math": [i32, _dp, _dp, _dp, i64],
+        "clb_last_variant": [h, C.POINTER(C.c_int32)],
         "clb_comm_unique_id": [C.c_void_p],
         "clb_comm_init": [h, C.c_void_p, i32, i32],
     }

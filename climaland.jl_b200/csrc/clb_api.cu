@@ -19,6 +19,7 @@
 #include "soil_fused.cuh"
 #include "soil_hooks.cuh"
 #include "soil_warp.cuh"
+#include "soil_pair.cuh"
 
 namespace {
 
@@ -108,6 +109,9 @@ struct clb_handle_s {
     int64_t sl = 0, sc = 0;    // strides of the per-cell mirrors: element (i, c) at i*sl + c*sc
     size_t cell_elems = 0;     // allocation size of a per-cell mirror
     bool out_of_place = false; // fused stage writes the U fields and leaves Y untouched
+    int last_variant = 0;      // kernel variant the last clb_implicit_step launched
+    clb::PairMaps pair_maps;   // TMA descriptors of the lane-pair kernel's inputs and the mirrors they describe
+    const double *pair_map_src[14] = {};
     double *field[CLB_F_NUM] = {};
     bool field_set[CLB_F_NUM] = {};
     // grid
@@ -295,6 +299,131 @@ clb::GridConst<NS> make_grid_const(clb_handle h)
     return g;
 }
 
+// Grid constants of the lane-pair kernel in its lane-local orientation (soil_pair.cuh):
+// bottom half slot q = level q, top half slot q = level 15 - q (pads for levels >= N).
+clb::PairGrid make_pair_grid(clb_handle h, double dtg)
+{
+    const int N = h->cfg.n_levels;
+    clb::PairGrid g;
+    for (int half = 0; half < 2; ++half) {
+        for (int q = 0; q < clb::kPairQ; ++q) {
+            const int level = half ? 15 - q : q;
+            const bool real = level < N;
+            g.z[half][q] = real ? h->z_c[level] : 0.0;
+            g.dti[half][q] = real ? dtg * h->inv_dz_c[level] : 0.0;
+        }
+        for (int f = 0; f <= clb::kPairQ; ++f) {
+            // face f lies between slots f-1 and f; inv_dz_f[i] is the face between levels i-1 and i
+            double v = 0.0;
+            if (f == clb::kPairQ) v = h->inv_dz_f[8];
+            else if (!half && f >= 1) v = h->inv_dz_f[f];
+            else if (half && f >= 1 && 16 - f <= N - 1) v = h->inv_dz_f[16 - f];
+            g.hidzf[half][f] = v / 2.0;
+        }
+    }
+    return g;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int encode_tiled_fn(EncodeTiledFn *out)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess)
+            return fail(CLB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    *out = fn;
+    return CLB_OK;
+}
+
+// TMA descriptor of one column-fastest per-cell mirror: dims {ncol, N} (columns beyond ncol read as 0),
+// row pitch ld doubles, box {16 columns, N levels}.
+int encode_field_map(clb_handle h, const double *ptr, CUtensorMap *map)
+{
+    EncodeTiledFn enc;
+    TRY(encode_tiled_fn(&enc));
+    const cuuint64_t dims[2] = {(cuuint64_t)h->cfg.n_columns, (cuuint64_t)h->cfg.n_levels};
+    const cuuint64_t strides[1] = {(cuuint64_t)h->ld * sizeof(double)};
+    const cuuint32_t box[2] = {16, (cuuint32_t)h->cfg.n_levels};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CLB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return CLB_OK;
+}
+
+// Raw fields of the lane-pair kernel in the order of its shared-memory slots (soil_pair.cuh)
+int make_pair_maps(clb_handle h, const clb::DevView &P, clb::PairMaps *maps)
+{
+    const double *eh[14] = {P.nu, P.theta_r, P.S_s, P.hcm_a, P.hcm_b, P.hcm_m, P.Y_theta_l, P.is_sat, P.Y_theta_i,
+                            P.rho_c_ds, P.K_lag, P.kappa_lag, P.theta_l_lag, P.Y_rho_e};
+    const double *ri[9] = {P.nu, P.theta_r, P.K_sat, P.S_s, P.hcm_a, P.hcm_b, P.hcm_m, P.Y_theta_l, P.is_sat};
+    const bool is_eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    const int n = is_eh ? 14 : 9;
+    const double **src = is_eh ? eh : ri;
+    for (int j = 0; j < n; ++j) {
+        if (h->pair_map_src[j] != src[j]) {  // descriptors are cached per handle; mirrors rarely move
+            if (src[j]) TRY(encode_field_map(h, src[j], &h->pair_maps.m[j]));
+            h->pair_map_src[j] = src[j];
+        }
+    }
+    *maps = h->pair_maps;
+    return CLB_OK;
+}
+
+template <int CLOSURE, int MODEL, int N>
+int launch_pair(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+{
+    // every stage constant of Richards fits in shared memory; EnergyHydrology keeps 14 of 17 there
+    // (2 warps x 14 slots x 2 KB = 56 KB per 64-thread block: 4 blocks per SM)
+    constexpr int NS = (MODEL == 1) ? 14 : 10;
+    constexpr int BLOCK = (N == 16) ? 128 : CLB_PAIR_BLOCK;  // N == 16 has no free pad row for the per-warp mbarrier
+    auto kern = clb::k_step_pair<CLOSURE, MODEL, N, NS, BLOCK>;
+    const size_t smem = clb::pair_smem_bytes<NS, N, BLOCK>();
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    const int64_t warps = (P.ncol + 15) / 16;
+    const unsigned grid = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
+    const clb::PairGrid g = make_pair_grid(h, dtg);
+    clb::PairMaps maps;
+    TRY(make_pair_maps(h, P, &maps));
+    kern<<<grid, BLOCK, smem, h->stream>>>(P, g, maps, dtg, max_iters);
+    return CLB_OK;
+}
+
+template <int N>
+int launch_pair_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+{
+    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    const bool vg = h->cfg.closure == CLB_VAN_GENUCHTEN;
+    if (eh) return vg ? launch_pair<0, 1, N>(h, P, dtg, max_iters) : launch_pair<1, 1, N>(h, P, dtg, max_iters);
+    return vg ? launch_pair<0, 0, N>(h, P, dtg, max_iters) : launch_pair<1, 0, N>(h, P, dtg, max_iters);
+}
+
+bool pair_variant_applies(clb_handle h)
+{
+    const int N = h->cfg.n_levels;
+    if (N != 15 && N != 16) return false;
+    if (h->cfg.math_mode != CLB_MATH_FAST) return false;
+    // a MoistureStateBC top re-evaluates the boundary fluxes every iteration (rre.jl:460-468): lane-per-cell kernel
+    if (h->cfg.model == CLB_RICHARDS && h->cfg.top_bc == 1) return false;
+    // its TMA boxes are cut from column-fastest mirrors
+    if (h->cfg.layout == CLB_LAYOUT_LEVEL_FASTEST) return false;
+    return true;
+}
+
 int step_inputs_ready(clb_handle h)
 {
     if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
@@ -420,7 +549,7 @@ int clb_create(clb_handle *out, const clb_config *cfg)
         return fail(CLB_ERR_INVALID, "clb_create: unknown boundary condition kind");
     if (cfg->layout < CLB_LAYOUT_AUTO || cfg->layout > CLB_LAYOUT_LEVEL_FASTEST)
         return fail(CLB_ERR_INVALID, "clb_create: unknown layout %d", cfg->layout);
-    if (cfg->kernel_variant < CLB_VARIANT_AUTO || cfg->kernel_variant > CLB_VARIANT_LANE_PER_CELL)
+    if (cfg->kernel_variant < CLB_VARIANT_AUTO || cfg->kernel_variant > CLB_VARIANT_LANE_PAIR)
         return fail(CLB_ERR_INVALID, "clb_create: unknown kernel_variant %d", cfg->kernel_variant);
     if (cfg->math_mode != CLB_MATH_FAST && cfg->math_mode != CLB_MATH_LIBM)
         return fail(CLB_ERR_INVALID, "clb_create: unknown math_mode %d", cfg->math_mode);
@@ -440,7 +569,9 @@ int clb_create(clb_handle *out, const clb_config *cfg)
     h->stream = (cudaStream_t)cfg->stream;
     h->ld = (cfg->n_columns + 31) / 32 * 32;
     int layout = cfg->layout;
-    if (layout == CLB_LAYOUT_AUTO) layout = (cfg->n_levels <= 32) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
+    // lane-per-cell kernels read level-fastest mirrors, every column-per-thread(-pair) kernel column-fastest ones
+    if (layout == CLB_LAYOUT_AUTO)
+        layout = (cfg->n_levels <= 32) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
     h->cfg.layout = layout;
     if (layout == CLB_LAYOUT_LEVEL_FASTEST) {
         h->sl = 1;
@@ -813,9 +944,14 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     }
     if (variant == CLB_VARIANT_REGISTER_COLUMN && N != 15)
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the register-column variant is built for N == 15");
+    if (variant == CLB_VARIANT_LANE_PAIR && !pair_variant_applies(h))
+        return fail(CLB_ERR_INVALID,
+                    "clb_implicit_step: the lane-pair variant needs N = 15 or 16, CLB_MATH_FAST, column-fastest mirrors and flux "
+                    "boundary conditions");
     if (variant == CLB_VARIANT_LANE_PER_CELL && N > 31)
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the lane-per-cell variant needs N <= 31");
     if (variant == CLB_VARIANT_GENERIC) TRY(ensure_work(h, eh ? 6 : 3));
+    h->last_variant = variant;
     if (h->out_of_place) {
         TRY(alloc_fields(h, {CLB_F_U_THETA_L, CLB_F_U_INTF_W}));
         if (eh) TRY(alloc_fields(h, {CLB_F_U_RHO_E_INT, CLB_F_U_INTF_E}));
@@ -826,7 +962,10 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     nvtxRangePushA("implicit_step!");
     int iters_done = max_iters;
     if (fixed) {
-        if (variant == CLB_VARIANT_LANE_PER_CELL) {
+        if (variant == CLB_VARIANT_LANE_PAIR) {
+            if (N == 15) TRY(launch_pair_n<15>(h, P, dtgamma, max_iters));
+            else TRY(launch_pair_n<16>(h, P, dtgamma, max_iters));
+        } else if (variant == CLB_VARIANT_LANE_PER_CELL) {
             const int cpw = (N <= 15) ? 2 : 1;  // columns per warp (one lane of each segment is a ghost)
             const int64_t warps = (P.ncol + cpw - 1) / cpw;
             const unsigned wgrid = (unsigned)((warps * 32 + kBlock - 1) / kBlock);
@@ -901,6 +1040,14 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters, cons
         TRY(clb_get_field(h, out_fields[j], out_ptrs[j], 1, cell ? N : 1, CLB_HOST));
     }
     return clb_sync(h);
+}
+
+int clb_last_variant(clb_handle h, int32_t *variant)
+{
+    TRY(check_handle(h));
+    if (!variant) return fail(CLB_ERR_INVALID, "clb_last_variant: null output");
+    *variant = h->last_variant;
+    return CLB_OK;
 }
 
 int clb_column_integral(clb_handle h, int32_t cell_field, int32_t col_field_out)

@@ -22,8 +22,9 @@ TOP_FLUX, TOP_MOISTURE_STATE = K["CLB_TOP_FLUX"], K["CLB_TOP_MOISTURE_STATE"]
 BOT_FLUX, BOT_FREE_DRAINAGE, BOT_MOISTURE_STATE = (K["CLB_BOT_FLUX"], K["CLB_BOT_FREE_DRAINAGE"],
                                                    K["CLB_BOT_MOISTURE_STATE"])
 MATH_FAST, MATH_LIBM = K["CLB_MATH_FAST"], K["CLB_MATH_LIBM"]
-VARIANT_AUTO, VARIANT_REGISTER_COLUMN, VARIANT_GENERIC, VARIANT_LANE_PER_CELL = (
-    K["CLB_VARIANT_AUTO"], K["CLB_VARIANT_REGISTER_COLUMN"], K["CLB_VARIANT_GENERIC"], K["CLB_VARIANT_LANE_PER_CELL"])
+VARIANT_AUTO, VARIANT_REGISTER_COLUMN, VARIANT_GENERIC, VARIANT_LANE_PER_CELL, VARIANT_LANE_PAIR = (
+    K["CLB_VARIANT_AUTO"], K["CLB_VARIANT_REGISTER_COLUMN"], K["CLB_VARIANT_GENERIC"], K["CLB_VARIANT_LANE_PER_CELL"],
+    K["CLB_VARIANT_LANE_PAIR"])
 LAYOUT_AUTO, LAYOUT_COLUMN_FASTEST, LAYOUT_LEVEL_FASTEST = (K["CLB_LAYOUT_AUTO"], K["CLB_LAYOUT_COLUMN_FASTEST"],
                                                             K["CLB_LAYOUT_LEVEL_FASTEST"])
 
@@ -154,6 +155,12 @@ class SoilColumnSolver:
             return dict(iterations=st.iterations, converged=bool(st.converged), dx_norm=st.dx_norm,
                         nan_count=st.nan_count)
         return None
+
+    def last_variant(self):
+        """CLB_VARIANT_* the last implicit_step launched (what VARIANT_AUTO resolved to)."""
+        v = C.c_int32(0)
+        check(self.L.clb_last_variant(self.h, C.byref(v)))
+        return int(v.value)
 
     def implicit_step_host(self, dtgamma, max_iters, inputs, outputs):
         """inputs / outputs: dict name -> contiguous float64 numpy array (reference layout,

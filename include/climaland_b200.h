@@ -77,7 +77,9 @@ enum { CLB_MATH_FAST = 0, CLB_MATH_LIBM = 1 };
 enum { CLB_VARIANT_AUTO = 0,
        CLB_VARIANT_REGISTER_COLUMN = 1, /* one thread per column, N = 15 in registers          */
        CLB_VARIANT_GENERIC = 2,         /* one thread per column, any N, scratch in HBM/L2      */
-       CLB_VARIANT_LANE_PER_CELL = 3    /* one lane per cell, shuffle stencil + cyclic reduction, N <= 31 */ };
+       CLB_VARIANT_LANE_PER_CELL = 3,   /* one lane per cell, shuffle stencil + cyclic reduction, N <= 31 */
+       CLB_VARIANT_LANE_PAIR = 4        /* two lanes per column (8 cells each), twisted Thomas, constants in
+                                           shared memory; N = 15 or 16, CLB_MATH_FAST, flux BCs         */ };
 /* layout of the library's per-cell mirrors (0 = let the library choose) */
 enum { CLB_LAYOUT_AUTO = 0,
        CLB_LAYOUT_COLUMN_FASTEST = 1,   /* element (i, c) at i*ld + c                              */
@@ -218,6 +220,9 @@ int clb_ldiv(clb_handle h);
  * ||dx||_2 <= tol over all columns of all ranks.  stats may be NULL; when it is
  * not, the call synchronises the stream to fill it. */
 int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double tol, clb_stats *stats);
+
+/* CLB_VARIANT_* the last clb_implicit_step launched (what CLB_VARIANT_AUTO resolved to; 0 before the first step). */
+int clb_last_variant(clb_handle h, int32_t *variant);
 
 /* Host-buffer convenience for the end-to-end path: upload the per-step inputs
  * (state and lagged cache, level-fastest host arrays with column stride N),
