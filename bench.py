@@ -174,7 +174,8 @@ KERNEL_NAMES = {
     1: "k_eh_step_reg<vanGenuchten, fast, 15> (thread per column)",
     2: "k_eh_step_generic<vanGenuchten, fast> (thread per column, scratch in HBM)",
     3: "k_step_warp<vanGenuchten, fast, EnergyHydrology, 16 lanes/column>",
-    4: "k_step_pair<vanGenuchten, EnergyHydrology, 15> (2 lanes/column, twisted Thomas, constants in shared memory)",
+    4: "k_step_lanes<vanGenuchten, EnergyHydrology, 15, quad> (4 lanes/column, twisted Thomas, TMA-staged constants in shared memory)",
+    5: "k_step_lanes<vanGenuchten, EnergyHydrology, 15, quad, pipelined> (persistent, 4 lanes/column, twisted Thomas, double-buffered TMA prefetch)",
 }
 
 

@@ -112,6 +112,7 @@ struct clb_handle_s {
     int last_variant = 0;      // kernel variant the last clb_implicit_step launched
     clb::PairMaps pair_maps;   // TMA descriptors of the lane-pair kernel's inputs and the mirrors they describe
     const double *pair_map_src[14] = {};
+    int pair_map_box = 0;      // columns per TMA box those descriptors were encoded for
     double *field[CLB_F_NUM] = {};
     bool field_set[CLB_F_NUM] = {};
     // grid
@@ -299,7 +300,7 @@ clb::GridConst<NS> make_grid_const(clb_handle h)
     return g;
 }
 
-// Grid constants of the lane-pair kernel in its lane-local orientation (soil_pair.cuh):
+// Grid constants of the lane-quad kernel in its lane-local orientation (soil_pair.cuh):
 // bottom half slot q = level q, top half slot q = level 15 - q (pads for levels >= N).
 clb::PairGrid make_pair_grid(clb_handle h, double dtg)
 {
@@ -344,14 +345,14 @@ int encode_tiled_fn(EncodeTiledFn *out)
 }
 
 // TMA descriptor of one column-fastest per-cell mirror: dims {ncol, N} (columns beyond ncol read as 0),
-// row pitch ld doubles, box {16 columns, N levels}.
-int encode_field_map(clb_handle h, const double *ptr, CUtensorMap *map)
+// row pitch ld doubles, box {columns of one warp, N levels}.
+int encode_field_map(clb_handle h, const double *ptr, int box_columns, CUtensorMap *map)
 {
     EncodeTiledFn enc;
     TRY(encode_tiled_fn(&enc));
     const cuuint64_t dims[2] = {(cuuint64_t)h->cfg.n_columns, (cuuint64_t)h->cfg.n_levels};
     const cuuint64_t strides[1] = {(cuuint64_t)h->ld * sizeof(double)};
-    const cuuint32_t box[2] = {16, (cuuint32_t)h->cfg.n_levels};
+    const cuuint32_t box[2] = {(cuuint32_t)box_columns, (cuuint32_t)h->cfg.n_levels};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -360,8 +361,8 @@ int encode_field_map(clb_handle h, const double *ptr, CUtensorMap *map)
     return CLB_OK;
 }
 
-// Raw fields of the lane-pair kernel in the order of its shared-memory slots (soil_pair.cuh)
-int make_pair_maps(clb_handle h, const clb::DevView &P, clb::PairMaps *maps)
+// Raw fields of the lane-quad kernel in the order of its shared-memory slots (soil_pair.cuh)
+int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::PairMaps *maps)
 {
     const double *eh[14] = {P.nu, P.theta_r, P.S_s, P.hcm_a, P.hcm_b, P.hcm_m, P.Y_theta_l, P.is_sat, P.Y_theta_i,
                             P.rho_c_ds, P.K_lag, P.kappa_lag, P.theta_l_lag, P.Y_rho_e};
@@ -369,9 +370,11 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, clb::PairMaps *maps)
     const bool is_eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
     const int n = is_eh ? 14 : 9;
     const double **src = is_eh ? eh : ri;
+    if (h->pair_map_box != box_columns) std::fill(h->pair_map_src, h->pair_map_src + 14, nullptr);
+    h->pair_map_box = box_columns;
     for (int j = 0; j < n; ++j) {
         if (h->pair_map_src[j] != src[j]) {  // descriptors are cached per handle; mirrors rarely move
-            if (src[j]) TRY(encode_field_map(h, src[j], &h->pair_maps.m[j]));
+            if (src[j]) TRY(encode_field_map(h, src[j], box_columns, &h->pair_maps.m[j]));
             h->pair_map_src[j] = src[j];
         }
     }
@@ -379,37 +382,55 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, clb::PairMaps *maps)
     return CLB_OK;
 }
 
-template <int CLOSURE, int MODEL, int N>
-int launch_pair(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+// Lane-quad kernel (soil_pair.cuh, four lanes per column, four cells per lane), two launch shapes:
+//   PIPELINED  persistent, 2 blocks of 128 threads per SM, each warp double-buffers its tiles: 2 x 14 slots x 1 KB
+//              of shared memory per warp (3 of EnergyHydrology's 17 stage constants stay in registers);
+//   plain      one tile per warp, all constants in shared memory (17 KB per warp), 3 blocks per SM.
+template <int CLOSURE, int MODEL, int N, bool PIPELINED>
+int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 {
-    // every stage constant of Richards fits in shared memory; EnergyHydrology keeps 14 of 17 there
-    // (2 warps x 14 slots x 2 KB = 56 KB per 64-thread block: 4 blocks per SM)
-    constexpr int NS = (MODEL == 1) ? 14 : 10;
-    constexpr int BLOCK = (N == 16) ? 128 : CLB_PAIR_BLOCK;  // N == 16 has no free pad row for the per-warp mbarrier
-    auto kern = clb::k_step_pair<CLOSURE, MODEL, N, NS, BLOCK>;
-    const size_t smem = clb::pair_smem_bytes<NS, N, BLOCK>();
+    constexpr int PARTS = 2, BLOCK = 128;
+#ifndef CLB_QUAD_MINB
+#define CLB_QUAD_MINB 3
+#endif
+#ifndef CLB_QUAD_NS
+#define CLB_QUAD_NS 17
+#endif
+    constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 10;
+    constexpr int NBUF = PIPELINED ? 2 : 1;
+    constexpr int MINB = PIPELINED ? 2 : CLB_QUAD_MINB;
+    constexpr int CPW = clb::LaneGeom<PARTS>::CPW;
+    auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB>;
+    const size_t smem = clb::pair_smem_bytes<PARTS, NS, NBUF, BLOCK>();
     static bool configured = false;  // per instantiation
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    const int64_t warps = (P.ncol + 15) / 16;
-    const unsigned grid = (unsigned)((warps * 32 + BLOCK - 1) / BLOCK);
+    const int64_t tiles = (P.ncol + CPW - 1) / CPW;
+    int64_t blocks = (tiles * 32 + BLOCK - 1) / BLOCK;
+    if (PIPELINED) {
+        int sms = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        blocks = std::min<int64_t>(blocks, (int64_t)sms * MINB);
+    }
     const clb::PairGrid g = make_pair_grid(h, dtg);
     clb::PairMaps maps;
-    TRY(make_pair_maps(h, P, &maps));
-    kern<<<grid, BLOCK, smem, h->stream>>>(P, g, maps, dtg, max_iters);
+    TRY(make_pair_maps(h, P, CPW, &maps));
+    kern<<<(unsigned)blocks, BLOCK, smem, h->stream>>>(P, g, maps, dtg, max_iters);
     return CLB_OK;
 }
 
-template <int N>
-int launch_pair_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+template <int N, bool PIPELINED>
+int launch_quad_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 {
     const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
     const bool vg = h->cfg.closure == CLB_VAN_GENUCHTEN;
-    if (eh) return vg ? launch_pair<0, 1, N>(h, P, dtg, max_iters) : launch_pair<1, 1, N>(h, P, dtg, max_iters);
-    return vg ? launch_pair<0, 0, N>(h, P, dtg, max_iters) : launch_pair<1, 0, N>(h, P, dtg, max_iters);
+    if (eh)
+        return vg ? launch_quad<0, 1, N, PIPELINED>(h, P, dtg, max_iters)
+                  : launch_quad<1, 1, N, PIPELINED>(h, P, dtg, max_iters);
+    return vg ? launch_quad<0, 0, N, PIPELINED>(h, P, dtg, max_iters) : launch_quad<1, 0, N, PIPELINED>(h, P, dtg, max_iters);
 }
 
 bool pair_variant_applies(clb_handle h)
@@ -549,7 +570,7 @@ int clb_create(clb_handle *out, const clb_config *cfg)
         return fail(CLB_ERR_INVALID, "clb_create: unknown boundary condition kind");
     if (cfg->layout < CLB_LAYOUT_AUTO || cfg->layout > CLB_LAYOUT_LEVEL_FASTEST)
         return fail(CLB_ERR_INVALID, "clb_create: unknown layout %d", cfg->layout);
-    if (cfg->kernel_variant < CLB_VARIANT_AUTO || cfg->kernel_variant > CLB_VARIANT_LANE_PAIR)
+    if (cfg->kernel_variant < CLB_VARIANT_AUTO || cfg->kernel_variant > CLB_VARIANT_LANE_QUAD_PIPELINED)
         return fail(CLB_ERR_INVALID, "clb_create: unknown kernel_variant %d", cfg->kernel_variant);
     if (cfg->math_mode != CLB_MATH_FAST && cfg->math_mode != CLB_MATH_LIBM)
         return fail(CLB_ERR_INVALID, "clb_create: unknown math_mode %d", cfg->math_mode);
@@ -944,9 +965,9 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     }
     if (variant == CLB_VARIANT_REGISTER_COLUMN && N != 15)
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the register-column variant is built for N == 15");
-    if (variant == CLB_VARIANT_LANE_PAIR && !pair_variant_applies(h))
+    if ((variant == CLB_VARIANT_LANE_QUAD || variant == CLB_VARIANT_LANE_QUAD_PIPELINED) && !pair_variant_applies(h))
         return fail(CLB_ERR_INVALID,
-                    "clb_implicit_step: the lane-pair variant needs N = 15 or 16, CLB_MATH_FAST, column-fastest mirrors and flux "
+                    "clb_implicit_step: the lane-quad variants need N = 15 or 16, CLB_MATH_FAST, column-fastest mirrors and flux "
                     "boundary conditions");
     if (variant == CLB_VARIANT_LANE_PER_CELL && N > 31)
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the lane-per-cell variant needs N <= 31");
@@ -962,9 +983,12 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     nvtxRangePushA("implicit_step!");
     int iters_done = max_iters;
     if (fixed) {
-        if (variant == CLB_VARIANT_LANE_PAIR) {
-            if (N == 15) TRY(launch_pair_n<15>(h, P, dtgamma, max_iters));
-            else TRY(launch_pair_n<16>(h, P, dtgamma, max_iters));
+        if (variant == CLB_VARIANT_LANE_QUAD) {
+            if (N == 15) TRY((launch_quad_n<15, false>(h, P, dtgamma, max_iters)));
+            else TRY((launch_quad_n<16, false>(h, P, dtgamma, max_iters)));
+        } else if (variant == CLB_VARIANT_LANE_QUAD_PIPELINED) {
+            if (N == 15) TRY((launch_quad_n<15, true>(h, P, dtgamma, max_iters)));
+            else TRY((launch_quad_n<16, true>(h, P, dtgamma, max_iters)));
         } else if (variant == CLB_VARIANT_LANE_PER_CELL) {
             const int cpw = (N <= 15) ? 2 : 1;  // columns per warp (one lane of each segment is a ghost)
             const int64_t warps = (P.ncol + cpw - 1) / cpw;

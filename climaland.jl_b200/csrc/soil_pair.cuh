@@ -45,8 +45,11 @@
 
 namespace clb {
 
-constexpr int kPairQ = 8;  // cell slots per lane
-constexpr int kPairW = 4;  // cells evaluated together (interleaved dependency chains)
+constexpr int kPairQ = 8;  // cell slots per half column
+#ifndef CLB_PAIR_W
+#define CLB_PAIR_W 4
+#endif
+constexpr int kPairW = CLB_PAIR_W;  // cells evaluated together (interleaved dependency chains)
 
 // Per-launch grid constants in the lane-local orientation, [half][slot]; a kernel
 // parameter (constant bank), indexed with the lane's half at run time.
@@ -73,23 +76,23 @@ enum { R_THETA_R = 0, R_NU, R_CA, R_CA2, R_CB, R_INV_SS, R_CC, R_CD, R_KSAT, R_T
 enum { E_THETA_R = 0, E_NU_EFF, E_ICE, E_RCBASE, E_CA, E_KC, E_CB, E_INV_SS, E_CC, E_CD, E_AK, E_AC, E_DEN22, E_OD22,
        E_C22, E_T1, E_T2 };
 
-constexpr int kPairTileBytes = 16 * 16 * 8;  // one slot of a warp: 16 level rows x 16 columns
 
 // TMA descriptors of the raw fields (column-fastest mirrors: dims {ncol, N}, box {16, N})
 struct PairMaps {
     CUtensorMap m[14];
 };
 
-template <int NS, int NTOT>
+// Q cells per lane, CPW columns per warp: a slot of the warp tile is [16 level rows][CPW columns].
+template <int NS, int NTOT, int Q, int CPW>
 struct PairStore {
     double *base;  // warp tile + this lane's column
-    int half;
-    double r[(NTOT > NS) ? (NTOT - NS) : 1][kPairQ];
-    // level row of cell slot q: bottom half q, top half 15 - q
+    int half, r0;  // r0: first slot of this lane within its half (0, or Q for the inner lane of a quad)
+    double r[(NTOT > NS) ? (NTOT - NS) : 1][Q];
+    // level row of cell q: slot r0 + q of the half, counted from the column's boundary
     __device__ __forceinline__ double *at(int q, int slot) const
     {
-        const int row = half ? 15 - q : q;
-        return base + (slot * 16 + row) * 16;
+        const int row = half ? 15 - (r0 + q) : r0 + q;
+        return base + (slot * 16 + row) * CPW;
     }
     template <int SLOT>
     __device__ __forceinline__ double get(int q) const
@@ -109,7 +112,8 @@ struct PairStore {
     }
 };
 
-__device__ __forceinline__ double xchg(double v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
+template <int MASK>
+__device__ __forceinline__ double xchg(double v) { return __shfl_xor_sync(0xffffffffu, v, MASK); }
 
 // ---- TMA / mbarrier (sm_90+ PTX; one barrier per warp, single phase) -------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -174,114 +178,186 @@ __device__ __forceinline__ ClosureConst pair_prepare(const HydroCell &p, double 
 #ifndef CLB_PAIR_BLOCK
 #define CLB_PAIR_BLOCK 64
 #endif
-#ifndef CLB_PAIR_MIN_BLOCKS
-#define CLB_PAIR_MIN_BLOCKS 4
-#endif
 
-// Dynamic shared memory of a block: one NS-slot tile per warp [+ one mbarrier per warp when N == 16;
-// for N < 16 the barrier sits in the (never loaded) level-15 row of slot 0 until the pad constants
-// overwrite it].
-template <int NS, int N, int BLOCK>
-constexpr size_t pair_smem_bytes()
+// Lane geometry of a column split over 2 * PARTS lanes (PARTS = 1: lane pair, 2: lane quad).
+//   lane = column-in-warp + CPW * (half * PARTS + part);  part 0 touches the column boundary,
+//   part PARTS-1 the seam.  xor CPW swaps the two parts of a half, xor CPW*PARTS swaps the halves.
+template <int PARTS>
+struct LaneGeom {
+    static_assert(PARTS == 1 || PARTS == 2, "lane pair or lane quad");
+    static constexpr int LPC = 2 * PARTS;     // lanes per column
+    static constexpr int CPW = 32 / LPC;      // columns per warp
+    static constexpr int Q = kPairQ / PARTS;  // cells per lane
+    static constexpr int SEAM = CPW * PARTS;
+    static constexpr int kSlotBytes = 16 * CPW * 8;  // one slot of a warp tile: 16 level rows x CPW columns
+};
+
+// Values of the neighbours across lane boundaries: `inner` = neighbour of this lane's last cell
+// (the other half's last cell at the seam, else the first cell of the next part), `outer` =
+// neighbour of its first cell (last cell of the previous part; finite garbage for part 0, whose
+// outer face is the column boundary and carries a zero coefficient).
+template <int PARTS>
+__device__ __forceinline__ void nb_exchange(double first, double last, bool innermost, double &outer, double &inner)
 {
-    return (size_t)(BLOCK / 32) * NS * kPairTileBytes + ((N == 16 || BLOCK != 64) ? (BLOCK / 32) * 8 : 0);
+    using Gm = LaneGeom<PARTS>;
+    const double seam = xchg<Gm::SEAM>(last);
+    if (PARTS == 1) {
+        inner = seam;
+        outer = first;
+    } else {
+        const double nb_first = xchg<Gm::CPW>(first), nb_last = xchg<Gm::CPW>(last);
+        inner = innermost ? seam : nb_first;
+        outer = nb_last;
+    }
 }
 
-template <int CLOSURE, int MODEL, int N, int NS, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 64 ? CLB_PAIR_MIN_BLOCKS : 2))
-    k_step_pair(const DevView P, const PairGrid G, const __grid_constant__ PairMaps M, double dtg, int max_iters)
+// Dynamic shared memory of a block: NBUF NS-slot tiles and NBUF mbarriers per warp.
+template <int PARTS, int NS, int NBUF, int BLOCK>
+__host__ __device__ constexpr size_t pair_smem_bytes()
 {
-    static_assert(N >= 9 && N <= 16, "lane-pair kernel: 9 <= N <= 16");
-    constexpr int Q = kPairQ, W = kPairW;
-    constexpr int Q0T = 16 - N;  // first real slot of the top half (pads before it)
+    return (size_t)(BLOCK / 32) * NBUF * (NS * LaneGeom<PARTS>::kSlotBytes + 8);
+}
+
+// Per-column scalars of a tile, fetched one tile ahead into registers.
+struct ColScalars {
+    double Rss, hg, top_w, bot_w, Ress, top_h, bot_h, intF_w, intF_e;
+};
+template <int MODEL>
+__device__ __forceinline__ ColScalars load_col_scalars(const DevView &P, int64_t cs)
+{
+    ColScalars v;
+    v.Rss = P.R_ss[cs];
+    v.hg = P.h_grad[cs];
+    v.top_w = P.top_bc_w[cs];
+    v.bot_w = P.bot_bc_w[cs];
+    v.intF_w = P.Y_intF_w[cs];
+    v.Ress = v.top_h = v.bot_h = v.intF_e = 0.0;
+    if (MODEL == 1) {
+        v.Ress = P.R_ess[cs];
+        v.top_h = P.top_bc_h[cs];
+        v.bot_h = P.bot_bc_h[cs];
+        v.intF_e = P.Y_intF_e[cs];
+    }
+    return v;
+}
+
+// PERSISTENT: every warp walks over tiles (CPW columns each) t = warp, warp + nwarps, ...; with
+// NBUF = 2 the TMA boxes and the per-column scalars of the next tile are requested before the
+// current tile is touched, so HBM latency hides behind a whole tile of FP64 work.
+template <int CLOSURE, int MODEL, int N, int PARTS, int NS, int NBUF, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    k_step_lanes(const DevView P, const PairGrid G, const __grid_constant__ PairMaps M, double dtg, int max_iters)
+{
+    using Gm = LaneGeom<PARTS>;
+    constexpr int Q = Gm::Q, CPW = Gm::CPW, W = (Q < kPairW) ? Q : kPairW;
+    constexpr int Q0T = 16 - N;  // first real slot of the top half (pads before it, all in part 0)
+    static_assert(N <= 16 && Q0T < Q, "lane-pair kernel: 9 <= N <= 16, lane-quad kernel: 13 <= N <= 16");
+    static_assert(NBUF == 1 || NBUF == 2, "single or double buffered");
     constexpr int NTOT = PairSlots<MODEL>::kConst, NRAW = PairSlots<MODEL>::kRaw;
     static_assert(NS >= NRAW && NS <= NTOT, "the raw fields are staged in the shared-memory slots");
     extern __shared__ __align__(128) unsigned char pair_sm[];
 
-    const int tid = threadIdx.x, lane = tid & 31, half = lane >> 4, wib = tid >> 5;
-    const int64_t warp = ((int64_t)blockIdx.x * BLOCK + tid) >> 5;
-    if (warp * 16 >= P.ncol) return;  // whole warp
-    const int64_t c = warp * 16 + (lane & 15);
-    const bool col_ok = c < P.ncol;
-    const int64_t cs = col_ok ? c : P.ncol - 1;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int idx = lane / CPW, half = idx / PARTS, part = idx % PARTS;
+    const int r0 = part * Q;
+    const bool innermost = (part == PARTS - 1), outermost = (part == 0);
+    const int64_t warp0 = ((int64_t)blockIdx.x * BLOCK + tid) >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    const int64_t ntiles = (P.ncol + CPW - 1) / CPW;
+    if (warp0 >= ntiles) return;  // whole warp
     const EarthConst &E = P.earth;
     const double C1 = E.cp_l * E.rho_l, C2 = E.cp_i * E.rho_i, T_ref = E.T_ref;
 
-    double *tile = reinterpret_cast<double *>(pair_sm + (size_t)wib * NS * kPairTileBytes);
-    PairStore<NS, NTOT> S;
-    S.base = tile + (lane & 15);
+    constexpr size_t kTileBytes = (size_t)NS * Gm::kSlotBytes;
+    unsigned char *const tiles = pair_sm + (size_t)wib * NBUF * kTileBytes;
+    const unsigned bar0 = smem_u32(pair_sm + (size_t)(BLOCK / 32) * NBUF * kTileBytes + (size_t)wib * NBUF * 8);
+    PairStore<NS, NTOT, Q, CPW> S;
     S.half = half;
+    S.r0 = r0;
+    auto level_of = [&](int q) { return half ? 15 - (r0 + q) : r0 + q; };
+    auto col_of = [&](int64_t t) { return t * CPW + (lane % CPW); };
+    auto col_clamped = [&](int64_t t) { const int64_t c_ = col_of(t); return c_ < P.ncol ? c_ : P.ncol - 1; };
 
-    // ---- every per-cell field of the stage: HBM -> shared memory, one TMA box per field --------
-    const unsigned bar = (N == 16 || BLOCK != 64) ? smem_u32(pair_sm + (size_t)(BLOCK / 32) * NS * kPairTileBytes + wib * 8)
-                                   : smem_u32(tile + 15 * 16);
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (unsigned)(NRAW - ((CLOSURE == kVanGenuchten) ? 0 : 1)) * N * 16 * 8);
-    }
-    __syncwarp();
-    {
+    // every per-cell field of a tile: HBM -> shared memory, one TMA box per field
+    auto request_tile = [&](int64_t t, int buf) {
+        const unsigned bar = bar0 + buf * 8;
+        if (lane == 0) mbar_expect_tx(bar, (unsigned)(NRAW - ((CLOSURE == kVanGenuchten) ? 0 : 1)) * N * CPW * 8);
+        __syncwarp();
         const bool skip = (CLOSURE != kVanGenuchten) && lane == ((MODEL == 1) ? 5 : 6);  // no m field for Brooks-Corey
         if (lane < NRAW && !skip)
-            tma_load_2d(smem_u32(tile) + lane * kPairTileBytes, &M.m[lane], (int)(warp * 16), 0, bar);
-    }
+            tma_load_2d(smem_u32(tiles + buf * kTileBytes) + lane * Gm::kSlotBytes, &M.m[lane], (int)(t * CPW), 0, bar);
+    };
 
-    // ---- per-column scalars (overlap the copies) ---------------------------------------------
-    const double ld_Rss = P.R_ss[cs], ld_hg = P.h_grad[cs];
-    const double top_w = P.top_bc_w[cs], bot_w = P.bot_bc_w[cs];
-    double ld_Ress = 0.0, top_h = 0.0, bot_h = 0.0;
-    if (MODEL == 1) {
-        ld_Ress = P.R_ess[cs];
-        top_h = P.top_bc_h[cs];
-        bot_h = P.bot_bc_h[cs];
+    if (lane == 0) {
+#pragma unroll
+        for (int b_ = 0; b_ < NBUF; ++b_) mbar_init(bar0 + b_ * 8, 1);
     }
+    __syncwarp();
+    request_tile(warp0, 0);
+    ColScalars nxt = load_col_scalars<MODEL>(P, col_clamped(warp0));
+
+    double dx2_acc = 0.0, bad = 0.0;
+    unsigned phase = 0;  // bit b: parity the next wait on buffer b expects
+    int buf = 0;
+#pragma unroll 1
+    for (int64_t tile_id = warp0; tile_id < ntiles; tile_id += nwarps) {
+    const int64_t c = col_of(tile_id);
+    const bool col_ok = c < P.ncol;
+    const ColScalars cur = nxt;
+    if (NBUF == 2) {
+        const int64_t tn = tile_id + nwarps;
+        if (tn < ntiles) {
+            // the other buffer held the previous tile's constants (generic-proxy accesses): order them
+            // before the async-proxy writes of the TMA
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            request_tile(tn, buf ^ 1);
+            nxt = load_col_scalars<MODEL>(P, col_clamped(tn));
+        }
+    }
+    S.base = reinterpret_cast<double *>(tiles + buf * kTileBytes) + (lane % CPW);
+
+    const double ld_Rss = cur.Rss, ld_hg = cur.hg;
+    const double top_w = cur.top_w, bot_w = cur.bot_w;
+    const double ld_Ress = cur.Ress, top_h = cur.top_h, bot_h = cur.bot_h;
     const double inv_hg = fm::rcp(fmax(ld_hg, kEps));
     const double src_w = ld_Rss * inv_hg, src_e = ld_Ress * inv_hg;
-    // boundary flux of this half in the inward convention; it enters at face 0 (bottom half,
-    // top half when N == 16) or at face Q0T (top half with pads)
+    // boundary flux of this half in the inward convention; it enters at face 0 of part 0 (bottom
+    // half, top half when N == 16) or at face Q0T of part 0 (top half with pads)
     const double bin_w = half ? -top_w : bot_w, bin_e = half ? -top_h : bot_h;
-    const double b0_w = (half && Q0T > 0) ? 0.0 : bin_w, b0_e = (half && Q0T > 0) ? 0.0 : bin_e;
-    const double bT_w = half ? bin_w : 0.0, bT_e = half ? bin_e : 0.0;  // used at face Q0T > 0 only
+    const bool at0 = outermost && !(half && Q0T > 0), atT = outermost && half;
+    const double b0_w = at0 ? bin_w : 0.0, b0_e = at0 ? bin_e : 0.0;
+    const double bT_w = atT ? bin_w : 0.0, bT_e = atT ? bin_e : 0.0;  // used at face Q0T > 0 only
 
     // flux integrals (W = -I, lagged boundary fluxes): their Newton recurrence does not depend on
     // the iterate, so it runs here, off the hot loop (one lane per column stores it)
     double dx2_int = 0.0;
     {
-        const double tiw = P.Y_intF_w[cs];
-        const double Tiw = -(top_w - bot_w) - ld_Rss;
-        double Uw = tiw, dxw = 0.0, Ue = 0.0, dxe = 0.0, tie = 0.0, Tie = 0.0;
-        if (MODEL == 1) {
-            tie = P.Y_intF_e[cs];
-            Tie = -(top_h - bot_h) - ld_Ress;
-            Ue = tie;
-        }
+        const double tiw = cur.intF_w, tie = cur.intF_e;
+        const double Tiw = -(top_w - bot_w) - ld_Rss, Tie = -(top_h - bot_h) - ld_Ress;
+        double Uw = tiw, dxw = 0.0, Ue = tie, dxe = 0.0;
         for (int it = 0; it < max_iters; ++it) {
             dxw = -(tiw + dtg * Tiw - Uw);
             Uw -= dxw;
             dxe = -(tie + dtg * Tie - Ue);
             Ue -= dxe;
         }
-        if (half == 0 && col_ok) {
+        if (idx == 0 && col_ok) {
             dx2_int = dxw * dxw + dxe * dxe;
             P.out_intF_w[c] = Uw;
             if (MODEL == 1) P.out_intF_e[c] = Ue;
         }
     }
 
-    mbar_wait(bar, 0);
-    __syncwarp();  // nobody polls the barrier any more
-    if (N < 16 && BLOCK == 64) {  // its bytes are about to be overwritten by the pad constants
-        if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-        __syncwarp();
-    }
+    mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u);
+    phase ^= 1u << buf;
 
     // ---- set-up: transform the raw fields in place into the stage constants ------------------
     double U1[Q], U2[Q];
-    double aK8 = 0.0, aC8 = 0.0, r22 = 0.0, c22_7 = 0.0;
+    double aK8 = 0.0, aC8 = 0.0, r22 = 0.0, c22_last = 0.0;  // inner face of the last cell; seam of W22
     if (MODEL == 0) {
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            const bool real = (half ? 15 - q : q) < N;
+            const bool real = level_of(q) < N;
             HydroCell hc;
             hc.nu = S.template get<0>(q); hc.theta_r = S.template get<1>(q); hc.K_sat = S.template get<2>(q);
             hc.S_s = S.template get<3>(q); hc.a = S.template get<4>(q); hc.b = S.template get<5>(q);
@@ -305,27 +381,27 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 64 ? CLB_PAIR_MIN_BLOCKS : 2)
             S.template put<R_T1>(q, fma(-dtg, src_w * sat, theta));
         }
     } else {
-        // rolling window over q-1, q, q+1 of the lagged fields that couple neighbours
-        auto lagged = [&](int q, double &K, double &kap, double &rc) {
-            const bool real = (half ? 15 - q : q) < N;
-            K = real ? S.template get<10>(q) : 0.0;
-            kap = real ? S.template get<11>(q) : 0.0;
-            // Jacobian uses the LAGGED theta_l for rho_c_s (energy_hydrology.jl:561-566)
-            rc = fm::rcp(volumetric_heat_capacity(real ? S.template get<12>(q) : 0.0, real ? S.template get<8>(q) : 0.0,
-                                                  real ? S.template get<9>(q) : 1e6, E));
-        };
-        double K_m = 0.0, kap_m = 0.0, rc_m = 0.0, K_0, kap_0, rc_0, K_p = 0.0, kap_p = 0.0, rc_p = 0.0;
-        lagged(0, K_0, kap_0, rc_0);
-        double K7 = 0.0, kap7 = 0.0, rc7 = 0.0;
-        lagged(Q - 1, K7, kap7, rc7);
-        const double K7p = xchg(K7), kap7p = xchg(kap7), rc7p = xchg(rc7);
-        aK8 = (K7 + K7p) * G.hidzf[half][Q];
-        aC8 = (kap7 + kap7p) * G.hidzf[half][Q];
-        double cprev = 0.0;
+        // lagged fields that couple neighbours: K, kappa and 1/rho_c_s at the LAGGED theta_l
+        // (the Jacobian's choice, energy_hydrology.jl:561-566)
+        double Kl[Q], kap[Q], rc[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            const bool real = (half ? 15 - q : q) < N;
-            if (q < Q - 1) lagged(q + 1, K_p, kap_p, rc_p);
+            const bool real = level_of(q) < N;
+            Kl[q] = real ? S.template get<10>(q) : 0.0;
+            kap[q] = real ? S.template get<11>(q) : 0.0;
+            rc[q] = fm::rcp(volumetric_heat_capacity(real ? S.template get<12>(q) : 0.0, real ? S.template get<8>(q) : 0.0,
+                                                     real ? S.template get<9>(q) : 1e6, E));
+        }
+        double K_out, K_in, kap_out, kap_in, rc_out, rc_in;
+        nb_exchange<PARTS>(Kl[0], Kl[Q - 1], innermost, K_out, K_in);
+        nb_exchange<PARTS>(kap[0], kap[Q - 1], innermost, kap_out, kap_in);
+        nb_exchange<PARTS>(rc[0], rc[Q - 1], innermost, rc_out, rc_in);
+        aK8 = (Kl[Q - 1] + K_in) * G.hidzf[half][r0 + Q];
+        aC8 = (kap[Q - 1] + kap_in) * G.hidzf[half][r0 + Q];
+        double aCo[Q], o22[Q], d22[Q], i22[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const bool real = level_of(q) < N;
             HydroCell hc;
             hc.nu = S.template get<0>(q); hc.theta_r = S.template get<1>(q); hc.K_sat = 0.0;
             hc.S_s = S.template get<2>(q); hc.a = S.template get<3>(q); hc.b = S.template get<4>(q);
@@ -340,45 +416,62 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 64 ? CLB_PAIR_MIN_BLOCKS : 2)
             const ClosureConst cc = pair_prepare<CLOSURE>(hc, nu_eff);
             U1[q] = theta;
             U2[q] = rho_e;
-            // lagged face coefficients and the row of W22 = dtgamma d(T_rho_e)/d(rho_e) - I, eliminated on the fly
-            const double hid_o = G.hidzf[half][q], dti = G.dti[half][q];
-            const double aK_o = (q == 0) ? 0.0 : (K_0 + K_m) * hid_o;
-            const double aC_o = (q == 0) ? 0.0 : (kap_0 + kap_m) * hid_o;
-            const double aC_in = (q < Q - 1) ? (kap_0 + kap_p) * G.hidzf[half][q + 1] : aC8;
-            const double o = (q == 0) ? 0.0 : (aC_o * rc_m) * dti;
-            const double i = (aC_in * ((q < Q - 1) ? rc_p : rc7p)) * dti;
-            const double d = fma(-((aC_in + aC_o) * rc_0), dti, -1.0);
-            const double den = fm::rcp(fma(-o, cprev, d));
-            cprev = i * den;
+            // lagged coefficients of the cell's outer face (zero table entry at the column boundary)
+            const double hid_o = G.hidzf[half][r0 + q];
+            const double aK_o = (Kl[q] + ((q == 0) ? K_out : Kl[q - 1])) * hid_o;
+            aCo[q] = (kap[q] + ((q == 0) ? kap_out : kap[q - 1])) * hid_o;
             S.template put<E_THETA_R>(q, hc.theta_r);
             S.template put<E_NU_EFF>(q, nu_eff);
             S.template put<E_ICE>(q, theta_i * E.rho_i * E.LH_f0);
             S.template put<E_RCBASE>(q, fma(theta_i, C2, rcds));
             S.template put<E_CA>(q, cc.ca);
-            S.template put<E_KC>(q, K_0 * C1);
+            S.template put<E_KC>(q, Kl[q] * C1);
             S.template put<E_CB>(q, cc.cb);
             S.template put<E_INV_SS>(q, cc.inv_Ss);
             S.template put<E_CC>(q, cc.cc);
             S.template put<E_CD>(q, cc.cd);
             S.template put<E_AK>(q, aK_o);
-            S.template put<E_AC>(q, aC_o);
-            S.template put<E_DEN22>(q, den);
-            S.template put<E_OD22>(q, o * den);
-            S.template put<E_C22>(q, cprev);
+            S.template put<E_AC>(q, aCo[q]);
             S.template put<E_T1>(q, fma(-dtg, src_w * sat, theta));
             S.template put<E_T2>(q, fma(-dtg, src_e * sat, rho_e));
-            K_m = K_0; kap_m = kap_0; rc_m = rc_0;
-            K_0 = K_p; kap_0 = kap_p; rc_0 = rc_p;
         }
-        c22_7 = cprev;
-        r22 = fm::rcp(fma(-c22_7, xchg(c22_7), 1.0));
+        // rows of W22 = dtgamma d(T_rho_e)/d(rho_e) - I and their elimination, boundary -> seam
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double dti = G.dti[half][r0 + q];
+            const double aC_in = (q < Q - 1) ? aCo[q + 1] : aC8;
+            o22[q] = (aCo[q] * ((q == 0) ? rc_out : rc[q - 1])) * dti;
+            i22[q] = (aC_in * ((q < Q - 1) ? rc[q + 1] : rc_in)) * dti;
+            d22[q] = fma(-((aC_in + aCo[q]) * rc[q]), dti, -1.0);
+        }
+        double cin = 0.0;
+#pragma unroll
+        for (int pass = 0; pass < PARTS; ++pass) {
+            double cp = cin;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double den = fm::rcp(fma(-o22[q], cp, d22[q]));
+                cp = i22[q] * den;
+                if (pass == PARTS - 1) {
+                    S.template put<E_DEN22>(q, den);
+                    S.template put<E_OD22>(q, o22[q] * den);
+                    S.template put<E_C22>(q, cp);
+                }
+            }
+            c22_last = cp;
+            if (pass + 1 < PARTS) {
+                const double rc_ = xchg<CPW>(cp);
+                cin = outermost ? 0.0 : rc_;
+            }
+        }
+        r22 = fm::rcp(fma(-c22_last, xchg<Gm::SEAM>(c22_last), 1.0));
     }
 
     // ---- Newton iterations -----------------------------------------------------------------
     double dx2 = 0.0;
 #pragma unroll 1
     for (int it = 0; it < max_iters; ++it) {
-        // cache_imp!: closures (and temperature) at the iterate, four cells at a time
+        // cache_imp!: closures (and temperature) at the iterate, W cells at a time
         double h[Q], dps[Q], Kc[Q], Td[Q], eK[Q];
 #pragma unroll
         for (int g = 0; g < Q; g += W) {
@@ -431,59 +524,65 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 64 ? CLB_PAIR_MIN_BLOCKS : 2)
             fmv::closure<CLOSURE, MODEL == 0, W>(th, thr, nue, ca, ca2, cb, ccc, cd, iSs, Ksat, K, psi, dp);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                h[g + j] = psi[j] + G.z[half][g + j];
+                h[g + j] = psi[j] + G.z[half][r0 + g + j];
                 dps[g + j] = dp[j];
                 if (MODEL == 0) Kc[g + j] = K[j];
             }
         }
-        const double h7p = xchg(h[Q - 1]), dps7p = xchg(dps[Q - 1]);
-        double K7p = 0.0, T7p = 0.0, eK7p = 0.0;
-        if (MODEL == 0) K7p = xchg(Kc[Q - 1]);
+        double h_out, h_in, dps_out, dps_in, K_out = 0.0, K_in = 0.0, T_out = 0.0, T_in = 0.0, eK_out = 0.0, eK_in = 0.0;
+        nb_exchange<PARTS>(h[0], h[Q - 1], innermost, h_out, h_in);
+        nb_exchange<PARTS>(dps[0], dps[Q - 1], innermost, dps_out, dps_in);
+        if (MODEL == 0) nb_exchange<PARTS>(Kc[0], Kc[Q - 1], innermost, K_out, K_in);
         if (MODEL == 1) {
-            T7p = xchg(Td[Q - 1]);
-            eK7p = xchg(eK[Q - 1]);
+            nb_exchange<PARTS>(Td[0], Td[Q - 1], innermost, T_out, T_in);
+            nb_exchange<PARTS>(eK[0], eK[Q - 1], innermost, eK_out, eK_in);
         }
 
-        // T_imp!, Wfact and the forward elimination of W11, boundary -> seam
-        double c1[Q], g1[Q], f2[Q], aE[Q + 1];
-        double Fw_o = b0_w, Fe_o = b0_e, aK_o = 0.0;
-        double cprev = 0.0, gprev = 0.0;
-        aE[0] = 0.0;
+        // T_imp! and Wfact: face fluxes, residuals and the rows of W11 = dtgamma dT/dtheta - I
+        double o1[Q], d1[Q], i1[Q], f1[Q], f2[Q], aE[Q + 1];
+        double Fw_o, Fe_o = 0.0, aK_o;
+        {
+            // outer face of the first cell: the column boundary (zero coefficient, boundary flux)
+            // or, for an inner part, the face shared with the previous part
+            const double hid_o = G.hidzf[half][r0];
+            const double dh0 = h[0] - h_out;
+            aK_o = (MODEL == 1) ? S.template get<E_AK>(0) : (Kc[0] + K_out) * hid_o;
+            Fw_o = b0_w - aK_o * dh0;
+            aE[0] = 0.0;
+            if (MODEL == 1) {
+                aE[0] = (eK[0] + eK_out) * hid_o;
+                Fe_o = fma(-S.template get<E_AC>(0), Td[0] - T_out, b0_e - aE[0] * dh0);
+            }
+        }
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            const double dti = G.dti[half][q];
-            const double hid_in = G.hidzf[half][q + 1];
-            const double h_in = (q < Q - 1) ? h[q + 1] : h7p;
-            const double dps_in = (q < Q - 1) ? dps[q + 1] : dps7p;
-            const double dh = h_in - h[q];
+            const double dti = G.dti[half][r0 + q];
+            const double hid_in = G.hidzf[half][r0 + q + 1];
+            const double hn = (q < Q - 1) ? h[q + 1] : h_in;
+            const double dpn = (q < Q - 1) ? dps[q + 1] : dps_in;
+            const double dh = hn - h[q];
             double aK_in, aC_in = 0.0;  // coefficients of the inner face
             if (MODEL == 1) {
                 aK_in = (q < Q - 1) ? S.template get<E_AK>(q + 1) : aK8;
                 aC_in = (q < Q - 1) ? S.template get<E_AC>(q + 1) : aC8;
             } else {
-                aK_in = (Kc[q] + ((q < Q - 1) ? Kc[q + 1] : K7p)) * hid_in;
+                aK_in = (Kc[q] + ((q < Q - 1) ? Kc[q + 1] : K_in)) * hid_in;
             }
             double Fw_in = -(aK_in * dh);
             if (Q0T > 0 && q + 1 == Q0T) Fw_in += bT_w;
             double t1;
             if (MODEL == 0) t1 = S.template get<R_T1>(q);
             else t1 = S.template get<E_T1>(q);
-            const double f1 = fma(Fw_o - Fw_in, dti, t1) - U1[q];
-            // row of W11 = dtgamma dT/dtheta - I in the lane-local orientation
-            const double o = (q == 0) ? 0.0 : (aK_o * dps[q - 1]) * dti;
-            const double i = (aK_in * dps_in) * dti;
-            const double d = fma(-((aK_in + aK_o) * dps[q]), dti, -1.0);
-            const double den = fm::rcp(fma(-o, cprev, d));
-            cprev = i * den;
-            gprev = fma(-o, gprev, f1) * den;
-            c1[q] = cprev;
-            g1[q] = gprev;
+            f1[q] = fma(Fw_o - Fw_in, dti, t1) - U1[q];
+            o1[q] = (aK_o * ((q == 0) ? dps_out : dps[q - 1])) * dti;
+            i1[q] = (aK_in * dpn) * dti;
+            d1[q] = fma(-((aK_in + aK_o) * dps[q]), dti, -1.0);
             if (MODEL == 1) {
-                const double T_in = (q < Q - 1) ? Td[q + 1] : T7p;
-                const double eK_in = (q < Q - 1) ? eK[q + 1] : eK7p;
-                const double aE_in = (eK[q] + eK_in) * hid_in;
+                const double Tn = (q < Q - 1) ? Td[q + 1] : T_in;
+                const double eKn = (q < Q - 1) ? eK[q + 1] : eK_in;
+                const double aE_in = (eK[q] + eKn) * hid_in;
                 aE[q + 1] = aE_in;
-                double Fe_in = fma(-aC_in, T_in - Td[q], -(aE_in * dh));
+                double Fe_in = fma(-aC_in, Tn - Td[q], -(aE_in * dh));
                 if (Q0T > 0 && q + 1 == Q0T) Fe_in += bT_e;
                 f2[q] = fma(Fe_o - Fe_in, dti, S.template get<E_T2>(q)) - U2[q];
                 Fe_o = Fe_in;
@@ -491,12 +590,40 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 64 ? CLB_PAIR_MIN_BLOCKS : 2)
             Fw_o = Fw_in;
             aK_o = aK_in;
         }
-        // seam: x_7 + c_7 x'_7 = g_7 in both lanes
-        const double c7p = xchg(c1[Q - 1]), g7p = xchg(g1[Q - 1]);
-        double x1[Q], y[Q];
-        x1[Q - 1] = fma(-c1[Q - 1], g7p, g1[Q - 1]) * fm::rcp(fma(-c1[Q - 1], c7p, 1.0));
+
+        // ldiv! of W11: twisted Thomas, eliminated boundary -> seam (once per part, the carry crossing
+        // lanes in between), 2x2 seam system, back substitution seam -> boundary
+        double c1[Q], g1[Q], x1[Q], y[Q];
+        {
+            double cin = 0.0, gin = 0.0;
 #pragma unroll
-        for (int q = Q - 2; q >= 0; --q) x1[q] = fma(-c1[q], x1[q + 1], g1[q]);
+            for (int pass = 0; pass < PARTS; ++pass) {
+                double cp = cin, gp = gin;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const double den = fm::rcp(fma(-o1[q], cp, d1[q]));
+                    cp = i1[q] * den;
+                    gp = fma(-o1[q], gp, f1[q]) * den;
+                    c1[q] = cp;
+                    g1[q] = gp;
+                }
+                if (pass + 1 < PARTS) {
+                    const double rc_ = xchg<CPW>(cp), rg_ = xchg<CPW>(gp);
+                    cin = outermost ? 0.0 : rc_;
+                    gin = outermost ? 0.0 : rg_;
+                }
+            }
+            const double cs_ = xchg<Gm::SEAM>(c1[Q - 1]), gs_ = xchg<Gm::SEAM>(g1[Q - 1]);
+            const double xs = fma(-c1[Q - 1], gs_, g1[Q - 1]) * fm::rcp(fma(-c1[Q - 1], cs_, 1.0));
+            double xn = xs;  // value of the inner neighbour's unknown, seam value for the innermost part
+#pragma unroll
+            for (int pass = 0; pass < PARTS; ++pass) {
+                x1[Q - 1] = (pass == 0) ? xs : (innermost ? xs : fma(-c1[Q - 1], xn, g1[Q - 1]));
+#pragma unroll
+                for (int q = Q - 2; q >= 0; --q) x1[q] = fma(-c1[q], x1[q + 1], g1[q]);
+                if (pass + 1 < PARTS) xn = xchg<CPW>(x1[0]);
+            }
+        }
         const bool last = (it == max_iters - 1);
         if (last) {
             dx2 = 0.0;
@@ -510,39 +637,54 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 64 ? CLB_PAIR_MIN_BLOCKS : 2)
         }
         if (MODEL == 1) {
             // ldiv!: BlockLowerTriangularSolve(theta_l): b2 = f2 - W21 x1 with
-            // W21 = -dtgamma (D . Diag(interp(-e_l K)) . G . Diag(dpsi)) - I  (energy_hydrology.jl:545-556)
-            const double y7p = xchg(y[Q - 1]);
-            double g2[Q];
-            double g2prev = 0.0;
+            // W21 = -dtgamma (D . Diag(interp(-e_l K)) . G . Diag(dpsi)) - I  (energy_hydrology.jl:545-556),
+            // then the pre-factored W22
+            double y_out, y_in;
+            nb_exchange<PARTS>(y[0], y[Q - 1], innermost, y_out, y_in);
+            double b2[Q], g2[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const double dti = G.dti[half][q];
-                const double y_in = (q < Q - 1) ? y[q + 1] : y7p;
-                double acc = aE[q + 1] * (y_in - y[q]);
-                if (q > 0) acc = fma(aE[q], y[q - 1] - y[q], acc);
-                const double s = fma(dti, acc, -x1[q]);
-                const double b2 = f2[q] - s;
-                g2prev = fma(-S.template get<E_OD22>(q), g2prev, b2 * S.template get<E_DEN22>(q));
-                g2[q] = g2prev;
+                const double yn = (q < Q - 1) ? y[q + 1] : y_in;
+                const double yo = (q == 0) ? y_out : y[q - 1];
+                const double acc = fma(aE[q], yo - y[q], aE[q + 1] * (yn - y[q]));
+                const double s = fma(G.dti[half][r0 + q], acc, -x1[q]);
+                b2[q] = (f2[q] - s) * S.template get<E_DEN22>(q);
             }
-            const double g27p = xchg(g2[Q - 1]);
-            double x2 = fma(-c22_7, g27p, g2[Q - 1]) * r22;
-            U2[Q - 1] -= x2;
-            if (last) dx2 = fma(x2, x2, dx2);
+            double gin = 0.0;
 #pragma unroll
-            for (int q = Q - 2; q >= 0; --q) {
-                x2 = fma(-S.template get<E_C22>(q), x2, g2[q]);
-                U2[q] -= x2;
-                if (last) dx2 = fma(x2, x2, dx2);
+            for (int pass = 0; pass < PARTS; ++pass) {
+                double gp = gin;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    gp = fma(-S.template get<E_OD22>(q), gp, b2[q]);
+                    g2[q] = gp;
+                }
+                if (pass + 1 < PARTS) {
+                    const double rg_ = xchg<CPW>(gp);
+                    gin = outermost ? 0.0 : rg_;
+                }
+            }
+            const double xs = fma(-c22_last, xchg<Gm::SEAM>(g2[Q - 1]), g2[Q - 1]) * r22;
+            double xn = xs, x2[Q];
+#pragma unroll
+            for (int pass = 0; pass < PARTS; ++pass) {
+                x2[Q - 1] = (pass == 0) ? xs : (innermost ? xs : fma(-c22_last, xn, g2[Q - 1]));
+#pragma unroll
+                for (int q = Q - 2; q >= 0; --q) x2[q] = fma(-S.template get<E_C22>(q), x2[q + 1], g2[q]);
+                if (pass + 1 < PARTS) xn = xchg<CPW>(x2[0]);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                U2[q] -= x2[q];
+                if (last) dx2 = fma(x2[q], x2[q], dx2);
             }
         }
     }
 
     // ---- write the new state -----------------------------------------------------------------
-    double bad = 0.0;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        const int level = half ? 15 - q : q;
+        const int level = level_of(q);
         if (level < N && col_ok) {
             const int64_t k = P.at(level, c);
             P.out_theta_l[k] = U1[q];
@@ -553,8 +695,16 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 64 ? CLB_PAIR_MIN_BLOCKS : 2)
             }
         }
     }
-    if (!col_ok) dx2 = 0.0;
-    accumulate_stats(P, dx2 + dx2_int, bad);
+    if (col_ok) dx2_acc += dx2 + dx2_int;
+    if (NBUF == 2) buf ^= 1;
+    else __syncwarp();
+    if (NBUF == 1 && tile_id + nwarps < ntiles) {  // single buffer: the next tile is requested only now
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        request_tile(tile_id + nwarps, 0);
+        nxt = load_col_scalars<MODEL>(P, col_clamped(tile_id + nwarps));
+    }
+    }  // tiles
+    accumulate_stats(P, dx2_acc, bad);
 }
 
 }  // namespace clb

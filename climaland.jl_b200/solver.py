@@ -22,9 +22,9 @@ TOP_FLUX, TOP_MOISTURE_STATE = K["CLB_TOP_FLUX"], K["CLB_TOP_MOISTURE_STATE"]
 BOT_FLUX, BOT_FREE_DRAINAGE, BOT_MOISTURE_STATE = (K["CLB_BOT_FLUX"], K["CLB_BOT_FREE_DRAINAGE"],
                                                    K["CLB_BOT_MOISTURE_STATE"])
 MATH_FAST, MATH_LIBM = K["CLB_MATH_FAST"], K["CLB_MATH_LIBM"]
-VARIANT_AUTO, VARIANT_REGISTER_COLUMN, VARIANT_GENERIC, VARIANT_LANE_PER_CELL, VARIANT_LANE_PAIR = (
+VARIANT_AUTO, VARIANT_REGISTER_COLUMN, VARIANT_GENERIC, VARIANT_LANE_PER_CELL, VARIANT_LANE_QUAD, VARIANT_LANE_QUAD_PIPELINED = (
     K["CLB_VARIANT_AUTO"], K["CLB_VARIANT_REGISTER_COLUMN"], K["CLB_VARIANT_GENERIC"], K["CLB_VARIANT_LANE_PER_CELL"],
-    K["CLB_VARIANT_LANE_PAIR"])
+    K["CLB_VARIANT_LANE_QUAD"], K["CLB_VARIANT_LANE_QUAD_PIPELINED"])
 LAYOUT_AUTO, LAYOUT_COLUMN_FASTEST, LAYOUT_LEVEL_FASTEST = (K["CLB_LAYOUT_AUTO"], K["CLB_LAYOUT_COLUMN_FASTEST"],
                                                             K["CLB_LAYOUT_LEVEL_FASTEST"])
 

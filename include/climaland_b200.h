@@ -78,8 +78,11 @@ enum { CLB_VARIANT_AUTO = 0,
        CLB_VARIANT_REGISTER_COLUMN = 1, /* one thread per column, N = 15 in registers          */
        CLB_VARIANT_GENERIC = 2,         /* one thread per column, any N, scratch in HBM/L2      */
        CLB_VARIANT_LANE_PER_CELL = 3,   /* one lane per cell, shuffle stencil + cyclic reduction, N <= 31 */
-       CLB_VARIANT_LANE_PAIR = 4        /* two lanes per column (8 cells each), twisted Thomas, constants in
-                                           shared memory; N = 15 or 16, CLB_MATH_FAST, flux BCs         */ };
+       CLB_VARIANT_LANE_QUAD = 4,       /* four lanes per column (4 cells each), twisted Thomas across the lanes,
+                                           TMA-staged stage constants in shared memory; N = 15 or 16,
+                                           CLB_MATH_FAST, flux BCs, column-fastest mirrors               */
+       CLB_VARIANT_LANE_QUAD_PIPELINED = 5 /* the same as a persistent kernel whose warps prefetch their next
+                                           tile (double-buffered shared memory)                          */ };
 /* layout of the library's per-cell mirrors (0 = let the library choose) */
 enum { CLB_LAYOUT_AUTO = 0,
        CLB_LAYOUT_COLUMN_FASTEST = 1,   /* element (i, c) at i*ld + c                              */
