@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -113,6 +114,10 @@ struct clb_handle_s {
     clb::PairMaps pair_maps;   // TMA descriptors of the lane-pair kernel's inputs and the mirrors they describe
     const double *pair_map_src[14] = {};
     int pair_map_box = 0;      // columns per TMA box those descriptors were encoded for
+    // prepared (reciprocal) mirrors of S_s / a / b / m read by the lane-quad kernels (soil_pair.cuh: k_prepare_params)
+    double *prep[4] = {};
+    bool prep_dirty = true;     // a parameter field changed since they were written
+    bool prep_volatile = false; // the caller holds a device pointer to a parameter mirror: re-prepare every stage
     double *field[CLB_F_NUM] = {};
     bool field_set[CLB_F_NUM] = {};
     // grid
@@ -361,12 +366,39 @@ int encode_field_map(clb_handle h, const double *ptr, int box_columns, CUtensorM
     return CLB_OK;
 }
 
-// Raw fields of the lane-quad kernel in the order of its shared-memory slots (soil_pair.cuh)
+inline bool is_closure_param(int field)
+{
+    return field == CLB_F_S_S || field == CLB_F_HCM_A || field == CLB_F_HCM_B || field == CLB_F_HCM_M;
+}
+
+// (Re)writes the prepared parameter mirrors when a parameter changed since the last stage.
+int ensure_prepared(clb_handle h, const clb::DevView &P)
+{
+    if (!h->prep_dirty && !h->prep_volatile) return CLB_OK;
+    for (auto &p : h->prep)
+        if (!p) CUDA_TRY(cudaMalloc(&p, h->cell_elems * sizeof(double)));
+    const int64_t n = (int64_t)h->cell_elems;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (h->cfg.closure == CLB_VAN_GENUCHTEN)
+        clb::k_prepare_params<0><<<grid, 256, 0, h->stream>>>(P.S_s, P.hcm_a, P.hcm_b, P.hcm_m, h->prep[0], h->prep[1],
+                                                              h->prep[2], h->prep[3], n);
+    else
+        clb::k_prepare_params<1><<<grid, 256, 0, h->stream>>>(P.S_s, P.hcm_a, P.hcm_b, nullptr, h->prep[0], h->prep[1],
+                                                              h->prep[2], h->prep[3], n);
+    CUDA_TRY(cudaGetLastError());
+    h->prep_dirty = false;
+    return CLB_OK;
+}
+
+// Fields of the lane-quad kernel in the order of its shared-memory slots (soil_pair.cuh); the closure
+// parameters S_s / a / b / m come from the prepared mirrors
 int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::PairMaps *maps)
 {
-    const double *eh[14] = {P.nu, P.theta_r, P.S_s, P.hcm_a, P.hcm_b, P.hcm_m, P.Y_theta_l, P.is_sat, P.Y_theta_i,
+    TRY(ensure_prepared(h, P));
+    const double *const *Q = h->prep;
+    const double *eh[14] = {P.nu, P.theta_r, Q[0], Q[1], Q[2], Q[3], P.Y_theta_l, P.is_sat, P.Y_theta_i,
                             P.rho_c_ds, P.K_lag, P.kappa_lag, P.theta_l_lag, P.Y_rho_e};
-    const double *ri[9] = {P.nu, P.theta_r, P.K_sat, P.S_s, P.hcm_a, P.hcm_b, P.hcm_m, P.Y_theta_l, P.is_sat};
+    const double *ri[9] = {P.nu, P.theta_r, P.K_sat, Q[0], Q[1], Q[2], Q[3], P.Y_theta_l, P.is_sat};
     const bool is_eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
     const int n = is_eh ? 14 : 9;
     const double **src = is_eh ? eh : ri;
@@ -383,13 +415,14 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::Pa
 }
 
 // Lane-quad kernel (soil_pair.cuh, four lanes per column, four cells per lane), two launch shapes:
-//   PIPELINED  persistent, 2 blocks of 128 threads per SM, each warp double-buffers its tiles: 2 x 14 slots x 1 KB
+//   PIPELINED  persistent, 1 block of 256 threads per SM, each warp double-buffers its tiles: 2 x 14 slots x 1 KB
 //              of shared memory per warp (3 of EnergyHydrology's 17 stage constants stay in registers);
 //   plain      one tile per warp, all constants in shared memory (17 KB per warp), 3 blocks per SM.
 template <int CLOSURE, int MODEL, int N, bool PIPELINED>
 int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 {
-    constexpr int PARTS = 2, BLOCK = 128;
+    // the pipelined shape is one 8-warp block per SM: 8 x 28 KB of tiles + the 2.5 KB of tables fill the 227 KB
+    constexpr int PARTS = 2, BLOCK = PIPELINED ? 256 : 128;
 #ifndef CLB_QUAD_MINB
 #define CLB_QUAD_MINB 3
 #endif
@@ -398,7 +431,7 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 #endif
     constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 10;
     constexpr int NBUF = PIPELINED ? 2 : 1;
-    constexpr int MINB = PIPELINED ? 2 : CLB_QUAD_MINB;
+    constexpr int MINB = PIPELINED ? 1 : CLB_QUAD_MINB;
     constexpr int CPW = clb::LaneGeom<PARTS>::CPW;
     auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB>;
     const size_t smem = clb::pair_smem_bytes<PARTS, NS, NBUF, BLOCK>();
@@ -410,7 +443,8 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
     }
     const int64_t tiles = (P.ncol + CPW - 1) / CPW;
     int64_t blocks = (tiles * 32 + BLOCK - 1) / BLOCK;
-    if (PIPELINED) {
+    static const bool persist = getenv("CLB_QUAD_PERSIST") != nullptr;
+    if (PIPELINED || persist) {
         int sms = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
         blocks = std::min<int64_t>(blocks, (int64_t)sms * MINB);
@@ -515,10 +549,17 @@ __global__ void __launch_bounds__(128) k_balance(const clb::DevView P, const dou
 // device-side evaluation of the soil_math.cuh functions, for the accuracy tests
 __global__ void k_test_math(int kind, const double *x, const double *y, double *out, int64_t n)
 {
+    __shared__ __align__(16) unsigned char tab_sm[clb::fmv::kMathTabBytes];
+    const clb::fmv::MathTab MT = clb::fmv::math_tab_fill(tab_sm, threadIdx.x);
+    __syncthreads();
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     double r = 0.0;
+    const double xv[1] = {x[k]};
+    double rv[1] = {0.0};
     switch (kind) {
+    case 6: clb::fmv::log_tab<1>(MT, xv, rv); r = rv[0]; break;
+    case 7: clb::fmv::exp_tab<1>(MT, xv, rv); r = rv[0]; break;
     case 0: r = clb::fm::rcp(x[k]); break;
     case 1: r = clb::fm::div(x[k], y[k]); break;
     case 2: r = clb::fm::log(x[k]); break;
@@ -591,8 +632,15 @@ int clb_create(clb_handle *out, const clb_config *cfg)
     h->ld = (cfg->n_columns + 31) / 32 * 32;
     int layout = cfg->layout;
     // lane-per-cell kernels read level-fastest mirrors, every column-per-thread(-pair) kernel column-fastest ones
-    if (layout == CLB_LAYOUT_AUTO)
-        layout = (cfg->n_levels <= 32) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
+    if (layout == CLB_LAYOUT_AUTO) {
+        const bool quad_ok = (cfg->n_levels == 15 || cfg->n_levels == 16) && cfg->math_mode == CLB_MATH_FAST &&
+                             !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
+                             (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_QUAD ||
+                              cfg->kernel_variant == CLB_VARIANT_LANE_QUAD_PIPELINED);
+        const bool lane_per_cell = cfg->n_levels <= 31 && (cfg->kernel_variant == CLB_VARIANT_AUTO ||
+                                                           cfg->kernel_variant == CLB_VARIANT_LANE_PER_CELL);
+        layout = (!quad_ok && lane_per_cell) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
+    }
     h->cfg.layout = layout;
     if (layout == CLB_LAYOUT_LEVEL_FASTEST) {
         h->sl = 1;
@@ -633,6 +681,7 @@ int clb_destroy(clb_handle h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (auto &p : h->field) cudaFree(p);
     for (auto &p : h->work) cudaFree(p);
+    for (auto &p : h->prep) cudaFree(p);
     cudaFree(h->carry);
     cudaFree(h->zeros_cell);
     cudaFree(h->zeros_col);
@@ -776,6 +825,7 @@ int clb_set_field(clb_handle h, int32_t field, const double *src, int64_t stride
     }
     CUDA_TRY(cudaGetLastError());
     h->field_set[field] = true;
+    if (is_closure_param(field)) h->prep_dirty = true;
     return CLB_OK;
 }
 
@@ -829,6 +879,7 @@ int clb_fill_field(clb_handle h, int32_t field, double value)
     clb::k_fill<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->field[field], n, value);
     CUDA_TRY(cudaGetLastError());
     h->field_set[field] = true;
+    if (is_closure_param(field)) h->prep_dirty = true;
     return CLB_OK;
 }
 
@@ -840,6 +891,7 @@ int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *str
     DeviceGuard guard(h->cfg.device);
     TRY(ensure_field(h, field));
     h->field_set[field] = true;  // the caller fills it in place
+    if (is_closure_param(field)) h->prep_volatile = true;
     *ptr = h->field[field];
     if (stride_level) *stride_level = is_cell_field(field) ? h->sl : 0;
     if (stride_column) *stride_column = is_cell_field(field) ? h->sc : 1;
@@ -956,7 +1008,9 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     if (!fixed) {
         variant = CLB_VARIANT_GENERIC;  // the tolerance path is one generic launch per iteration
     } else if (variant == CLB_VARIANT_AUTO) {
-        if (level_fast && N <= 31)
+        if (pair_variant_applies(h))
+            variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
+        else if (level_fast && N <= 31)
             variant = CLB_VARIANT_LANE_PER_CELL;
         else if (N == 15)
             variant = CLB_VARIANT_REGISTER_COLUMN;

@@ -9,6 +9,7 @@
 // Same algorithms, coefficients and rounding sequence per value as soil_math.cuh / CellEval.
 #pragma once
 #include "soil_closures.cuh"
+#include "soil_math_tables.cuh"
 
 namespace clb {
 namespace fmv {
@@ -126,13 +127,99 @@ __device__ __forceinline__ void exp_clamped(const double (&x)[W], double (&out)[
     }
 }
 
+// ---- table-driven log / exp (tables: soil_math_tables.cuh, copied to shared memory per block) -----
+// The closures use a logarithm only as (a factor of) the argument of an exp, so what they need is
+// an ABSOLUTE error of ~2^-56 max(1, |log x|), not a relative one near x = 1; that is what one table
+// look-up and a degree-6 series give at less than half the FP64 instructions of the series-only
+// versions (log 11 against 26, exp 10 against 17; tests/test_cuda_math.py states the bounds).
+struct MathTab {
+    const double2 *logt;  // [128] { 1/c, ln c }
+    const double *expt;   // [64] 2^(j/64)
+};
+constexpr int kMathTabBytes = mtab::kLogN * 16 + mtab::kExpN * 8;
+
+// the first kLogN threads of a block fill the tables; the caller synchronises the block
+__device__ __forceinline__ MathTab math_tab_fill(unsigned char *smem, int tid)
+{
+    double2 *lt = reinterpret_cast<double2 *>(smem);
+    double *et = reinterpret_cast<double *>(smem + mtab::kLogN * 16);
+    if (tid < mtab::kLogN) lt[tid] = mtab::g_log_tab[tid];
+    if (tid < mtab::kExpN) et[tid] = mtab::g_exp_tab[tid];
+    return MathTab{lt, et};
+}
+
+// log(x), x normal and > 0: x = 2^k z, z in [0.6875, 1.375); ln z = ln c + log1p(r), r = z/c - 1 by one fma
+template <int W>
+__device__ __forceinline__ void log_tab(const MathTab &T, const double (&x)[W], double (&out)[W])
+{
+    double z[W], dk[W], r[W], w[W], r2[W], p01[W], p23[W];
+    double2 e[W];
+    CLB_V {
+        const int hx = __double2hiint(x[j]);
+        const int tmp = hx - mtab::kLogOffHi;
+        const int k = tmp >> 20;
+        e[j] = T.logt[(tmp >> 13) & (mtab::kLogN - 1)];
+        z[j] = __hiloint2double(hx - (tmp & 0xfff00000), __double2loint(x[j]));
+        dk[j] = __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;
+    }
+    CLB_V r[j] = fma(z[j], e[j].x, -1.0);
+    CLB_V w[j] = fma(dk[j], mtab::kLn2, e[j].y);
+    CLB_V r2[j] = r[j] * r[j];
+    CLB_V p01[j] = fma(r[j], 0.33333333333333333, -0.5);
+    CLB_V p23[j] = fma(r[j], 0.2, -0.25);
+    CLB_V p23[j] = fma(r2[j], -0.16666666666666667, p23[j]);
+    CLB_V p01[j] = fma(r2[j], p23[j], p01[j]);
+    CLB_V r[j] = fma(r2[j], p01[j], r[j]);
+    CLB_V out[j] = w[j] + r[j];
+}
+
+// exp(x), no special cases, power of two clamped to the normal range: x = (64 e + i) ln2/64 + r
+template <int W>
+__device__ __forceinline__ void exp_tab(const MathTab &T, const double (&x)[W], double (&out)[W])
+{
+    const double MAGIC = 6755399441055744.0;
+    double t[W], r[W], r2[W], q23[W], q45[W], tb[W];
+    int k[W];
+    CLB_V t[j] = fma(x[j], mtab::kExpScale, MAGIC);
+    CLB_V {
+        k[j] = __double2loint(t[j]);
+        t[j] = t[j] - MAGIC;
+        tb[j] = T.expt[k[j] & (mtab::kExpN - 1)];
+    }
+    CLB_V r[j] = fma(t[j], -mtab::kLn2NHi, x[j]);
+    CLB_V r[j] = fma(t[j], -mtab::kLn2NLo, r[j]);
+    CLB_V r2[j] = r[j] * r[j];
+    CLB_V q23[j] = fma(r[j], mtab::kExpC3, mtab::kExpC2);
+    CLB_V q45[j] = fma(r[j], mtab::kExpC5, mtab::kExpC4);
+    CLB_V q23[j] = fma(r2[j], q45[j], q23[j]);
+    CLB_V r[j] = fma(r2[j], q23[j], r[j]);
+    CLB_V r[j] = fma(tb[j], r[j], tb[j]);
+    CLB_V {
+        const int kc = min(max(k[j] >> 6, -1021), 1022);
+        out[j] = __hiloint2double(__double2hiint(r[j]) + (kc << 20), __double2loint(r[j]));
+    }
+}
+
+template <bool TAB, int W>
+__device__ __forceinline__ void log_any(const MathTab &T, const double (&x)[W], double (&out)[W])
+{
+    if constexpr (TAB) log_tab<W>(T, x, out);
+    else log_pos<W>(x, out);
+}
+template <bool TAB, int W>
+__device__ __forceinline__ void exp_any(const MathTab &T, const double (&x)[W], double (&out)[W])
+{
+    if constexpr (TAB) exp_tab<W>(T, x, out);
+    else exp_clamped<W>(x, out);
+}
+
 // K (optional), psi and dpsi/dtheta of W cells (soil_hydrology_parameterizations.jl:45-50, 109-173,
 // 220-289).  Branch-free: the unsaturated formulas run on every value with finite garbage on saturated
 // ones; the S < 1 / S == 1 decisions are selects on the same IEEE comparisons as the reference.
 // Constants: ClosureConst of soil_pair.cuh (van Genuchten ca = 1/m, ca2 = m, cb = 1/n, cc = 1/alpha,
 // cd = 1/(alpha m n range); Brooks-Corey ca = -1/c, ca2 = 2/c + 3, cb = psi_b, cc = -psi_b/(c range)).
-template <int CLOSURE, bool WK, int W>
-__device__ __forceinline__ void closure(const double (&theta)[W], const double (&theta_r)[W], const double (&nu_eff)[W],
+template <int CLOSURE, bool WK, int W, bool TAB = false>
+__device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[W], const double (&theta_r)[W], const double (&nu_eff)[W],
                                         const double (&ca)[W], const double (&ca2)[W], const double (&cb)[W],
                                         const double (&cc)[W], const double (&cd)[W], const double (&inv_Ss)[W],
                                         const double (&K_sat)[W], double (&K)[W], double (&psi)[W], double (&dps)[W])
@@ -144,26 +231,26 @@ __device__ __forceinline__ void closure(const double (&theta)[W], const double (
     CLB_V range[j] = nu_safe[j] - theta_r[j];
     CLB_V num[j] = th_safe[j] - theta_r[j];
     div<W>(num, range, S);
-    log_pos<W>(S, L);
+    log_any<TAB, W>(T, S, L);
     if (CLOSURE == kVanGenuchten) {
         double Ee[W], A[W], omA[W], arg[W], l1[W], qn[W], den[W], rd[W];
         CLB_V Ee[j] = L[j] * ca[j];
-        exp_clamped<W>(Ee, A);  // S^(1/m)
+        exp_any<TAB, W>(T, Ee, A);  // S^(1/m)
         CLB_V omA[j] = 1.0 - A[j];
         // 1 - A is 0 only when S^(1/m) rounds to 1; a floor keeps log finite (dpsi is selected below)
         CLB_V arg[j] = max_nn(omA[j], 1e-300);
-        log_pos<W>(arg, l1);
+        log_any<TAB, W>(T, arg, l1);
         if (WK) {
             double em[W], t[W], sq[W];
             CLB_V em[j] = ca2[j] * l1[j];
-            exp_clamped<W>(em, t);
+            exp_any<TAB, W>(T, em, t);
             sqrt<W>(S, sq);
             CLB_V t[j] = 1.0 - t[j];
             CLB_V K[j] = (S[j] < 1.0) ? (sq[j] * (t[j] * t[j])) * K_sat[j] : K_sat[j];
         }
         // (S^(-1/m) - 1)^(1/n) = ((1 - A)/A)^(1/n);  dpsi = that / ((1 - A) S alpha m n range)
         CLB_V arg[j] = (l1[j] - Ee[j]) * cb[j];
-        exp_clamped<W>(arg, qn);
+        exp_any<TAB, W>(T, arg, qn);
         CLB_V den[j] = omA[j] * S[j];
         rcp<W>(den, rd);
         CLB_V {
@@ -178,11 +265,11 @@ __device__ __forceinline__ void closure(const double (&theta)[W], const double (
         if (WK) {
             double ek[W], t[W];
             CLB_V ek[j] = ca2[j] * L[j];
-            exp_clamped<W>(ek, t);
+            exp_any<TAB, W>(T, ek, t);
             CLB_V K[j] = (S[j] < 1.0) ? t[j] * K_sat[j] : K_sat[j];
         }
         CLB_V arg[j] = L[j] * ca[j];
-        exp_clamped<W>(arg, pw);  // S^(-1/c)
+        exp_any<TAB, W>(T, arg, pw);  // S^(-1/c)
         rcp<W>(S, rS);
         CLB_V {
             const double psi_s = (S[j] == 1.0) ? cb[j] : (th_safe[j] - nu_safe[j]) * inv_Ss[j] + cb[j];

@@ -146,33 +146,63 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map
         : "memory");
 }
 
+// the same box, only as far as L2 (no shared memory is committed to it)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c0, int l0)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(l0) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Prepared closure constants:
 //   van Genuchten  ca = 1/m, ca2 = m, cb = 1/n, cc = 1/alpha, cd = 1/(alpha m n range)
 //   Brooks-Corey   ca = -1/c, ca2 = 2/c + 3, cb = psi_b, cc = -psi_b/(c range), cd unused
 struct ClosureConst {
     double ca, ca2, cb, cc, cd, inv_Ss;
 };
-template <int CLOSURE>
-__device__ __forceinline__ ClosureConst pair_prepare(const HydroCell &p, double nu_eff)
+// The time-invariant reciprocals are not recomputed every stage: the kernel reads PREPARED mirrors
+// (k_prepare_params, written when a parameter field changes) in the slots of S_s / a / b / m:
+//   van Genuchten  1/S_s, 1/alpha, 1/n, 1/m          Brooks-Corey  1/S_s, -1/c, psi_b, (unused)
+// so a stage needs one reciprocal per cell (1/range, range depends on theta_i) instead of five.
+template <int CLOSURE, bool WANT_M>
+__device__ __forceinline__ ClosureConst pair_prepare(double inv_Ss, double pa, double pb, double pm, double theta_r, double nu_eff)
 {
-    const double theta_lo = p.theta_r + kSqrtEps;
-    const double range = fmax(nu_eff, theta_lo) - p.theta_r;
+    const double theta_lo = theta_r + kSqrtEps;
+    const double inv_range = fm::rcp(fmax(nu_eff, theta_lo) - theta_r);
     ClosureConst c;
-    c.inv_Ss = fm::rcp(p.S_s);
+    c.inv_Ss = inv_Ss;
     if (CLOSURE == kVanGenuchten) {
-        c.ca = fm::rcp(p.m);
-        c.ca2 = p.m;
-        c.cb = fm::rcp(p.b);
-        c.cc = fm::rcp(p.a);
-        c.cd = fm::rcp((p.a * p.m * p.b) * range);
+        c.ca = pm;
+        c.ca2 = WANT_M ? fm::rcp(pm) : 0.0;  // m itself: only the conductivity (Richards) needs it
+        c.cb = pb;
+        c.cc = pa;
+        c.cd = ((pa * pm) * pb) * inv_range;
     } else {
-        c.ca = -fm::rcp(p.a);
-        c.ca2 = fma(-2.0, c.ca, 3.0);
-        c.cb = p.b;
-        c.cc = -fm::div(p.b, p.a * range);
+        c.ca = pa;
+        c.ca2 = fma(-2.0, pa, 3.0);
+        c.cb = pb;
+        c.cc = (pb * pa) * inv_range;
         c.cd = 0.0;
     }
     return c;
+}
+
+// elementwise over the (padded) per-cell mirrors; exact IEEE divisions, run once per parameter change
+template <int CLOSURE>
+__global__ void k_prepare_params(const double *__restrict__ S_s, const double *__restrict__ a, const double *__restrict__ b,
+                                 const double *__restrict__ m, double *__restrict__ o_ss, double *__restrict__ o_a,
+                                 double *__restrict__ o_b, double *__restrict__ o_m, int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    o_ss[k] = 1.0 / S_s[k];
+    if (CLOSURE == kVanGenuchten) {
+        o_a[k] = 1.0 / a[k];
+        o_b[k] = 1.0 / b[k];
+        o_m[k] = 1.0 / m[k];
+    } else {
+        o_a[k] = -1.0 / a[k];
+        o_b[k] = b[k];
+    }
 }
 
 #ifndef CLB_PAIR_BLOCK
@@ -211,11 +241,11 @@ __device__ __forceinline__ void nb_exchange(double first, double last, bool inne
     }
 }
 
-// Dynamic shared memory of a block: NBUF NS-slot tiles and NBUF mbarriers per warp.
+// Dynamic shared memory of a block: the log / exp tables, then NBUF NS-slot tiles and NBUF mbarriers per warp.
 template <int PARTS, int NS, int NBUF, int BLOCK>
 __host__ __device__ constexpr size_t pair_smem_bytes()
 {
-    return (size_t)(BLOCK / 32) * NBUF * (NS * LaneGeom<PARTS>::kSlotBytes + 8);
+    return (size_t)fmv::kMathTabBytes + (size_t)(BLOCK / 32) * NBUF * (NS * LaneGeom<PARTS>::kSlotBytes + 8);
 }
 
 // Per-column scalars of a tile, fetched one tile ahead into registers.
@@ -255,13 +285,19 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     static_assert(NBUF == 1 || NBUF == 2, "single or double buffered");
     constexpr int NTOT = PairSlots<MODEL>::kConst, NRAW = PairSlots<MODEL>::kRaw;
     static_assert(NS >= NRAW && NS <= NTOT, "the raw fields are staged in the shared-memory slots");
-    extern __shared__ __align__(128) unsigned char pair_sm[];
+    extern __shared__ __align__(128) unsigned char pair_sm_all[];
+    static_assert(fmv::kMathTabBytes % 128 == 0 && BLOCK >= mtab::kLogN, "table block keeps the TMA tiles 128-byte aligned");
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const fmv::MathTab MT = fmv::math_tab_fill(pair_sm_all, tid);
+    __syncthreads();  // the only block-wide barrier: everything below is warp-private
+    unsigned char *const pair_sm = pair_sm_all + fmv::kMathTabBytes;
     const int idx = lane / CPW, half = idx / PARTS, part = idx % PARTS;
     const int r0 = part * Q;
     const bool innermost = (part == PARTS - 1), outermost = (part == 0);
-    const int64_t warp0 = ((int64_t)blockIdx.x * BLOCK + tid) >> 5;
+    // warp w of block b starts at tile w * gridDim + b: when the tiles do not divide evenly the extra ones go to
+    // one warp of every SM first instead of to every warp of the first SMs
+    const int64_t warp0 = (int64_t)wib * gridDim.x + blockIdx.x;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     const int64_t ntiles = (P.ncol + CPW - 1) / CPW;
     if (warp0 >= ntiles) return;  // whole warp
@@ -304,6 +340,28 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     const int64_t c = col_of(tile_id);
     const bool col_ok = c < P.ncol;
     const ColScalars cur = nxt;
+    if (NBUF == 1) {
+        // single buffer: the next tile cannot land in shared memory yet; start it towards L2 so that the
+        // TMA issued after this tile's store is an L2 hit
+        const int64_t tn = tile_id + nwarps;
+        if (tn < ntiles) {
+            const bool skip = (CLOSURE != kVanGenuchten) && lane == ((MODEL == 1) ? 5 : 6);
+            if (lane < NRAW && !skip) tma_prefetch_l2_2d(&M.m[lane], (int)(tn * CPW), 0);
+            if (lane >= 16 && lane < 16 + ((MODEL == 1) ? 9 : 5)) {  // the CPW per-column scalars of an array share a line
+                const int j_ = lane - 16;
+                const double *a_ = P.R_ss;
+                a_ = (j_ == 1) ? P.h_grad : a_;
+                a_ = (j_ == 2) ? P.top_bc_w : a_;
+                a_ = (j_ == 3) ? P.bot_bc_w : a_;
+                a_ = (j_ == 4) ? P.Y_intF_w : a_;
+                a_ = (j_ == 5) ? P.R_ess : a_;
+                a_ = (j_ == 6) ? P.top_bc_h : a_;
+                a_ = (j_ == 7) ? P.bot_bc_h : a_;
+                a_ = (j_ == 8) ? P.Y_intF_e : a_;
+                prefetch_l2(a_ + tn * CPW);
+            }
+        }
+    }
     if (NBUF == 2) {
         const int64_t tn = tile_id + nwarps;
         if (tn < ntiles) {
@@ -358,16 +416,17 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const bool real = level_of(q) < N;
-            HydroCell hc;
-            hc.nu = S.template get<0>(q); hc.theta_r = S.template get<1>(q); hc.K_sat = S.template get<2>(q);
-            hc.S_s = S.template get<3>(q); hc.a = S.template get<4>(q); hc.b = S.template get<5>(q);
-            hc.m = S.template get<6>(q);
+            double nu = S.template get<0>(q), theta_r = S.template get<1>(q), K_sat = S.template get<2>(q);
+            double iSs = S.template get<3>(q), pa = S.template get<4>(q), pb = S.template get<5>(q);
+            double pm = (CLOSURE == kVanGenuchten) ? S.template get<6>(q) : 0.0;
             double theta = S.template get<7>(q), sat = S.template get<8>(q);
             if (!real) {  // pad slot: benign parameters, identity rows (dti = 0, zero face coefficients)
-                hc.nu = 0.5; hc.theta_r = 0.1; hc.K_sat = 0.0; hc.S_s = 1e-3; hc.a = 1.0; hc.b = 2.0; hc.m = 0.5;
+                nu = 0.5; theta_r = 0.1; K_sat = 0.0; iSs = 1e3; pb = (CLOSURE == kVanGenuchten) ? 0.5 : 2.0;
+                pa = (CLOSURE == kVanGenuchten) ? 1.0 : -1.0; pm = 2.0;
                 theta = 0.3; sat = 0.0;
             }
-            const ClosureConst cc = pair_prepare<CLOSURE>(hc, hc.nu);
+            const ClosureConst cc = pair_prepare<CLOSURE, true>(iSs, pa, pb, pm, theta_r, nu);
+            struct { double nu, theta_r, K_sat; } hc = {nu, theta_r, K_sat};
             U1[q] = theta;
             S.template put<R_THETA_R>(q, hc.theta_r);
             S.template put<R_NU>(q, hc.nu);
@@ -402,18 +461,19 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const bool real = level_of(q) < N;
-            HydroCell hc;
-            hc.nu = S.template get<0>(q); hc.theta_r = S.template get<1>(q); hc.K_sat = 0.0;
-            hc.S_s = S.template get<2>(q); hc.a = S.template get<3>(q); hc.b = S.template get<4>(q);
-            hc.m = S.template get<5>(q);
+            double nu = S.template get<0>(q), theta_r = S.template get<1>(q);
+            double iSs = S.template get<2>(q), pa = S.template get<3>(q), pb = S.template get<4>(q);
+            double pm = (CLOSURE == kVanGenuchten) ? S.template get<5>(q) : 0.0;
             double theta = S.template get<6>(q), sat = S.template get<7>(q), theta_i = S.template get<8>(q),
                    rcds = S.template get<9>(q), rho_e = S.template get<13>(q);
             if (!real) {
-                hc.nu = 0.5; hc.theta_r = 0.1; hc.S_s = 1e-3; hc.a = 1.0; hc.b = 2.0; hc.m = 0.5;
+                nu = 0.5; theta_r = 0.1; iSs = 1e3; pb = (CLOSURE == kVanGenuchten) ? 0.5 : 2.0;
+                pa = (CLOSURE == kVanGenuchten) ? 1.0 : -1.0; pm = 2.0;
                 theta = 0.3; sat = 0.0; theta_i = 0.0; rcds = 1e6; rho_e = 0.0;
             }
-            const double nu_eff = hc.nu - theta_i;
-            const ClosureConst cc = pair_prepare<CLOSURE>(hc, nu_eff);
+            const double nu_eff = nu - theta_i;
+            const ClosureConst cc = pair_prepare<CLOSURE, false>(iSs, pa, pb, pm, theta_r, nu_eff);
+            struct { double theta_r; } hc = {theta_r};
             U1[q] = theta;
             U2[q] = rho_e;
             // lagged coefficients of the cell's outer face (zero table entry at the column boundary)
@@ -444,24 +504,38 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             i22[q] = (aC_in * ((q < Q - 1) ? rc[q + 1] : rc_in)) * dti;
             d22[q] = fma(-((aC_in + aCo[q]) * rc[q]), dti, -1.0);
         }
-        double cin = 0.0;
+        // Elimination boundary -> seam WITHOUT a reciprocal in the dependency chain: the leading principal
+        // minors D_q = d_q D_{q-1} - (o_q i_{q-1}) D_{q-2} run as one fma per cell; the pivots' reciprocals
+        // D_{q-1}/D_q are then Q independent divisions.  (|d| >= 1 and the rows are diagonally dominant, so D
+        // only grows: <= |d|^16, far inside the double range.)  An inner part continues the recurrence of
+        // the outer one: (D_{Q-1}, i_{Q-1} D_{Q-2}) cross lanes between the passes.
+        {
+            double Din = 1.0, iDin = 0.0, D[Q], iD[Q];
 #pragma unroll
-        for (int pass = 0; pass < PARTS; ++pass) {
-            double cp = cin;
+            for (int pass = 0; pass < PARTS; ++pass) {
+                double Dp = Din, iDp = iDin;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double den = fm::rcp(fma(-o22[q], cp, d22[q]));
-                cp = i22[q] * den;
-                if (pass == PARTS - 1) {
-                    S.template put<E_DEN22>(q, den);
-                    S.template put<E_OD22>(q, o22[q] * den);
-                    S.template put<E_C22>(q, cp);
+                for (int q = 0; q < Q; ++q) {
+                    iD[q] = i22[q] * Dp;
+                    D[q] = fma(d22[q], Dp, -(o22[q] * iDp));
+                    iDp = iD[q];
+                    Dp = D[q];
+                }
+                if (pass + 1 < PARTS) {
+                    const double rD_ = xchg<CPW>(D[Q - 1]), riD_ = xchg<CPW>(iD[Q - 1]);
+                    Din = outermost ? 1.0 : rD_;
+                    iDin = outermost ? 0.0 : riD_;
                 }
             }
-            c22_last = cp;
-            if (pass + 1 < PARTS) {
-                const double rc_ = xchg<CPW>(cp);
-                cin = outermost ? 0.0 : rc_;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double rD = fm::rcp(D[q]);
+                const double den = ((q == 0) ? Din : D[q - 1]) * rD;
+                const double cp = iD[q] * rD;
+                S.template put<E_DEN22>(q, den);
+                S.template put<E_OD22>(q, o22[q] * den);
+                S.template put<E_C22>(q, cp);
+                if (q == Q - 1) c22_last = cp;
             }
         }
         r22 = fm::rcp(fma(-c22_last, xchg<Gm::SEAM>(c22_last), 1.0));
@@ -521,7 +595,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     Ksat[j] = S.template get<R_KSAT>(g + j);
                 }
             }
-            fmv::closure<CLOSURE, MODEL == 0, W>(th, thr, nue, ca, ca2, cb, ccc, cd, iSs, Ksat, K, psi, dp);
+            fmv::closure<CLOSURE, MODEL == 0, W, true>(MT, th, thr, nue, ca, ca2, cb, ccc, cd, iSs, Ksat, K, psi, dp);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 h[g + j] = psi[j] + G.z[half][r0 + g + j];
@@ -595,23 +669,33 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         // lanes in between), 2x2 seam system, back substitution seam -> boundary
         double c1[Q], g1[Q], x1[Q], y[Q];
         {
-            double cin = 0.0, gin = 0.0;
+            // forward elimination by the minors' recurrence (see the W22 set-up): D_q as there,
+            // gamma_q = f_q D_{q-1} - o_q gamma_{q-1}; then c_q = i_q D_{q-1} / D_q and g_q = gamma_q / D_q
+            double Din = 1.0, iDin = 0.0, gin = 0.0, D[Q], iD[Q], gam[Q];
 #pragma unroll
             for (int pass = 0; pass < PARTS; ++pass) {
-                double cp = cin, gp = gin;
+                double Dp = Din, iDp = iDin, gp = gin;
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const double den = fm::rcp(fma(-o1[q], cp, d1[q]));
-                    cp = i1[q] * den;
-                    gp = fma(-o1[q], gp, f1[q]) * den;
-                    c1[q] = cp;
-                    g1[q] = gp;
+                    iD[q] = i1[q] * Dp;
+                    gam[q] = fma(-o1[q], gp, f1[q] * Dp);
+                    D[q] = fma(d1[q], Dp, -(o1[q] * iDp));
+                    iDp = iD[q];
+                    gp = gam[q];
+                    Dp = D[q];
                 }
                 if (pass + 1 < PARTS) {
-                    const double rc_ = xchg<CPW>(cp), rg_ = xchg<CPW>(gp);
-                    cin = outermost ? 0.0 : rc_;
+                    const double rD_ = xchg<CPW>(D[Q - 1]), riD_ = xchg<CPW>(iD[Q - 1]), rg_ = xchg<CPW>(gam[Q - 1]);
+                    Din = outermost ? 1.0 : rD_;
+                    iDin = outermost ? 0.0 : riD_;
                     gin = outermost ? 0.0 : rg_;
                 }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double rD = fm::rcp(D[q]);
+                c1[q] = iD[q] * rD;
+                g1[q] = gam[q] * rD;
             }
             const double cs_ = xchg<Gm::SEAM>(c1[Q - 1]), gs_ = xchg<Gm::SEAM>(g1[Q - 1]);
             const double xs = fma(-c1[Q - 1], gs_, g1[Q - 1]) * fm::rcp(fma(-c1[Q - 1], cs_, 1.0));

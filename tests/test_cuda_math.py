@@ -67,3 +67,23 @@ def test_sqrt():
     got = _run(4, x)
     assert _ulp_err(got[x > 0], np.sqrt(x[x > 0])) <= 1.0
     assert got[-4] == 0.0 and got[-3] == 1.0 and got[-2] == 2.0 and got[-1] == 0.5
+
+
+def test_table_log():
+    """log_tab (soil_mathv.cuh): one table look-up + degree-6 series.  The closures only ever feed a
+    logarithm into an exp, so the contract is absolute near x = 1: |err| <= 2 ulp or 2^-58."""
+    x = np.concatenate([_samples(1e-300, 1e300), _samples(1e-9, 1.0, seed=3), 1.0 - _samples(1e-16, 0.5, seed=4),
+                        1.0 + _samples(1e-16, 0.5, seed=5), [1.0, 0.5, 2.0, 0.6875, 1.375, np.nextafter(0.6875, 0)]])
+    got = _run(6, x)
+    want = np.log(x)
+    err = np.abs(got - want)
+    bound = np.maximum(2.0 * np.spacing(np.abs(want)), 2.0 ** -58)
+    assert np.all(err <= bound), (x[np.argmax(err / bound)], np.max(err / bound))
+
+
+def test_table_exp():
+    x = np.concatenate([_samples(-700.0, 700.0, log=False), _samples(-1.0, 1.0, log=False, seed=6),
+                        -_samples(1e-17, 1e-3, seed=7), [0.0]])
+    got = _run(7, x)
+    assert _ulp_err(got, np.exp(x)) <= 2.0
+    assert got[-1] == 1.0
