@@ -118,6 +118,9 @@ struct clb_handle_s {
     double *prep[4] = {};
     bool prep_dirty = true;     // a parameter field changed since they were written
     bool prep_volatile = false; // the caller holds a device pointer to a parameter mirror: re-prepare every stage
+    // this handle's last enqueued operation wrote a time-invariant parameter mirror: the next stage kernel must
+    // not start reading parameters before it completes (no programmatic dependent launch for that one)
+    bool param_write_pending = true;
     double *field[CLB_F_NUM] = {};
     bool field_set[CLB_F_NUM] = {};
     // grid
@@ -370,6 +373,12 @@ inline bool is_closure_param(int field)
 {
     return field == CLB_F_S_S || field == CLB_F_HCM_A || field == CLB_F_HCM_B || field == CLB_F_HCM_M;
 }
+// fields the lane-quad kernels fetch before griddepcontrol.wait (soil_pair.cuh: is_param)
+inline bool is_invariant_param(int field)
+{
+    return is_closure_param(field) || field == CLB_F_NU || field == CLB_F_THETA_R || field == CLB_F_K_SAT ||
+           field == CLB_F_RHO_C_DS;
+}
 
 // (Re)writes the prepared parameter mirrors when a parameter changed since the last stage.
 int ensure_prepared(clb_handle h, const clb::DevView &P)
@@ -387,6 +396,7 @@ int ensure_prepared(clb_handle h, const clb::DevView &P)
                                                               h->prep[2], h->prep[3], n);
     CUDA_TRY(cudaGetLastError());
     h->prep_dirty = false;
+    h->param_write_pending = true;
     return CLB_OK;
 }
 
@@ -452,7 +462,21 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
     const clb::PairGrid g = make_pair_grid(h, dtg);
     clb::PairMaps maps;
     TRY(make_pair_maps(h, P, CPW, &maps));
-    kern<<<(unsigned)blocks, BLOCK, smem, h->stream>>>(P, g, maps, dtg, max_iters);
+    // programmatic dependent launch: the kernel's prologue (tables, barriers, the first tile's parameter
+    // fields) may overlap the tail of the stream's previous kernel unless that kernel may be writing this
+    // handle's parameter mirrors
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)blocks);
+    lc.blockDim = dim3(BLOCK);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = (h->param_write_pending || h->prep_volatile) ? 0 : 1;
+    CUDA_TRY(cudaLaunchKernelEx(&lc, kern, P, g, maps, dtg, (int)max_iters));
+    h->param_write_pending = false;
     return CLB_OK;
 }
 
@@ -826,6 +850,8 @@ int clb_set_field(clb_handle h, int32_t field, const double *src, int64_t stride
     CUDA_TRY(cudaGetLastError());
     h->field_set[field] = true;
     if (is_closure_param(field)) h->prep_dirty = true;
+    if (is_invariant_param(field)) h->param_write_pending = true;
+    if (is_invariant_param(field)) h->param_write_pending = true;
     return CLB_OK;
 }
 
@@ -880,6 +906,7 @@ int clb_fill_field(clb_handle h, int32_t field, double value)
     CUDA_TRY(cudaGetLastError());
     h->field_set[field] = true;
     if (is_closure_param(field)) h->prep_dirty = true;
+    if (is_invariant_param(field)) h->param_write_pending = true;
     return CLB_OK;
 }
 
@@ -891,7 +918,7 @@ int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *str
     DeviceGuard guard(h->cfg.device);
     TRY(ensure_field(h, field));
     h->field_set[field] = true;  // the caller fills it in place
-    if (is_closure_param(field)) h->prep_volatile = true;
+    if (is_invariant_param(field)) h->prep_volatile = true;
     *ptr = h->field[field];
     if (stride_level) *stride_level = is_cell_field(field) ? h->sl : 0;
     if (stride_column) *stride_column = is_cell_field(field) ? h->sc : 1;
@@ -1031,8 +1058,12 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
         TRY(alloc_fields(h, {CLB_F_U_THETA_L, CLB_F_U_INTF_W}));
         if (eh) TRY(alloc_fields(h, {CLB_F_U_RHO_E_INT, CLB_F_U_INTF_E}));
     }
-    CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(double), h->stream));
     clb::DevView P = make_view(h);
+    const bool quad = variant == CLB_VARIANT_LANE_QUAD || variant == CLB_VARIANT_LANE_QUAD_PIPELINED;
+    if (quad && fixed && !stats)
+        P.stats = nullptr;  // nobody reads them: no memset between stages, no atomics in the kernel
+    else
+        CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 3 * sizeof(double), h->stream));
     const unsigned grid = grid_for(P.ncol);
     nvtxRangePushA("implicit_step!");
     int iters_done = max_iters;

@@ -290,7 +290,6 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const fmv::MathTab MT = fmv::math_tab_fill(pair_sm_all, tid);
-    __syncthreads();  // the only block-wide barrier: everything below is warp-private
     unsigned char *const pair_sm = pair_sm_all + fmv::kMathTabBytes;
     const int idx = lane / CPW, half = idx / PARTS, part = idx % PARTS;
     const int r0 = part * Q;
@@ -300,7 +299,6 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     const int64_t warp0 = (int64_t)wib * gridDim.x + blockIdx.x;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     const int64_t ntiles = (P.ncol + CPW - 1) / CPW;
-    if (warp0 >= ntiles) return;  // whole warp
     const EarthConst &E = P.earth;
     const double C1 = E.cp_l * E.rho_l, C2 = E.cp_i * E.rho_i, T_ref = E.T_ref;
 
@@ -314,13 +312,21 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     auto col_of = [&](int64_t t) { return t * CPW + (lane % CPW); };
     auto col_clamped = [&](int64_t t) { const int64_t c_ = col_of(t); return c_ < P.ncol ? c_ : P.ncol - 1; };
 
-    // every per-cell field of a tile: HBM -> shared memory, one TMA box per field
-    auto request_tile = [&](int64_t t, int buf) {
+    // every per-cell field of a tile: HBM -> shared memory, one TMA box per field.  `which`: 1 = the
+    // time-invariant parameter fields (safe to fetch while the previous launch of the stream still runs),
+    // 2 = the stage inputs (state, lagged cache), 3 = all
+    auto is_param = [&](int j) {
+        return (MODEL == 1) ? (j <= 5 || j == 9) : (j <= 6);
+    };
+    auto request_tile = [&](int64_t t, int buf, int which) {
         const unsigned bar = bar0 + buf * 8;
-        if (lane == 0) mbar_expect_tx(bar, (unsigned)(NRAW - ((CLOSURE == kVanGenuchten) ? 0 : 1)) * N * CPW * 8);
-        __syncwarp();
+        if (which & 1) {
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)(NRAW - ((CLOSURE == kVanGenuchten) ? 0 : 1)) * N * CPW * 8);
+            __syncwarp();
+        }
         const bool skip = (CLOSURE != kVanGenuchten) && lane == ((MODEL == 1) ? 5 : 6);  // no m field for Brooks-Corey
-        if (lane < NRAW && !skip)
+        const bool mine = is_param(lane) ? (which & 1) : (which & 2);
+        if (lane < NRAW && !skip && mine)
             tma_load_2d(smem_u32(tiles + buf * kTileBytes) + lane * Gm::kSlotBytes, &M.m[lane], (int)(t * CPW), 0, bar);
     };
 
@@ -329,7 +335,17 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         for (int b_ = 0; b_ < NBUF; ++b_) mbar_init(bar0 + b_ * 8, 1);
     }
     __syncwarp();
-    request_tile(warp0, 0);
+    const bool has_tile = warp0 < ntiles;
+    if (has_tile) request_tile(warp0, 0, 1);
+    __syncthreads();  // the tables are in place; the only block-wide barrier: everything below is warp-private
+    // Programmatic dependent launch (both are no-ops without the launch attribute): up to here this launch
+    // only read time-invariant parameter fields, so it may overlap the tail of the stream's previous kernel;
+    // everything below waits for that kernel to complete.  The next launch is released only now, so its
+    // prologue can overlap this kernel alone, never one further back.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!has_tile) return;  // whole warp
+    request_tile(warp0, 0, 2);
     ColScalars nxt = load_col_scalars<MODEL>(P, col_clamped(warp0));
 
     double dx2_acc = 0.0, bad = 0.0;
@@ -368,7 +384,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             // the other buffer held the previous tile's constants (generic-proxy accesses): order them
             // before the async-proxy writes of the TMA
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            request_tile(tn, buf ^ 1);
+            request_tile(tn, buf ^ 1, 3);
             nxt = load_col_scalars<MODEL>(P, col_clamped(tn));
         }
     }
@@ -784,11 +800,11 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     else __syncwarp();
     if (NBUF == 1 && tile_id + nwarps < ntiles) {  // single buffer: the next tile is requested only now
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        request_tile(tile_id + nwarps, 0);
+        request_tile(tile_id + nwarps, 0, 3);
         nxt = load_col_scalars<MODEL>(P, col_clamped(tile_id + nwarps));
     }
     }  // tiles
-    accumulate_stats(P, dx2_acc, bad);
+    if (P.stats) accumulate_stats(P, dx2_acc, bad);  // only when the caller asked for clb_stats
 }
 
 }  // namespace clb
