@@ -210,15 +210,19 @@ __global__ void k_prepare_params(const double *__restrict__ S_s, const double *_
 #endif
 
 // Lane geometry of a column split over 2 * PARTS lanes (PARTS = 1: lane pair, 2: lane quad).
-//   lane = column-in-warp + CPW * (half * PARTS + part);  part 0 touches the column boundary,
-//   part PARTS-1 the seam.  xor CPW swaps the two parts of a half, xor CPW*PARTS swaps the halves.
+//   lane = column-in-warp + CPW * (part * 2 + half);  part 0 touches the column boundary,
+//   part PARTS-1 the seam.  xor CPW swaps the halves, xor 2*CPW swaps the two parts of a half.
+//   With the half in the low bit a half-warp (the unit of a 64-bit shared-memory access) holds the
+//   level rows q' and 15 - q' of a slot: opposite parity, i.e. the two 64-byte halves of the 32 banks,
+//   so the slot accesses are conflict-free (half-major order put rows q and q + 4 on the same banks).
 template <int PARTS>
 struct LaneGeom {
     static_assert(PARTS == 1 || PARTS == 2, "lane pair or lane quad");
     static constexpr int LPC = 2 * PARTS;     // lanes per column
     static constexpr int CPW = 32 / LPC;      // columns per warp
     static constexpr int Q = kPairQ / PARTS;  // cells per lane
-    static constexpr int SEAM = CPW * PARTS;
+    static constexpr int SEAM = CPW;          // xor mask: the other half of the column
+    static constexpr int PARTX = 2 * CPW;     // xor mask: the other part of this half (lane quad)
     static constexpr int kSlotBytes = 16 * CPW * 8;  // one slot of a warp tile: 16 level rows x CPW columns
 };
 
@@ -235,7 +239,7 @@ __device__ __forceinline__ void nb_exchange(double first, double last, bool inne
         inner = seam;
         outer = first;
     } else {
-        const double nb_first = xchg<Gm::CPW>(first), nb_last = xchg<Gm::CPW>(last);
+        const double nb_first = xchg<Gm::PARTX>(first), nb_last = xchg<Gm::PARTX>(last);
         inner = innermost ? seam : nb_first;
         outer = nb_last;
     }
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const fmv::MathTab MT = fmv::math_tab_fill(pair_sm_all, tid);
     unsigned char *const pair_sm = pair_sm_all + fmv::kMathTabBytes;
-    const int idx = lane / CPW, half = idx / PARTS, part = idx % PARTS;
+    const int idx = lane / CPW, half = idx & 1, part = idx >> 1;
     const int r0 = part * Q;
     const bool innermost = (part == PARTS - 1), outermost = (part == 0);
     // warp w of block b starts at tile w * gridDim + b: when the tiles do not divide evenly the extra ones go to
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     Dp = D[q];
                 }
                 if (pass + 1 < PARTS) {
-                    const double rD_ = xchg<CPW>(D[Q - 1]), riD_ = xchg<CPW>(iD[Q - 1]);
+                    const double rD_ = xchg<Gm::PARTX>(D[Q - 1]), riD_ = xchg<Gm::PARTX>(iD[Q - 1]);
                     Din = outermost ? 1.0 : rD_;
                     iDin = outermost ? 0.0 : riD_;
                 }
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     Dp = D[q];
                 }
                 if (pass + 1 < PARTS) {
-                    const double rD_ = xchg<CPW>(D[Q - 1]), riD_ = xchg<CPW>(iD[Q - 1]), rg_ = xchg<CPW>(gam[Q - 1]);
+                    const double rD_ = xchg<Gm::PARTX>(D[Q - 1]), riD_ = xchg<Gm::PARTX>(iD[Q - 1]), rg_ = xchg<Gm::PARTX>(gam[Q - 1]);
                     Din = outermost ? 1.0 : rD_;
                     iDin = outermost ? 0.0 : riD_;
                     gin = outermost ? 0.0 : rg_;
@@ -721,7 +725,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 x1[Q - 1] = (pass == 0) ? xs : (innermost ? xs : fma(-c1[Q - 1], xn, g1[Q - 1]));
 #pragma unroll
                 for (int q = Q - 2; q >= 0; --q) x1[q] = fma(-c1[q], x1[q + 1], g1[q]);
-                if (pass + 1 < PARTS) xn = xchg<CPW>(x1[0]);
+                if (pass + 1 < PARTS) xn = xchg<Gm::PARTX>(x1[0]);
             }
         }
         const bool last = (it == max_iters - 1);
@@ -760,7 +764,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     g2[q] = gp;
                 }
                 if (pass + 1 < PARTS) {
-                    const double rg_ = xchg<CPW>(gp);
+                    const double rg_ = xchg<Gm::PARTX>(gp);
                     gin = outermost ? 0.0 : rg_;
                 }
             }
@@ -771,7 +775,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 x2[Q - 1] = (pass == 0) ? xs : (innermost ? xs : fma(-c22_last, xn, g2[Q - 1]));
 #pragma unroll
                 for (int q = Q - 2; q >= 0; --q) x2[q] = fma(-S.template get<E_C22>(q), x2[q + 1], g2[q]);
-                if (pass + 1 < PARTS) xn = xchg<CPW>(x2[0]);
+                if (pass + 1 < PARTS) xn = xchg<Gm::PARTX>(x2[0]);
             }
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
