@@ -426,8 +426,8 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::Pa
 
 // Lane-quad kernel (soil_pair.cuh, four lanes per column, four cells per lane), two launch shapes:
 //   PIPELINED  persistent, 1 block of 256 threads per SM, each warp double-buffers its tiles: 2 x 14 slots x 1 KB
-//              of shared memory per warp (3 of EnergyHydrology's 17 stage constants stay in registers);
-//   plain      one tile per warp, all constants in shared memory (17 KB per warp), 3 blocks per SM.
+//              of shared memory per warp (4 of EnergyHydrology's 18 stage constants stay in registers);
+//   plain      one tile per warp, all constants in shared memory (18 KB per warp), 3 blocks per SM.
 template <int CLOSURE, int MODEL, int N, bool PIPELINED>
 int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 {
@@ -437,9 +437,9 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 #define CLB_QUAD_MINB 3
 #endif
 #ifndef CLB_QUAD_NS
-#define CLB_QUAD_NS 17
+#define CLB_QUAD_NS 18
 #endif
-    constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 10;
+    constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 11;
     constexpr int NBUF = PIPELINED ? 2 : 1;
     constexpr int MINB = PIPELINED ? 1 : CLB_QUAD_MINB;
     constexpr int CPW = clb::LaneGeom<PARTS>::CPW;

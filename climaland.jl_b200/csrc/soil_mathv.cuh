@@ -220,17 +220,24 @@ __device__ __forceinline__ void exp_any(const MathTab &T, const double (&x)[W], 
 // cd = 1/(alpha m n range); Brooks-Corey ca = -1/c, ca2 = 2/c + 3, cb = psi_b, cc = -psi_b/(c range)).
 template <int CLOSURE, bool WK, int W, bool TAB = false>
 __device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[W], const double (&theta_r)[W], const double (&nu_eff)[W],
-                                        const double (&ca)[W], const double (&ca2)[W], const double (&cb)[W],
+                                        const double (&inv_range)[W], const double (&ca)[W], const double (&ca2)[W], const double (&cb)[W],
                                         const double (&cc)[W], const double (&cd)[W], const double (&inv_Ss)[W],
                                         const double (&K_sat)[W], double (&K)[W], double (&psi)[W], double (&dps)[W])
 {
+    // effective saturation: the quotient num / range of the reference is taken as num * (1/range) with the
+    // stage-constant reciprocal (<= 1.5 ulp instead of 0.5 ulp); its comparisons with 1 are decided exactly
+    // as the reference's: num and range are doubles, so the correctly rounded quotient is < 1 iff num < range
+    // and == 1 iff num == range, and th_safe - theta_r vs nu_safe - theta_r compare as th_safe vs nu_safe
+    // except when both differences round to the same double, which the explicit differences below keep.
     double lo[W], nu_safe[W], range[W], th_safe[W], num[W], S[W], L[W];
+    bool unsat[W], sat1[W];
     CLB_V lo[j] = theta_r[j] + kSqrtEps;
     CLB_V nu_safe[j] = max_nn(nu_eff[j], lo[j]);
     CLB_V th_safe[j] = max_nn(theta[j], lo[j]);
     CLB_V range[j] = nu_safe[j] - theta_r[j];
     CLB_V num[j] = th_safe[j] - theta_r[j];
-    div<W>(num, range, S);
+    CLB_V S[j] = num[j] * inv_range[j];
+    CLB_V { unsat[j] = num[j] < range[j]; sat1[j] = num[j] == range[j]; }
     log_any<TAB, W>(T, S, L);
     if (CLOSURE == kVanGenuchten) {
         double Ee[W], A[W], omA[W], arg[W], l1[W], qn[W], den[W], rd[W];
@@ -246,7 +253,7 @@ __device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[
             exp_any<TAB, W>(T, em, t);
             sqrt<W>(S, sq);
             CLB_V t[j] = 1.0 - t[j];
-            CLB_V K[j] = (S[j] < 1.0) ? (sq[j] * (t[j] * t[j])) * K_sat[j] : K_sat[j];
+            CLB_V K[j] = unsat[j] ? (sq[j] * (t[j] * t[j])) * K_sat[j] : K_sat[j];
         }
         // (S^(-1/m) - 1)^(1/n) = ((1 - A)/A)^(1/n);  dpsi = that / ((1 - A) S alpha m n range)
         CLB_V arg[j] = (l1[j] - Ee[j]) * cb[j];
@@ -254,11 +261,11 @@ __device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[
         CLB_V den[j] = omA[j] * S[j];
         rcp<W>(den, rd);
         CLB_V {
-            const double psi_s = (S[j] == 1.0) ? -0.0 : (th_safe[j] - nu_safe[j]) * inv_Ss[j];
-            psi[j] = (S[j] < 1.0) ? -(qn[j] * cc[j]) : psi_s;
+            const double psi_s = sat1[j] ? -0.0 : (th_safe[j] - nu_safe[j]) * inv_Ss[j];
+            psi[j] = unsat[j] ? -(qn[j] * cc[j]) : psi_s;
             double d = (qn[j] * cd[j]) * rd[j];
             d = (omA[j] <= 0.0) ? INFINITY : d;
-            dps[j] = (S[j] < 1.0) ? d : inv_Ss[j];
+            dps[j] = unsat[j] ? d : inv_Ss[j];
         }
     } else {
         double arg[W], pw[W], rS[W];
@@ -266,15 +273,15 @@ __device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[
             double ek[W], t[W];
             CLB_V ek[j] = ca2[j] * L[j];
             exp_any<TAB, W>(T, ek, t);
-            CLB_V K[j] = (S[j] < 1.0) ? t[j] * K_sat[j] : K_sat[j];
+            CLB_V K[j] = unsat[j] ? t[j] * K_sat[j] : K_sat[j];
         }
         CLB_V arg[j] = L[j] * ca[j];
         exp_any<TAB, W>(T, arg, pw);  // S^(-1/c)
         rcp<W>(S, rS);
         CLB_V {
-            const double psi_s = (S[j] == 1.0) ? cb[j] : (th_safe[j] - nu_safe[j]) * inv_Ss[j] + cb[j];
-            psi[j] = (S[j] < 1.0) ? cb[j] * pw[j] : psi_s;
-            dps[j] = (S[j] < 1.0) ? (cc[j] * pw[j]) * rS[j] : inv_Ss[j];
+            const double psi_s = sat1[j] ? cb[j] : (th_safe[j] - nu_safe[j]) * inv_Ss[j] + cb[j];
+            psi[j] = unsat[j] ? cb[j] * pw[j] : psi_s;
+            dps[j] = unsat[j] ? (cc[j] * pw[j]) * rS[j] : inv_Ss[j];
         }
     }
 }

@@ -60,21 +60,21 @@ struct PairGrid {
 };
 
 // Stage constants per cell: slots [0, NS) in shared memory, the rest in registers.
-//   Richards (10)         theta_r, nu, ca, ca2, cb, 1/S_s, cc, cd, K_sat, t1
-//   EnergyHydrology (17)  theta_r, nu_eff, ice energy, rho_c base, ca, K_lag rho_l c_l, cb, 1/S_s, cc, cd,
-//                         aK_o, aC_o (outer-face coefficients), den22, od22 | c22, t1, t2
+//   Richards (11)         theta_r, nu, ca, ca2, cb, 1/S_s, cc, cd, K_sat, t1, 1/range
+//   EnergyHydrology (18)  theta_r, nu_eff, ice energy, rho_c base, ca, K_lag rho_l c_l, cb, 1/S_s, cc, cd,
+//                         aK_o, aC_o (outer-face coefficients), den22, od22 | c22, t1, t2, 1/range
 // t1 / t2: constant part of the residual, temp - dtgamma * (implicit source).
 // Raw fields (what TMA brings in, same slots before the in-place transform):
 //   Richards (9)          nu, theta_r, K_sat, S_s, a, b, m, theta_l, is_sat
 //   EnergyHydrology (14)  nu, theta_r, S_s, a, b, m, theta_l, is_sat, theta_i, rho_c_ds, K, kappa, theta_l_lag, rho_e
 template <int MODEL>
 struct PairSlots {
-    static constexpr int kConst = (MODEL == 1) ? 17 : 10;
+    static constexpr int kConst = (MODEL == 1) ? 18 : 11;
     static constexpr int kRaw = (MODEL == 1) ? 14 : 9;
 };
-enum { R_THETA_R = 0, R_NU, R_CA, R_CA2, R_CB, R_INV_SS, R_CC, R_CD, R_KSAT, R_T1 };
+enum { R_THETA_R = 0, R_NU, R_CA, R_CA2, R_CB, R_INV_SS, R_CC, R_CD, R_KSAT, R_T1, R_IRANGE };
 enum { E_THETA_R = 0, E_NU_EFF, E_ICE, E_RCBASE, E_CA, E_KC, E_CB, E_INV_SS, E_CC, E_CD, E_AK, E_AC, E_DEN22, E_OD22,
-       E_C22, E_T1, E_T2 };
+       E_C22, E_T1, E_T2, E_IRANGE };
 
 
 // TMA descriptors of the raw fields (column-fastest mirrors: dims {ncol, N}, box {16, N})
@@ -157,7 +157,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 //   van Genuchten  ca = 1/m, ca2 = m, cb = 1/n, cc = 1/alpha, cd = 1/(alpha m n range)
 //   Brooks-Corey   ca = -1/c, ca2 = 2/c + 3, cb = psi_b, cc = -psi_b/(c range), cd unused
 struct ClosureConst {
-    double ca, ca2, cb, cc, cd, inv_Ss;
+    double ca, ca2, cb, cc, cd, inv_Ss, inv_range;
 };
 // The time-invariant reciprocals are not recomputed every stage: the kernel reads PREPARED mirrors
 // (k_prepare_params, written when a parameter field changes) in the slots of S_s / a / b / m:
@@ -170,6 +170,7 @@ __device__ __forceinline__ ClosureConst pair_prepare(double inv_Ss, double pa, d
     const double inv_range = fm::rcp(fmax(nu_eff, theta_lo) - theta_r);
     ClosureConst c;
     c.inv_Ss = inv_Ss;
+    c.inv_range = inv_range;
     if (CLOSURE == kVanGenuchten) {
         c.ca = pm;
         c.ca2 = WANT_M ? fm::rcp(pm) : 0.0;  // m itself: only the conductivity (Richards) needs it
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             S.template put<R_CD>(q, cc.cd);
             S.template put<R_KSAT>(q, hc.K_sat);
             S.template put<R_T1>(q, fma(-dtg, src_w * sat, theta));
+            S.template put<R_IRANGE>(q, cc.inv_range);
         }
     } else {
         // lagged fields that couple neighbours: K, kappa and 1/rho_c_s at the LAGGED theta_l
@@ -514,6 +516,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             S.template put<E_AC>(q, aCo[q]);
             S.template put<E_T1>(q, fma(-dtg, src_w * sat, theta));
             S.template put<E_T2>(q, fma(-dtg, src_e * sat, rho_e));
+            S.template put<E_IRANGE>(q, cc.inv_range);
         }
         // rows of W22 = dtgamma d(T_rho_e)/d(rho_e) - I and their elimination, boundary -> seam
 #pragma unroll
@@ -569,7 +572,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         double h[Q], dps[Q], Kc[Q], Td[Q], eK[Q];
 #pragma unroll
         for (int g = 0; g < Q; g += W) {
-            double th[W], thr[W], nue[W], ca[W], ca2[W], cb[W], iSs[W], ccc[W], cd[W], Ksat[W];
+            double th[W], thr[W], nue[W], ca[W], ca2[W], cb[W], iSs[W], ccc[W], cd[W], Ksat[W], irg[W];
             double K[W], psi[W], dp[W];
 #pragma unroll
             for (int j = 0; j < W; ++j) {
@@ -602,6 +605,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     iSs[j] = S.template get<E_INV_SS>(g + j);
                     ccc[j] = S.template get<E_CC>(g + j);
                     cd[j] = S.template get<E_CD>(g + j);
+                    irg[j] = S.template get<E_IRANGE>(g + j);
                 }
             } else {
 #pragma unroll
@@ -613,9 +617,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     ccc[j] = S.template get<R_CC>(g + j);
                     cd[j] = S.template get<R_CD>(g + j);
                     Ksat[j] = S.template get<R_KSAT>(g + j);
+                    irg[j] = S.template get<R_IRANGE>(g + j);
                 }
             }
-            fmv::closure<CLOSURE, MODEL == 0, W, true>(MT, th, thr, nue, ca, ca2, cb, ccc, cd, iSs, Ksat, K, psi, dp);
+            fmv::closure<CLOSURE, MODEL == 0, W, true>(MT, th, thr, nue, irg, ca, ca2, cb, ccc, cd, iSs, Ksat, K, psi, dp);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 h[g + j] = psi[j] + G.z[half][r0 + g + j];
