@@ -566,7 +566,11 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 
     // ---- Newton iterations -----------------------------------------------------------------
     double dx2 = 0.0;
-#pragma unroll 1
+#ifndef CLB_NEWTON_UNROLL
+#define CLB_NEWTON_UNROLL 1
+#endif
+    constexpr int kNewtonUnroll = CLB_NEWTON_UNROLL;
+#pragma unroll kNewtonUnroll
     for (int it = 0; it < max_iters; ++it) {
         // cache_imp!: closures (and temperature) at the iterate, W cells at a time
         double h[Q], dps[Q], Kc[Q], Td[Q], eK[Q];
@@ -797,10 +801,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         if (level < N && col_ok) {
             const int64_t k = P.at(level, c);
             P.out_theta_l[k] = U1[q];
-            if (!isfinite(U1[q])) bad += 1.0;
-            if (MODEL == 1) {
-                P.out_rho_e[k] = U2[q];
-                if (!isfinite(U2[q])) bad += 1.0;
+            if (MODEL == 1) P.out_rho_e[k] = U2[q];
+            if (P.stats) {  // the NaN count is only taken when the caller asked for clb_stats
+                if (!isfinite(U1[q])) bad += 1.0;
+                if (MODEL == 1 && !isfinite(U2[q])) bad += 1.0;
             }
         }
     }
