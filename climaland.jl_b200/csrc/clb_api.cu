@@ -21,6 +21,7 @@
 #include "soil_hooks.cuh"
 #include "soil_warp.cuh"
 #include "soil_pair.cuh"
+#include "soil_explicit.cuh"
 
 namespace {
 
@@ -139,6 +140,9 @@ struct clb_handle_s {
     double *zeros_cell = nullptr, *zeros_col = nullptr;  // stand-ins for fields the configuration does not use
     double *d_stats = nullptr;  // [0] dx^2, [1] non-finite count, [2] norm of the tolerance path, [3..6] balance
     int32_t *d_flags = nullptr; // [0] converged, [1] iterations of the tolerance path
+    // explicit stage of EnergyHydrology (soil_explicit.cuh)
+    clb::ExplicitConst explicit_k = {};
+    bool explicit_set = false;
     // multi-GPU
     NcclComm comm = nullptr;
     int32_t n_ranks = 1, rank = 0;
@@ -598,6 +602,68 @@ __global__ void k_test_math(int kind, const double *x, const double *y, double *
 }  // namespace
 
 // =============================================================================
+// ---- the explicit stage of EnergyHydrology (soil_explicit.cuh) --------------------------------
+namespace {
+
+int explicit_ready(clb_handle h, bool aux, bool phase, const char *who)
+{
+    if (h->cfg.model != CLB_ENERGY_HYDROLOGY)
+        return fail(CLB_ERR_INVALID, "%s: EnergyHydrology only (RichardsModel's update_aux! is clb_update_implicit_cache)", who);
+    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
+    if (!h->explicit_set) return fail(CLB_ERR_UNSET, "%s: clb_set_explicit_params was never called", who);
+    TRY(require(h, {CLB_F_NU, CLB_F_THETA_R, CLB_F_K_SAT, CLB_F_S_S, CLB_F_HCM_A, CLB_F_HCM_B, CLB_F_RHO_C_DS,
+                    CLB_F_Y_THETA_L, CLB_F_Y_RHO_E_INT, CLB_F_Y_THETA_I}, who));
+    if (h->cfg.closure == CLB_VAN_GENUCHTEN) TRY(require(h, {CLB_F_HCM_M}, who));
+    if (aux) {
+        TRY(require(h, {CLB_F_KAPPA_DRY, CLB_F_KAPPA_SAT_UNFROZEN, CLB_F_KAPPA_SAT_FROZEN, CLB_F_NU_SS_OM,
+                        CLB_F_NU_SS_QUARTZ, CLB_F_NU_SS_GRAVEL}, who));
+        TRY(alloc_fields(h, {CLB_F_THETA_L_LAG, CLB_F_KAPPA_LAG, CLB_F_K_LAG, CLB_F_P_T, CLB_F_P_PSI,
+                             CLB_F_P_TF_DEPRESSED, CLB_F_TOTAL_WATER, CLB_F_TOTAL_ENERGY}));
+    } else {
+        TRY(require(h, {CLB_F_THETA_L_LAG, CLB_F_KAPPA_LAG, CLB_F_P_T}, who));
+    }
+    if (phase) TRY(alloc_fields(h, {CLB_F_DYE_THETA_L, CLB_F_DYE_THETA_I}));
+    return CLB_OK;
+}
+
+clb::ExplicitView make_explicit_view(clb_handle h)
+{
+    clb::ExplicitView X;
+    double *const *F = h->field;
+    X.kappa_dry = F[CLB_F_KAPPA_DRY]; X.kappa_sat_unfrozen = F[CLB_F_KAPPA_SAT_UNFROZEN];
+    X.kappa_sat_frozen = F[CLB_F_KAPPA_SAT_FROZEN];
+    X.nu_ss_om = F[CLB_F_NU_SS_OM]; X.nu_ss_quartz = F[CLB_F_NU_SS_QUARTZ]; X.nu_ss_gravel = F[CLB_F_NU_SS_GRAVEL];
+    X.p_theta_l = F[CLB_F_THETA_L_LAG]; X.p_kappa = F[CLB_F_KAPPA_LAG]; X.p_K = F[CLB_F_K_LAG];
+    X.p_T = F[CLB_F_P_T]; X.p_psi = F[CLB_F_P_PSI]; X.p_Tf = F[CLB_F_P_TF_DEPRESSED];
+    X.total_water = F[CLB_F_TOTAL_WATER]; X.total_energy = F[CLB_F_TOTAL_ENERGY];
+    X.dYe_theta_l = F[CLB_F_DYE_THETA_L]; X.dYe_theta_i = F[CLB_F_DYE_THETA_I];
+    X.k = h->explicit_k;
+    return X;
+}
+
+template <bool AUX, bool PHASE>
+int launch_explicit(clb_handle h, const char *who)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    TRY(explicit_ready(h, AUX, PHASE, who));
+    const clb::DevView P = make_view(h);
+    const clb::ExplicitView X = make_explicit_view(h);
+    const dim3 grid(grid_for(P.ncol), (unsigned)P.N);
+    nvtxRangePushA(who);
+    const int cl = h->cfg.closure, ma = h->cfg.math_mode;
+    if (cl == 0 && ma == 0) clb::k_explicit_cells<0, 0, AUX, PHASE><<<grid, kBlock, 0, h->stream>>>(P, X);
+    else if (cl == 0 && ma == 1) clb::k_explicit_cells<0, 1, AUX, PHASE><<<grid, kBlock, 0, h->stream>>>(P, X);
+    else if (cl == 1 && ma == 0) clb::k_explicit_cells<1, 0, AUX, PHASE><<<grid, kBlock, 0, h->stream>>>(P, X);
+    else clb::k_explicit_cells<1, 1, AUX, PHASE><<<grid, kBlock, 0, h->stream>>>(P, X);
+    if (AUX) clb::k_explicit_totals<<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, X);
+    nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int clb_test_math(int32_t kind, const double *x, const double *y, double *out, int64_t n)
@@ -942,6 +1008,21 @@ int clb_update_implicit_cache(clb_handle h)
     CUDA_TRY(cudaGetLastError());
     return CLB_OK;
 }
+
+int clb_set_explicit_params(clb_handle h, const clb_explicit_params *p)
+{
+    TRY(check_handle(h));
+    if (!p) return fail(CLB_ERR_INVALID, "clb_set_explicit_params: null parameters");
+    if (!(p->grav > 0.0) || !(p->T_freeze > 0.0))
+        return fail(CLB_ERR_INVALID, "clb_set_explicit_params: grav and T_freeze must be positive");
+    h->explicit_k = {p->Omega, p->gamma, p->gammaT_ref, p->alpha, p->beta, p->T_freeze, p->grav};
+    h->explicit_set = true;
+    return CLB_OK;
+}
+
+int clb_update_aux(clb_handle h) { return launch_explicit<true, false>(h, "update_aux!"); }
+int clb_phase_change_source(clb_handle h) { return launch_explicit<false, true>(h, "source!(PhaseChange)"); }
+int clb_update_aux_and_phase_change(clb_handle h) { return launch_explicit<true, true>(h, "update_aux! + PhaseChange"); }
 
 int clb_update_boundary_fluxes(clb_handle h)
 {

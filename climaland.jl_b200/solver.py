@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import K, ClbError, Config, Stats, check
+from ._lib import K, ClbError, Config, ExplicitParams, Stats, check
 
 # LandParameters constants (ClimaParams defaults; passed in as numbers,
 # src/shared_utilities/Parameters.jl:86-105)
@@ -146,6 +146,21 @@ class SoilColumnSolver:
 
     def ldiv(self):
         check(self.L.clb_ldiv(self.h))
+
+    # ---- explicit stage of EnergyHydrology -------------------
+    def set_explicit_params(self, *, Omega, gamma, gammaT_ref, alpha, beta, T_freeze, grav):
+        """Scalars of EnergyHydrologyParameters (energy_hydrology.jl:150-160) + T_freeze, grav."""
+        p = ExplicitParams(Omega, gamma, gammaT_ref, alpha, beta, T_freeze, grav)
+        check(self.L.clb_set_explicit_params(self.h, C.byref(p)))
+
+    def update_aux(self):
+        check(self.L.clb_update_aux(self.h))
+
+    def phase_change_source(self):
+        check(self.L.clb_phase_change_source(self.h))
+
+    def update_aux_and_phase_change(self):
+        check(self.L.clb_update_aux_and_phase_change(self.h))
 
     def implicit_step(self, dtgamma, max_iters, tol=-1.0, want_stats=False):
         st = Stats() if want_stats else None

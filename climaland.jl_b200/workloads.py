@@ -90,6 +90,31 @@ def make_workload(model, ncol, N=15, seed=0, topmodel=False, ice=True, depth=50.
     return w
 
 
+# scalars of EnergyHydrologyParameters pinned by the reference's own test
+# (test/standalone/Soil/soil_parameterizations.jl:71-76); T_freeze, grav: ClimaParams defaults
+EXPLICIT_SCALARS = dict(Omega=7.0, gamma=2.64e-2, gammaT_ref=288.0, alpha=0.24, beta=18.3, T_freeze=273.15, grav=9.81)
+
+
+def make_explicit_params(w, seed=0):
+    """The six per-cell parameter fields only the explicit stage reads (update_aux!,
+    energy_hydrology.jl:722-814), derived as EnergyHydrologyParameters derives them
+    (soil_heat_parameterizations.jl:338-395) from synthetic soil composition fractions."""
+    rng = np.random.default_rng(10_000 + seed)
+    shp = w["nu"].shape
+    nu = w["nu"]
+    om = rng.uniform(0.0, 0.2, shp)
+    quartz = rng.uniform(0.1, 0.5, shp)
+    gravel = rng.uniform(0.0, 0.2, shp)
+    k_om, k_quartz, k_min, k_ice, k_liq, k_air = 0.25, 8.0, 2.5, 2.21, 0.57, 0.025
+    k_solid = k_om ** om * k_quartz ** quartz * k_min ** (1.0 - om - quartz)
+    rho_p = 2700.0
+    rho_b = (1.0 - nu) * rho_p
+    return dict(nu_ss_om=om, nu_ss_quartz=quartz, nu_ss_gravel=gravel,
+                kappa_sat_frozen=k_solid ** (1.0 - nu) * k_ice ** nu,
+                kappa_sat_unfrozen=k_solid ** (1.0 - nu) * k_liq ** nu,
+                kappa_dry=((0.053 * k_solid - k_air) * rho_b + k_air * rho_p) / (rho_p - (1.0 - 0.053) * rho_b))
+
+
 CELL_PARAMS = ("nu", "theta_r", "K_sat", "S_s", "hcm_a", "hcm_b", "hcm_m", "rho_c_ds", "k_lag", "kappa_lag",
                "theta_l_lag", "is_saturated")
 COL_PARAMS = ("r_ss", "r_ess", "h_grad", "theta_bc_top", "theta_bc_bot")

@@ -15,6 +15,8 @@
  *                               (ClimaCore MatrixFields.field_matrix_solve!)
  *   Newton/ARS111 stage         src/simulations/Simulations.jl:127-135
  *                               (ClimaTimeSteppers IMEXAlgorithm + NewtonsMethod)
+ *   make_update_aux (EH)        energy_hydrology.jl:722-814   } the explicit stage right before the
+ *   source!(::PhaseChange)      energy_hydrology.jl:846-906   } implicit solve
  *
  * Conventions
  *   - plain C: pointers, sizes, strides; no C++ or torch types.
@@ -45,7 +47,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define CLB_ABI_VERSION 1
+#define CLB_ABI_VERSION 2
 
 typedef struct clb_handle_s *clb_handle;
 
@@ -117,6 +119,12 @@ typedef enum {
     CLB_F_X_THETA_L, CLB_F_X_RHO_E_INT, CLB_F_X_THETA_I,
     /* ---- new state of the fused stage in out-of-place mode -- cell */
     CLB_F_U_THETA_L, CLB_F_U_RHO_E_INT,
+    /* ---- explicit stage of EnergyHydrology (energy_hydrology.jl:722-906) -- cell
+     *      parameters only update_aux! reads (EnergyHydrologyParameters :60-170) */
+    CLB_F_KAPPA_DRY, CLB_F_KAPPA_SAT_UNFROZEN, CLB_F_KAPPA_SAT_FROZEN,
+    CLB_F_NU_SS_OM, CLB_F_NU_SS_QUARTZ, CLB_F_NU_SS_GRAVEL,
+    CLB_F_P_TF_DEPRESSED,                    /* p.soil.Tf_depressed */
+    CLB_F_DYE_THETA_L, CLB_F_DYE_THETA_I,    /* explicit tendency the PhaseChange source adds into */
     CLB_F_NUM_CELL,
     /* ---- per-column fields */
     CLB_F_R_SS = CLB_F_NUM_CELL, CLB_F_R_ESS, CLB_F_H_GRAD,     /* lagged TOPMODEL */
@@ -128,6 +136,7 @@ typedef enum {
     CLB_F_B_INTF_W, CLB_F_B_INTF_E, CLB_F_X_INTF_W, CLB_F_X_INTF_E,
     CLB_F_AREA_WEIGHT,                        /* weights of the global balance sums */
     CLB_F_U_INTF_W, CLB_F_U_INTF_E,           /* out-of-place new flux integrals */
+    CLB_F_TOTAL_ENERGY,                       /* p.soil.total_energy (explicit update_aux!) */
     CLB_F_NUM
 } clb_field;
 
@@ -213,6 +222,28 @@ int clb_compute_jacobian(clb_handle h, double dtgamma);
 /* ldiv!(x, W, b): BlockDiagonalSolve / BlockLowerTriangularSolve(theta_l),
  * implicit_timestepping.jl:160-171; x = -b for the -I blocks. */
 int clb_ldiv(clb_handle h);
+
+/* ---- the explicit stage of EnergyHydrology ------------- */
+/* Scalars of EnergyHydrologyParameters (energy_hydrology.jl:150-160: Omega, gamma,
+ * gammaT_ref, alpha, beta of the Balland-Arp / impedance / viscosity closures) and the
+ * LandParameters constants T_freeze, grav (Parameters.jl:21-22). */
+typedef struct {
+    double Omega, gamma, gammaT_ref, alpha, beta, T_freeze, grav;
+} clb_explicit_params;
+int clb_set_explicit_params(clb_handle h, const clb_explicit_params *p);
+/* update_aux!(p, Y, t) of EnergyHydrology, energy_hydrology.jl:722-814: from Y.{theta_l, rho_e_int,
+ * theta_i} writes p.soil.theta_l -> CLB_F_THETA_L_LAG, kappa -> CLB_F_KAPPA_LAG, K -> CLB_F_K_LAG (the
+ * lagged inputs of the implicit stage, produced in place), T -> CLB_F_P_T, psi -> CLB_F_P_PSI,
+ * Tf_depressed -> CLB_F_P_TF_DEPRESSED, total_water -> CLB_F_TOTAL_WATER, total_energy ->
+ * CLB_F_TOTAL_ENERGY.  RichardsModel's update_aux! is clb_update_implicit_cache (models.jl:207-210). */
+int clb_update_aux(clb_handle h);
+/* source!(dY, ::PhaseChange, Y, p, model), energy_hydrology.jl:846-906: ADDS -S into
+ * CLB_F_DYE_THETA_L and (rho_l / rho_i) S into CLB_F_DYE_THETA_I, S = phase_change_source(p.theta_l,
+ * Y.theta_i, p.T, thermal_time(rho_c_s, dz, p.kappa), ...) (soil_heat_parameterizations.jl:35-122). */
+int clb_phase_change_source(clb_handle h);
+/* Both in one pass over the fields (the source reads the aux values it has just computed): what a
+ * resident explicit stage calls. */
+int clb_update_aux_and_phase_change(clb_handle h);
 
 /* ---- the fused implicit stage -------------------------------------------- */
 /* One implicit ARS111 stage on the resident state Y (in: U = temp, out: new U):

@@ -59,6 +59,23 @@ class _Jacobian(C.Structure):
                                    "w22_lo", "w22_di", "w22_up")]
 
 
+class _ExplicitParams(C.Structure):
+    _fields_ = [(n, _dp) for n in ("kappa_dry", "kappa_sat_unfrozen", "kappa_sat_frozen", "nu_ss_om",
+                                   "nu_ss_quartz", "nu_ss_gravel")] + \
+               [(n, C.c_double) for n in ("Omega", "gamma", "gammaT_ref", "alpha", "beta", "T_freeze", "grav")]
+
+
+class _Aux(C.Structure):
+    _fields_ = [(n, _dp) for n in ("theta_l", "kappa", "T", "K", "psi", "Tf_depressed", "total_water",
+                                   "total_energy")]
+
+
+# scalar parameters of the explicit stage: EnergyHydrologyParameters defaults pinned by the reference's
+# test/standalone/Soil/soil_parameterizations.jl:71-76; T_freeze / grav: ClimaParams 1.1.4 defaults
+EXPLICIT_SCALARS = dict(Omega=7.0, gamma=2.64e-2, gammaT_ref=288.0, alpha=0.24, beta=18.3, T_freeze=273.15,
+                        grav=9.81)
+EXPLICIT_CELL = ("kappa_dry", "kappa_sat_unfrozen", "kappa_sat_frozen", "nu_ss_om", "nu_ss_quartz", "nu_ss_gravel")
+
 _lib = None
 
 
@@ -76,11 +93,22 @@ def lib():
                             ("orc_volumetric_heat_capacity", 7), ("orc_temperature_from_rho_e_int", 6),
                             ("orc_volumetric_internal_energy", 6),
                             ("orc_volumetric_internal_energy_liq", 4), ("orc_heaviside", 2),
-                            ("orc_impedance_factor", 2), ("orc_viscosity_factor", 3)]:
+                            ("orc_impedance_factor", 2), ("orc_viscosity_factor", 3),
+                            ("orc_kappa_sat", 4), ("orc_relative_saturation", 3), ("orc_kersten_number", 7),
+                            ("orc_thermal_conductivity", 3), ("orc_thermal_time", 3)]:
             f = getattr(L, name)
             f.restype = d
             f.argtypes = [d] * nargs
+        L.orc_soil_Tf_depressed.restype = d
+        L.orc_soil_Tf_depressed.argtypes = [C.c_int] + [d] * 12
+        L.orc_phase_change_source.restype = d
+        L.orc_phase_change_source.argtypes = [C.c_int] + [d] * 14
         pp, ps, pc, pj = (C.POINTER(t) for t in (_Problem, _State, _Cache, _Jacobian))
+        px, pa = C.POINTER(_ExplicitParams), C.POINTER(_Aux)
+        L.orc_update_aux.argtypes = [pp, px, ps, pa]
+        L.orc_update_aux.restype = None
+        L.orc_phase_change.argtypes = [pp, px, ps, pa, _dp, _dp]
+        L.orc_phase_change.restype = None
         L.orc_update_implicit_cache.argtypes = [pp, ps, pc]
         L.orc_update_boundary_fluxes.argtypes = [pp, ps, pc]
         L.orc_compute_imp_tendency.argtypes = [pp, ps, pc, ps]
@@ -190,6 +218,23 @@ class Problem:
                                      int(max_iters), float(tol), C.byref(nrm))
         return it, nrm.value
 
+    # ---- explicit stage of EnergyHydrology -------------------------------
+    def explicit_params(self, scalars=None, **cell_fields):
+        """EnergyHydrologyParameters the explicit stage reads: six per-cell fields + scalars."""
+        return ExplicitParams(self, scalars, **cell_fields)
+
+    def new_aux(self):
+        return Aux(self)
+
+    def update_aux(self, X, Y, a):
+        P, x, y, aa = self.c_struct(), X.c_struct(), Y.c_struct(), a.c_struct()
+        lib().orc_update_aux(C.byref(P), C.byref(x), C.byref(y), C.byref(aa))
+
+    def phase_change(self, X, Y, a, dtheta_l, dtheta_i):
+        """source!(dY, ::PhaseChange, ...): ADDS into dtheta_l, dtheta_i (C-contiguous (ncol, N))."""
+        P, x, y, aa = self.c_struct(), X.c_struct(), Y.c_struct(), a.c_struct()
+        lib().orc_phase_change(C.byref(P), C.byref(x), C.byref(y), C.byref(aa), _ptr(dtheta_l), _ptr(dtheta_i))
+
     def column_integral(self, field):
         out = np.zeros(self.ncol)
         P = self.c_struct()
@@ -228,6 +273,30 @@ class Cache(_Bundle):
     cell = ("K", "psi", "T")
     col = ("top_bc_w", "bot_bc_w", "top_bc_h", "bot_bc_h", "dfluxBCdY", "total_water")
     ctype = _Cache
+
+
+class Aux(_Bundle):
+    cell = ("theta_l", "kappa", "T", "K", "psi", "Tf_depressed")
+    col, ctype = ("total_water", "total_energy"), _Aux
+
+
+class ExplicitParams:
+    def __init__(self, prob, scalars=None, **cell_fields):
+        self.scalars = dict(EXPLICIT_SCALARS)
+        self.scalars.update(scalars or {})
+        self.f = {}
+        for k in EXPLICIT_CELL:
+            a = np.empty((prob.ncol, prob.N))
+            a[...] = cell_fields[k]
+            self.f[k] = a
+
+    def c_struct(self):
+        s = _ExplicitParams()
+        for k, v in self.f.items():
+            setattr(s, k, _ptr(v))
+        for k, v in self.scalars.items():
+            setattr(s, k, float(v))
+        return s
 
 
 class Jacobian(_Bundle):

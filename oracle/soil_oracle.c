@@ -613,3 +613,149 @@ void orc_column_integral(const orc_problem *P, const double *field, double *out)
         out[c] = s;
     }
 }
+
+/* ------------------------------------------------------------------ */
+/* explicit stage of EnergyHydrology: update_aux! and PhaseChange      */
+/* (the step immediately before the implicit solve)  */
+/* ------------------------------------------------------------------ */
+
+/* soil_heat_parameterizations.jl:240-254 */
+double orc_kappa_sat(double theta_l, double theta_i, double kappa_sat_unfrozen, double kappa_sat_frozen)
+{
+    double theta_w = theta_l + theta_i;
+    if (theta_w < EPS64) return (kappa_sat_unfrozen + kappa_sat_frozen) / 2.0;
+    return pow(kappa_sat_unfrozen, theta_l / theta_w) * pow(kappa_sat_frozen, theta_i / theta_w);
+}
+
+/* soil_heat_parameterizations.jl:283-285 */
+double orc_relative_saturation(double theta_l, double theta_i, double nu) { return (theta_l + theta_i) / nu; }
+
+/* soil_heat_parameterizations.jl:301-323 (Balland and Arp) */
+double orc_kersten_number(double theta_i, double S_r, double alpha, double beta, double nu_ss_om,
+                          double nu_ss_quartz, double nu_ss_gravel)
+{
+    if (theta_i < EPS64) {
+        return pow(S_r, (1.0 + nu_ss_om - alpha * nu_ss_quartz - nu_ss_gravel) / 2.0) *
+               pow(pow(1.0 + exp(-beta * S_r), -3.0) - pow((1.0 - S_r) / 2.0, 3.0), 1.0 - nu_ss_om);
+    }
+    return pow(S_r, 1.0 + nu_ss_om);
+}
+
+/* soil_heat_parameterizations.jl:266-269 */
+double orc_thermal_conductivity(double kappa_dry, double K_e, double kappa_sat)
+{
+    return K_e * kappa_sat + (1.0 - K_e) * kappa_dry;
+}
+
+/* soil_heat_parameterizations.jl:59-61: 3 * rho_c * dz^2 / kappa */
+double orc_thermal_time(double rho_c, double dz, double kappa) { return 3.0 * rho_c * (dz * dz) / kappa; }
+
+static inline double any_matric_potential(int closure, double a, double b, double m, double S)
+{
+    return closure == ORC_VAN_GENUCHTEN ? orc_vg_matric_potential(a, b, m, S) : orc_bc_matric_potential(a, b, S);
+}
+
+static inline double any_inverse_matric_potential(int closure, double a, double b, double m, double psi)
+{
+    return closure == ORC_VAN_GENUCHTEN ? orc_vg_inverse_matric_potential(a, b, m, psi)
+                                        : orc_bc_inverse_matric_potential(a, b, psi);
+}
+
+/* soil_heat_parameterizations.jl:35-52.  The signature is (.., _rho_ice, _rho_liq, ..) and the body
+ * uses _rho_ice / _rho_liq; the two arguments are named by POSITION here because the reference's two call
+ * sites pass them in different orders (see orc_update_aux). */
+double orc_soil_Tf_depressed(int closure, double a, double b, double m, double theta_l, double theta_i, double nu,
+                             double theta_r, double rho_first, double rho_second, double T_freeze, double grav,
+                             double LH_f0)
+{
+    double theta_tot = dmin(rho_first / rho_second * theta_i + theta_l, nu);
+    double psi_w0 = any_matric_potential(closure, a, b, m, orc_effective_saturation(nu, theta_tot, theta_r));
+    return dmax(T_freeze * exp(grav * psi_w0 / LH_f0), 1.0);
+}
+
+/* soil_heat_parameterizations.jl:89-122 */
+double orc_phase_change_source(int closure, double a, double b, double m, double theta_l, double theta_i, double T,
+                               double tau, double nu, double theta_r, double rho_i, double rho_l, double LH_f0,
+                               double T_freeze, double grav)
+{
+    double Tf = orc_soil_Tf_depressed(closure, a, b, m, theta_l, theta_i, nu, theta_r, rho_i, rho_l, T_freeze, grav,
+                                      LH_f0);
+    double psi_T = LH_f0 / grav * log(T / Tf) * orc_heaviside(Tf - T, 0.0);
+    double theta_tot = dmin(rho_i / rho_l * theta_i + theta_l, nu);
+    double psi_w0 = any_matric_potential(closure, a, b, m, orc_effective_saturation(nu, theta_tot, theta_r));
+    double theta_star = any_inverse_matric_potential(closure, a, b, m, psi_w0 + psi_T) * (nu - theta_r) + theta_r;
+    return (theta_l - theta_star) / tau;
+}
+
+/* update_aux!(p, Y, t): energy_hydrology.jl:722-814.
+ *   theta_l  :746-747   volumetric_liquid_fraction(theta_l, nu - theta_i, theta_r)
+ *   kappa    :757-771   thermal_conductivity(kappa_dry, kersten_number(..), kappa_sat(..))
+ *   T        :773-783   temperature_from_rho_e_int(rho_e_int, theta_i, volumetric_heat_capacity(p.theta_l, ..))
+ *   K        :785-792   impedance * viscosity * hydraulic_conductivity(effective_saturation(nu, theta_l, theta_r))
+ *                       -- the saturation uses nu, NOT nu - theta_i, and the augmented theta_l (Y), not p.theta_l
+ *   psi      :793-794   pressure_head(.., nu - theta_i, ..)
+ *   Tf_depressed :800-811  called as soil_Tf_depressed(.., _rho_l, _rho_i, ..) while the function's positional
+ *                       parameters are (_rho_ice, _rho_liq): the cached field therefore uses rho_l / rho_i as
+ *                       the ice-to-liquid ratio.  PhaseChange (below) calls it with (_rho_i, _rho_l).  Both are
+ *                       restated as the reference evaluates them.
+ *   total_water  :1292-1306  column integral of theta_l + theta_i * rho_i / rho_l
+ *   total_energy :1318-1327  column integral of rho_e_int */
+void orc_update_aux(const orc_problem *P, const orc_explicit_params *X, const orc_state *Y, orc_aux *a)
+{
+    const int N = P->N;
+    FOR_COLUMNS(P, c)
+    {
+        double tw = 0.0, te = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const int64_t k = c * N + i;
+            const double nu = P->nu[k], theta_r = P->theta_r[k];
+            const double th = Y->theta_l[k], thi = Y->theta_i[k];
+            const double theta_l = orc_volumetric_liquid_fraction(th, nu - thi, theta_r);
+            a->theta_l[k] = theta_l;
+            a->kappa[k] = orc_thermal_conductivity(
+                X->kappa_dry[k],
+                orc_kersten_number(thi, orc_relative_saturation(theta_l, thi, nu), X->alpha, X->beta, X->nu_ss_om[k],
+                                   X->nu_ss_quartz[k], X->nu_ss_gravel[k]),
+                orc_kappa_sat(theta_l, thi, X->kappa_sat_unfrozen[k], X->kappa_sat_frozen[k]));
+            const double T = orc_temperature_from_rho_e_int(
+                Y->rho_e_int[k], thi,
+                orc_volumetric_heat_capacity(theta_l, thi, P->rho_c_ds[k], P->rho_l, P->cp_l, P->rho_i, P->cp_i),
+                P->rho_i, P->T_ref, P->LH_f0);
+            a->T[k] = T;
+            a->K[k] = orc_impedance_factor(thi / (theta_l + thi - theta_r), X->Omega) *
+                      orc_viscosity_factor(T, X->gamma, X->gammaT_ref) *
+                      hcm_conductivity(P, k, orc_effective_saturation(nu, th, theta_r));
+            a->psi[k] = hcm_pressure_head(P, k, th, nu - thi);
+            a->Tf_depressed[k] = orc_soil_Tf_depressed(P->closure, P->hcm_a[k], P->hcm_b[k], P->hcm_m ? P->hcm_m[k] : 0.0,
+                                                       theta_l, thi, nu, theta_r, P->rho_l, P->rho_i, X->T_freeze,
+                                                       X->grav, P->LH_f0);
+            tw += (th + thi * P->rho_i / P->rho_l) * dz_cell(P, i);
+            te += Y->rho_e_int[k] * dz_cell(P, i);
+        }
+        if (a->total_water) a->total_water[c] = tw;
+        if (a->total_energy) a->total_energy[c] = te;
+    }
+}
+
+/* source!(dY, ::PhaseChange, Y, p, model): energy_hydrology.jl:846-906; dz = layer thickness
+ * (model.domain.fields.dz = Domains.get_dz's third value, Domains.jl:947-948) */
+void orc_phase_change(const orc_problem *P, const orc_explicit_params *X, const orc_state *Y, const orc_aux *a,
+                      double *dtheta_l, double *dtheta_i)
+{
+    const int N = P->N;
+    FOR_COLUMNS(P, c)
+    {
+        for (int i = 0; i < N; ++i) {
+            const int64_t k = c * N + i;
+            const double thi = Y->theta_i[k];
+            const double rho_c = orc_volumetric_heat_capacity(a->theta_l[k], thi, P->rho_c_ds[k], P->rho_l, P->cp_l,
+                                                              P->rho_i, P->cp_i);
+            const double tau = orc_thermal_time(rho_c, dz_cell(P, i), a->kappa[k]);
+            const double s = orc_phase_change_source(P->closure, P->hcm_a[k], P->hcm_b[k], P->hcm_m ? P->hcm_m[k] : 0.0,
+                                                     a->theta_l[k], thi, a->T[k], tau, P->nu[k], P->theta_r[k],
+                                                     P->rho_i, P->rho_l, P->LH_f0, X->T_freeze, X->grav);
+            dtheta_l[k] += -s;
+            dtheta_i[k] += (P->rho_l / P->rho_i) * s;
+        }
+    }
+}

@@ -108,6 +108,43 @@ double orc_heaviside(double x, double a);
 double orc_impedance_factor(double f_i, double Omega);
 double orc_viscosity_factor(double T, double gamma, double gammaT_ref);
 
+double orc_kappa_sat(double theta_l, double theta_i, double kappa_sat_unfrozen, double kappa_sat_frozen);
+double orc_relative_saturation(double theta_l, double theta_i, double nu);
+double orc_kersten_number(double theta_i, double S_r, double alpha, double beta, double nu_ss_om,
+                          double nu_ss_quartz, double nu_ss_gravel);
+double orc_thermal_conductivity(double kappa_dry, double K_e, double kappa_sat);
+double orc_thermal_time(double rho_c, double dz, double kappa);
+/* closure: ORC_VAN_GENUCHTEN (a = alpha, b = n, m) | ORC_BROOKS_COREY (a = c, b = psi_b).  rho_first / rho_second
+ * are the reference's positional `_rho_ice`, `_rho_liq` arguments (see orc_update_aux for why they are named
+ * by position). */
+double orc_soil_Tf_depressed(int closure, double a, double b, double m, double theta_l, double theta_i, double nu,
+                             double theta_r, double rho_first, double rho_second, double T_freeze, double grav,
+                             double LH_f0);
+double orc_phase_change_source(int closure, double a, double b, double m, double theta_l, double theta_i, double T,
+                               double tau, double nu, double theta_r, double rho_i, double rho_l, double LH_f0,
+                               double T_freeze, double grav);
+
+/* ---- explicit stage of EnergyHydrology ------------------------------------- */
+/* the parameters only the explicit stage reads (EnergyHydrologyParameters, energy_hydrology.jl:60-170) */
+typedef struct {
+    const double *kappa_dry, *kappa_sat_unfrozen, *kappa_sat_frozen;   /* [ncol*N] */
+    const double *nu_ss_om, *nu_ss_quartz, *nu_ss_gravel;              /* [ncol*N] */
+    double Omega, gamma, gammaT_ref, alpha, beta;                      /* scalars (:150-160) */
+    double T_freeze, grav;                                             /* LandParameters */
+} orc_explicit_params;
+
+/* p.soil.{theta_l, kappa, T, K, psi, Tf_depressed, total_water, total_energy} */
+typedef struct {
+    double *theta_l, *kappa, *T, *K, *psi, *Tf_depressed;   /* [ncol*N] */
+    double *total_water, *total_energy;                     /* [ncol] */
+} orc_aux;
+
+/* update_aux!(p, Y, t) of EnergyHydrology: energy_hydrology.jl:722-814 */
+void orc_update_aux(const orc_problem *P, const orc_explicit_params *X, const orc_state *Y, orc_aux *a);
+/* source!(dY, ::PhaseChange, Y, p, model): energy_hydrology.jl:846-906; ADDS into dtheta_l / dtheta_i */
+void orc_phase_change(const orc_problem *P, const orc_explicit_params *X, const orc_state *Y, const orc_aux *a,
+                      double *dtheta_l, double *dtheta_i);
+
 /* ---- the hooks (each cites the reference in soil_oracle.c) */
 void orc_update_implicit_cache(const orc_problem *P, const orc_state *Y, orc_cache *p);
 /* explicit-stage flavour of the boundary-flux update: always evaluates (rre.jl:111-149) */

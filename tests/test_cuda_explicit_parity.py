@@ -1,0 +1,115 @@
+"""GPU parity of the explicit-stage soil kernels (update_aux! of EnergyHydrology and the PhaseChange
+source; energy_hydrology.jl:722-906) against the CPU oracle on identical seeded inputs,
+through the C ABI.  Tolerance: 1e-12 norm-wise relative per call (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, cuda_solver, oracle_problem
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _setup(ncol, N, seed, closure, math_mode, layout):
+    import climaland_b200 as cl
+    from climaland_b200 import workloads
+    w = workloads.make_workload("energy_hydrology", ncol, N=N, seed=seed, topmodel=False)
+    if closure == 1:
+        from test_cuda_hooks_parity import _to_brooks_corey
+        w = _to_brooks_corey(w)
+    xp = workloads.make_explicit_params(w, seed)
+    P, Y, cache = oracle_problem(w, closure=closure, nthreads=4)
+    Xp = P.explicit_params(**xp)
+    a = P.new_aux()
+    P.update_aux(Xp, Y, a)
+    s = cuda_solver(w, closure=closure, math_mode=math_mode, layout=layout)
+    for k, v in xp.items():
+        s.set(k, v)
+    s.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+    P.cache = cache  # boundary fluxes of the workload, for the implicit stage
+    return cl, w, P, Xp, Y, a, s
+
+
+AUX_FIELDS = [("theta_l_lag", "theta_l"), ("kappa_lag", "kappa"), ("k_lag", "K"), ("p_t", "T"), ("p_psi", "psi"),
+              ("p_tf_depressed", "Tf_depressed"), ("total_water", "total_water"), ("total_energy", "total_energy")]
+
+
+@pytest.mark.parametrize("layout", [1, 2], ids=["colfast", "levfast"])
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["fast", "libm"])
+@pytest.mark.parametrize("closure,N,ncol", [(0, 15, 1000), (0, 50, 130), (1, 15, 257)])
+def test_update_aux(closure, N, ncol, math_mode, layout):
+    cl, w, P, Xp, Y, a, s = _setup(ncol, N, 11, closure, math_mode, layout)
+    s.update_aux()
+    for dev, orc_name in AUX_FIELDS:
+        assert_close(s.get(dev), getattr(a, orc_name), TOL, orc_name)
+    s.close()
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["separate", "fused"])
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["fast", "libm"])
+@pytest.mark.parametrize("closure,N,ncol", [(0, 15, 1000), (1, 15, 257)])
+def test_phase_change_source(closure, N, ncol, math_mode, fused):
+    cl, w, P, Xp, Y, a, s = _setup(ncol, N, 12, closure, math_mode, 0)
+    rng = np.random.default_rng(0)
+    d0l, d0i = rng.normal(0, 1e-8, Y.theta_l.shape), rng.normal(0, 1e-8, Y.theta_l.shape)
+    dl, di = d0l.copy(), d0i.copy()
+    P.phase_change(Xp, Y, a, dl, di)
+    s.set("dye_theta_l", d0l)
+    s.set("dye_theta_i", d0i)
+    if fused:
+        s.update_aux_and_phase_change()
+    else:
+        s.update_aux()
+        s.phase_change_source()
+    # the source itself (what was added) to 1e-12 of its own scale, and the accumulated tendency
+    assert_close(s.get("dye_theta_l") - d0l, dl - d0l, 1e-9, "source (difference of accumulations)")
+    assert_close(s.get("dye_theta_l"), dl, TOL, "dY.theta_l")
+    assert_close(s.get("dye_theta_i"), di, TOL, "dY.theta_i")
+    s.close()
+
+
+def test_phase_change_alone_matches_source_scale():
+    """zero initial tendency: the kernel's source against the oracle's at 1e-12 of the source's own scale"""
+    cl, w, P, Xp, Y, a, s = _setup(2000, 15, 13, 0, 0, 0)
+    dl, di = np.zeros_like(Y.theta_l), np.zeros_like(Y.theta_l)
+    P.phase_change(Xp, Y, a, dl, di)
+    s.update_aux_and_phase_change()
+    assert np.abs(dl).max() > 0.0
+    assert_close(s.get("dye_theta_l"), dl, TOL, "source theta_l")
+    assert_close(s.get("dye_theta_i"), di, TOL, "source theta_i")
+    s.close()
+
+
+def test_explicit_stage_feeds_the_implicit_stage():
+    """update_aux! writes the lagged inputs of the implicit stage in place: a fused implicit stage after
+    it matches the oracle's stage run on the oracle's own aux values."""
+    cl, w, P, Xp, Y, a, s = _setup(512, 15, 14, 0, 0, 0)
+    s.update_aux()
+    P.set("K_lag", a.K)
+    P.set("kappa_lag", a.kappa)
+    P.set("theta_l_lag", a.theta_l)
+    U = Y.copy()
+    P.implicit_step(U, 900.0, 3, p=P.cache)
+    s.implicit_step(900.0, 3)
+    assert_close(s.get("y_theta_l"), U.theta_l, TOL, "theta_l after the stage")
+    assert_close(s.get("y_rho_e_int"), U.rho_e_int, TOL, "rho_e_int after the stage")
+    s.close()
+
+
+def test_errors():
+    import climaland_b200 as cl
+    from climaland_b200 import workloads
+    w = workloads.make_workload("energy_hydrology", 64, N=15, seed=1)
+    s = cuda_solver(w)
+    with pytest.raises(cl.ClbError, match="clb_set_explicit_params"):
+        s.update_aux()
+    s.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+    with pytest.raises(cl.ClbError, match="never set"):
+        s.update_aux()
+    s.close()
+    wr = workloads.make_workload("richards", 64, N=15, seed=1)
+    r = cuda_solver(wr)
+    r.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+    with pytest.raises(cl.ClbError, match="EnergyHydrology only"):
+        r.update_aux()
+    r.close()
