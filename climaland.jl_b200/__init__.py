@@ -11,9 +11,10 @@ from .solver import (BOT_FLUX, BOT_FREE_DRAINAGE, BOT_MOISTURE_STATE, BROOKS_COR
                      LAYOUT_COLUMN_FASTEST, LAYOUT_LEVEL_FASTEST, SoilColumnSolver)
 
 from .soil import (B200SoilJacobian, BrooksCorey, Column, EnergyHydrology, EnergyHydrologyParameters, FreeDrainage,
-                   FusedSoilNewton, HeatFluxBC, IMEXAlgorithm, LandSimulation, MoistureStateBC, NewtonsMethod,
+                   FusedSoilNewton, HeatFluxBC, IMEXAlgorithm, LandSimulation, MoistureStateBC, NewtonsMethod, PhaseChange,
                    RichardsModel, RichardsParameters, TOPMODELSubsurfaceRunoff, WaterFluxBC, WaterHeatBC,
                    initialize, initialize_jacobian, ldiv, make_compute_imp_tendency, make_compute_jacobian,
-                   make_update_boundary_fluxes, make_update_implicit_cache, vanGenuchten)
+                   make_phase_change_source, make_update_aux, make_update_boundary_fluxes, make_update_implicit_cache,
+                   vanGenuchten)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

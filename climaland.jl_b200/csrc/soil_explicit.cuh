@@ -17,9 +17,13 @@
 // thread-per-column kernel (3 reads per cell).  Pointwise FP64 work: ~17 powers per cell.
 //   LIBM mode: the reference's pow / exp / log expressions literally with CUDA libm.
 //   FAST mode: x^y = exp(y log x) with the branch-free functions of soil_math.cuh (<= ~4e-15 relative for
-//              the exponents that occur); zero bases are handled explicitly.
+//              the exponents that occur); zero bases are handled explicitly; integer powers are products,
+//              10^x = exp(x ln 10), products of powers share one exp, and a cell without ice evaluates the
+//              closure and the depressed freezing point once instead of twice (theta_i = 0 makes the two
+//              saturations / the two ice-to-liquid ratios coincide).
 #pragma once
 #include "soil_device.cuh"
+#include "soil_mathv.cuh"
 
 namespace clb {
 
@@ -37,16 +41,37 @@ struct ExplicitView {
     ExplicitConst k;
 };
 
+// Table-driven log / exp of soil_mathv.cuh (11 / 10 FP64 instructions against 26 / 17 of the series-only
+// versions), reading the 2.5 KB of tables through L1 from global memory.  tlog: x normal and > 0, absolute
+// error ~2^-56 max(1, |log x|) -- what a power needs, not a relative bound near 1; texp: no special cases, the
+// power of two is clamped to the normal range.
+__device__ __forceinline__ double tlog(double x)
+{
+    const fmv::MathTab MT{mtab::g_log_tab, mtab::g_exp_tab};
+    const double xv[1] = {x};
+    double r[1];
+    fmv::log_tab<1>(MT, xv, r);
+    return r[0];
+}
+__device__ __forceinline__ double texp(double x)
+{
+    const fmv::MathTab MT{mtab::g_log_tab, mtab::g_exp_tab};
+    const double xv[1] = {x};
+    double r[1];
+    fmv::exp_tab<1>(MT, xv, r);
+    return r[0];
+}
+
 // x^y for x >= 0 (y finite): the reference's Float64 ^ Float64
 template <int MATH>
 __device__ __forceinline__ double pw(double x, double y)
 {
     if (MATH == kMathLibm) return pow(x, y);
     if (x == 0.0) return (y > 0.0) ? 0.0 : ((y == 0.0) ? 1.0 : INFINITY);
-    return fm::exp(y * fm::log(x));
+    return texp(y * tlog(x));
 }
 template <int MATH>
-__device__ __forceinline__ double ex(double x) { return (MATH == kMathLibm) ? exp(x) : fm::exp(x); }
+__device__ __forceinline__ double ex(double x) { return (MATH == kMathLibm) ? exp(x) : texp(x); }
 template <int MATH>
 __device__ __forceinline__ double lg(double x) { return (MATH == kMathLibm) ? log(x) : fm::log(x); }
 
@@ -54,7 +79,11 @@ __device__ __forceinline__ double lg(double x) { return (MATH == kMathLibm) ? lo
 template <int CLOSURE, int MATH>
 __device__ __forceinline__ double matric_potential(const HydroCell &p, double S)
 {
-    if (CLOSURE == kVanGenuchten) return -pw<MATH>((pw<MATH>(S, -1.0 / p.m) - 1.0) * pw<MATH>(p.a, -p.b), 1.0 / p.b);
+    if (CLOSURE == kVanGenuchten) {
+        if (MATH == kMathLibm) return -pw<MATH>((pw<MATH>(S, -1.0 / p.m) - 1.0) * pw<MATH>(p.a, -p.b), 1.0 / p.b);
+        // (u alpha^-n)^(1/n) = u^(1/n) / alpha
+        return -(pw<MATH>(pw<MATH>(S, -1.0 / p.m) - 1.0, 1.0 / p.b) / p.a);
+    }
     return p.b * pw<MATH>(S, -1.0 / p.a);
 }
 
@@ -92,7 +121,9 @@ __device__ __forceinline__ double kappa_sat(double theta_l, double theta_i, doub
 {
     const double theta_w = theta_l + theta_i;
     if (theta_w < kEps) return (ku + kf) / 2.0;
-    return pw<MATH>(ku, theta_l / theta_w) * pw<MATH>(kf, theta_i / theta_w);
+    if (MATH == kMathLibm) return pw<MATH>(ku, theta_l / theta_w) * pw<MATH>(kf, theta_i / theta_w);
+    if (theta_i == 0.0) return ku;  // ku^1 * kf^0
+    return texp((theta_l / theta_w) * tlog(ku) + (theta_i / theta_w) * tlog(kf));
 }
 
 // soil_heat_parameterizations.jl:301-323
@@ -100,9 +131,16 @@ template <int MATH>
 __device__ __forceinline__ double kersten_number(double theta_i, double S_r, double alpha, double beta, double om,
                                                  double quartz, double gravel)
 {
-    if (theta_i < kEps)
-        return pw<MATH>(S_r, (1.0 + om - alpha * quartz - gravel) / 2.0) *
-               pw<MATH>(pw<MATH>(1.0 + ex<MATH>(-beta * S_r), -3.0) - pw<MATH>((1.0 - S_r) / 2.0, 3.0), 1.0 - om);
+    if (theta_i < kEps) {
+        if (MATH == kMathLibm)
+            return pw<MATH>(S_r, (1.0 + om - alpha * quartz - gravel) / 2.0) *
+                   pw<MATH>(pw<MATH>(1.0 + ex<MATH>(-beta * S_r), -3.0) - pw<MATH>((1.0 - S_r) / 2.0, 3.0), 1.0 - om);
+        const double e1 = 1.0 + texp(-beta * S_r), h = (1.0 - S_r) / 2.0;
+        const double base = 1.0 / (e1 * e1 * e1) - h * h * h;
+        // S_r^a * base^b = exp(a log S_r + b log base)
+        if (!(base > 0.0)) return (base == 0.0) ? 0.0 : NAN;  // pow(0, b > 0) = 0; a negative base is a DomainError upstream
+        return texp(((1.0 + om - alpha * quartz - gravel) / 2.0) * tlog(S_r) + (1.0 - om) * tlog(base));
+    }
     return pw<MATH>(S_r, 1.0 + om);
 }
 
@@ -122,7 +160,7 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
     const HydroCell cell = load_cell(P, q);
     const double th = P.Y_theta_l[q], thi = P.Y_theta_i[q];
     const double rcds = __ldg(P.rho_c_ds + q);
-    double theta_l, kappa, T;
+    double theta_l, kappa, T, Tf_aux = 0.0, psi_w0_aux = 0.0;
     if (AUX) {
         // theta_l = volumetric_liquid_fraction(theta_l, nu - theta_i, theta_r)
         {
@@ -137,18 +175,24 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
         kappa = K_e * ks + (1.0 - K_e) * __ldg(X.kappa_dry + q);
         T = temperature_from_rho_e_int(P.Y_rho_e[q], thi, volumetric_heat_capacity(theta_l, thi, rcds, E), E);
         // K = impedance * viscosity * hydraulic_conductivity(effective_saturation(nu, theta_l(Y), theta_r))
-        double Kh, psi, d;
-        CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, false, false>(th, Kh, psi, d);
-        const double imp = pw<MATH>(10.0, -X.k.Omega * (thi / (theta_l + thi - cell.theta_r)));
+        double Kh, psi, d0, d1;
+        if (MATH == kMathFast && thi == 0.0) {  // nu - theta_i == nu: one closure evaluation gives K and psi
+            CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, true, false>(th, Kh, psi, d0);
+        } else {
+            CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, false, false>(th, Kh, d0, d1);
+            CellEval<CLOSURE, MATH>(cell, cell.nu - thi).template eval<false, true, false>(th, d0, psi, d1);
+        }
+        const double f_i = thi / (theta_l + thi - cell.theta_r);
+        const double imp = (MATH == kMathLibm) ? pow(10.0, -X.k.Omega * f_i)
+                                               : ((thi == 0.0) ? 1.0 : texp((-X.k.Omega * f_i) * 2.302585092994045684));
         const double visc = ex<MATH>(X.k.gamma * (T - X.k.gammaT_ref));
-        CellEval<CLOSURE, MATH>(cell, cell.nu - thi).template eval<false, true, false>(th, d, psi, d);
-        double psi_w0;
         X.p_theta_l[q] = theta_l;
         X.p_kappa[q] = kappa;
         X.p_T[q] = T;
         X.p_K[q] = imp * visc * Kh;
         X.p_psi[q] = psi;
-        X.p_Tf[q] = soil_Tf_depressed<CLOSURE, MATH>(cell, theta_l, thi, E.rho_l, E.rho_i, X.k, E.LH_f0, psi_w0);
+        Tf_aux = soil_Tf_depressed<CLOSURE, MATH>(cell, theta_l, thi, E.rho_l, E.rho_i, X.k, E.LH_f0, psi_w0_aux);
+        X.p_Tf[q] = Tf_aux;
     } else {
         theta_l = X.p_theta_l[q];
         kappa = X.p_kappa[q];
@@ -157,8 +201,13 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
     if (PHASE) {
         const double dz = P.dz_c[i];
         const double tau = 3.0 * volumetric_heat_capacity(theta_l, thi, rcds, E) * (dz * dz) / kappa;
-        double psi_w0;
-        const double Tf = soil_Tf_depressed<CLOSURE, MATH>(cell, theta_l, thi, E.rho_i, E.rho_l, X.k, E.LH_f0, psi_w0);
+        double psi_w0, Tf;
+        if (AUX && MATH == kMathFast && thi == 0.0) {  // without ice the density ratio does not enter theta_tot
+            Tf = Tf_aux;
+            psi_w0 = psi_w0_aux;
+        } else {
+            Tf = soil_Tf_depressed<CLOSURE, MATH>(cell, theta_l, thi, E.rho_i, E.rho_l, X.k, E.LH_f0, psi_w0);
+        }
         const double psi_T = E.LH_f0 / X.k.grav * lg<MATH>(T / Tf) * heaviside(Tf - T);
         const double theta_star =
             inverse_matric_potential<CLOSURE, MATH>(cell, psi_w0 + psi_T) * (cell.nu - cell.theta_r) + cell.theta_r;

@@ -15,6 +15,8 @@ minus the `!` -- so the parity tests read like the reference's own tests:
     make_update_implicit_cache / make_compute_imp_tendency / make_compute_jacobian
                                                      models.jl:238-306, implicit_timestepping.jl:25-28
     initialize_jacobian + ldiv                       implicit_timestepping.jl:63-172
+    make_update_aux (EnergyHydrology) / PhaseChange + source
+                                                     energy_hydrology.jl:722-814, 826-906
     IMEXAlgorithm(ARS111, NewtonsMethod) / LandSimulation / step / solve
                                                      simulations/Simulations.jl:115-332
 
@@ -57,10 +59,23 @@ class RichardsParameters:
 
 
 class EnergyHydrologyParameters(RichardsParameters):
-    def __init__(self, *, hydrology_cm, ν, K_sat, S_s, θ_r, ρc_ds, earth_param_set=None):
+    """energy_hydrology.jl:60-170.  The implicit path needs ρc_ds only; the explicit stage
+    (make_update_aux, PhaseChange) also reads the thermal-conductivity fields and the scalar
+    closures' constants, whose defaults are the reference's (test/standalone/Soil/
+    soil_parameterizations.jl:71-76); T_freeze / grav belong to earth_param_set in the reference."""
+    def __init__(self, *, hydrology_cm, ν, K_sat, S_s, θ_r, ρc_ds, earth_param_set=None, κ_dry=None,
+                 κ_sat_unfrozen=None, κ_sat_frozen=None, ν_ss_om=None, ν_ss_quartz=None, ν_ss_gravel=None,
+                 α=0.24, β=18.3, γ=2.64e-2, γT_ref=288.0, Ω=7.0, T_freeze=273.15, grav=9.81):
         super().__init__(hydrology_cm=hydrology_cm, ν=ν, K_sat=K_sat, S_s=S_s, θ_r=θ_r)
         self.ρc_ds = ρc_ds
         self.earth_param_set = dict(_s.EARTH if earth_param_set is None else earth_param_set)
+        self.κ_dry, self.κ_sat_unfrozen, self.κ_sat_frozen = κ_dry, κ_sat_unfrozen, κ_sat_frozen
+        self.ν_ss_om, self.ν_ss_quartz, self.ν_ss_gravel = ν_ss_om, ν_ss_quartz, ν_ss_gravel
+        self.α, self.β, self.γ, self.γT_ref, self.Ω, self.T_freeze, self.grav = α, β, γ, γT_ref, Ω, T_freeze, grav
+
+    def has_explicit_fields(self):
+        return all(v is not None for v in (self.κ_dry, self.κ_sat_unfrozen, self.κ_sat_frozen, self.ν_ss_om,
+                                           self.ν_ss_quartz, self.ν_ss_gravel))
 
 
 # ---- boundary conditions -------------------------------------------------------------------
@@ -92,6 +107,11 @@ class WaterHeatBC:
 class TOPMODELSubsurfaceRunoff:
     """Implicit source: the lagged p.soil.{R_ss, R_ess, h∇, is_saturated} are inputs."""
     explicit = False
+
+
+class PhaseChange:
+    """PhaseChange source (energy_hydrology.jl:826-829): explicit in every prognostic variable."""
+    explicit = True
 
 
 # ---- domain --------------------------------------------------------------------------------
@@ -138,6 +158,14 @@ class _SoilModel:
             self._set_param(name, v)
         if self.kind == _s.ENERGY_HYDROLOGY:
             self._set_param("rho_c_ds", parameters.ρc_ds)
+            if getattr(parameters, "has_explicit_fields", lambda: False)():
+                q = parameters
+                for name, v in (("kappa_dry", q.κ_dry), ("kappa_sat_unfrozen", q.κ_sat_unfrozen),
+                                ("kappa_sat_frozen", q.κ_sat_frozen), ("nu_ss_om", q.ν_ss_om),
+                                ("nu_ss_quartz", q.ν_ss_quartz), ("nu_ss_gravel", q.ν_ss_gravel)):
+                    self._set_param(name, v)
+                self.solver.set_explicit_params(Omega=q.Ω, gamma=q.γ, gammaT_ref=q.γT_ref, alpha=q.α, beta=q.β,
+                                                T_freeze=q.T_freeze, grav=q.grav)
 
     @staticmethod
     def _water(bc):
@@ -278,6 +306,43 @@ def make_update_implicit_cache(model):
         model.solver.update_implicit_cache()
         _pull_cache(model, p)
     return update_implicit_cache
+
+
+def make_update_aux(model):
+    """update_aux!(p, Y, t).  EnergyHydrology: energy_hydrology.jl:722-814 (θ_l, κ, T, K, ψ, Tf_depressed,
+    total_water, total_energy).  RichardsModel: rre.jl:368-380, which is also its implicit cache update
+    (models.jl:207-210)."""
+    if model.kind == _s.RICHARDS:
+        return make_update_implicit_cache(model)
+
+    def update_aux(p, Y, t):
+        _push_state(model, Y)
+        s = model.solver
+        s.update_aux()
+        for dev, name in (("theta_l_lag", "θ_l"), ("kappa_lag", "κ"), ("k_lag", "K"), ("p_t", "T"), ("p_psi", "ψ"),
+                          ("p_tf_depressed", "Tf_depressed"), ("total_water", "total_water"),
+                          ("total_energy", "total_energy")):
+            if not hasattr(p.soil, name):
+                setattr(p.soil, name, model._col() if name.startswith("total") else model._cell())
+            s.get(dev, getattr(p.soil, name))
+    return update_aux
+
+
+def make_phase_change_source(model):
+    """source!(dY, src::PhaseChange, Y, p, model): energy_hydrology.jl:846-906; adds to dY.soil.ϑ_l, θ_i."""
+    def source(dY, src, Y, p, model_=None):
+        assert isinstance(src, PhaseChange)
+        s = model.solver
+        _push_state(model, Y)
+        s.set("theta_l_lag", p.soil.θ_l)
+        s.set("kappa_lag", p.soil.κ)
+        s.set("p_t", p.soil.T)
+        s.set("dye_theta_l", dY.soil.ϑ_l)
+        s.set("dye_theta_i", dY.soil.θ_i)
+        s.phase_change_source()
+        s.get("dye_theta_l", dY.soil.ϑ_l)
+        s.get("dye_theta_i", dY.soil.θ_i)
+    return source
 
 
 def make_update_boundary_fluxes(model):

@@ -24,6 +24,7 @@ module ClimaLandB200
 using LinearAlgebra
 import ClimaLand
 import ClimaLand: Soil
+import ClimaLand.Parameters as LP
 import ClimaCore: Fields, Spaces
 import ClimaTimeSteppers
 import CUDA
@@ -31,7 +32,7 @@ import CUDA
 const libclb = get(ENV, "CLIMALAND_B200_LIB", "libclimaland_b200.so")
 
 # ---- enums of include/climaland_b200.h ------------------------------------------------------
-const CLB_ABI_VERSION = Int32(1)
+const CLB_ABI_VERSION = Int32(2)
 const CLB_RICHARDS, CLB_ENERGY_HYDROLOGY = Int32(0), Int32(1)
 const CLB_VAN_GENUCHTEN, CLB_BROOKS_COREY = Int32(0), Int32(1)
 const CLB_TOP_FLUX, CLB_TOP_MOISTURE_STATE = Int32(0), Int32(1)
@@ -48,10 +49,12 @@ const CLB_HOST, CLB_DEVICE = Int32(0), Int32(1)
     F_W11_LO; F_W11_DI; F_W11_UP; F_W21_LO; F_W21_DI; F_W21_UP; F_W22_LO; F_W22_DI; F_W22_UP
     F_B_THETA_L; F_B_RHO_E_INT; F_B_THETA_I; F_X_THETA_L; F_X_RHO_E_INT; F_X_THETA_I
     F_U_THETA_L; F_U_RHO_E_INT
+    F_KAPPA_DRY; F_KAPPA_SAT_UNFROZEN; F_KAPPA_SAT_FROZEN; F_NU_SS_OM; F_NU_SS_QUARTZ; F_NU_SS_GRAVEL
+    F_P_TF_DEPRESSED; F_DYE_THETA_L; F_DYE_THETA_I
     F_R_SS; F_R_ESS; F_H_GRAD; F_THETA_BC_TOP; F_THETA_BC_BOT
     F_TOP_BC_W; F_BOT_BC_W; F_TOP_BC_H; F_BOT_BC_H; F_DFLUXBCDY; F_TOTAL_WATER
     F_Y_INTF_W; F_Y_INTF_E; F_DY_INTF_W; F_DY_INTF_E; F_B_INTF_W; F_B_INTF_E; F_X_INTF_W; F_X_INTF_E
-    F_AREA_WEIGHT; F_U_INTF_W; F_U_INTF_E
+    F_AREA_WEIGHT; F_U_INTF_W; F_U_INTF_E; F_TOTAL_ENERGY
 end
 
 # struct clb_config (same field order and widths as the header)
@@ -76,6 +79,17 @@ struct ClbConfig
     LH_f0::Float64
     layout::Int32
     reserved::Int32
+end
+
+# struct clb_explicit_params
+struct ClbExplicitParams
+    Omega::Float64
+    gamma::Float64
+    gammaT_ref::Float64
+    alpha::Float64
+    beta::Float64
+    T_freeze::Float64
+    grav::Float64
 end
 
 struct ClbStats
@@ -253,6 +267,50 @@ function make_update_implicit_cache(b::B200Soil)
         end
         return nothing
     end
+end
+
+# ---- the explicit stage of EnergyHydrology (SURVEY 8f rank 1) ------------------------------------
+"""
+    set_explicit_params!(b, model)
+
+Uploads what only `update_aux!` reads: the six thermal-conductivity / composition fields of
+`EnergyHydrologyParameters` (energy_hydrology.jl:60-170) and its scalar closure constants.
+Called once (the parameters are time-invariant).
+"""
+function set_explicit_params!(b::B200Soil, model::Soil.EnergyHydrology)
+    q = model.parameters
+    eps_ = q.earth_param_set
+    for (id, f) in ((F_KAPPA_DRY, q.κ_dry), (F_KAPPA_SAT_UNFROZEN, q.κ_sat_unfrozen),
+                    (F_KAPPA_SAT_FROZEN, q.κ_sat_frozen), (F_NU_SS_OM, q.ν_ss_om),
+                    (F_NU_SS_QUARTZ, q.ν_ss_quartz), (F_NU_SS_GRAVEL, q.ν_ss_gravel))
+        set_field!(b.h, id, f)
+    end
+    x = Ref(ClbExplicitParams(q.Ω, q.γ, q.γT_ref, q.α, q.β, LP.T_freeze(eps_), LP.grav(eps_)))
+    check(ccall((:clb_set_explicit_params, libclb), Cint, (Ptr{Cvoid}, Ref{ClbExplicitParams}), b.h.ptr, x))
+end
+
+"update_aux!(p, Y, t) of EnergyHydrology: src/standalone/Soil/energy_hydrology.jl:722-814"
+function make_update_aux(b::B200Soil)
+    function update_aux!(p, Y, t)
+        push_state!(b, Y)
+        check(ccall((:clb_update_aux, libclb), Cint, (Ptr{Cvoid},), b.h.ptr))
+        # the lagged inputs of the implicit stage now sit in the library's mirrors; Julia's copies of the
+        # cache are refreshed for the other explicit tendencies (boundary fluxes, runoff, canopy coupling)
+        get_field!(p.soil.θ_l, b.h, F_THETA_L_LAG); get_field!(p.soil.κ, b.h, F_KAPPA_LAG)
+        get_field!(p.soil.K, b.h, F_K_LAG); get_field!(p.soil.T, b.h, F_P_T); get_field!(p.soil.ψ, b.h, F_P_PSI)
+        get_field!(p.soil.Tf_depressed, b.h, F_P_TF_DEPRESSED)
+        get_field!(p.soil.total_water, b.h, F_TOTAL_WATER); get_field!(p.soil.total_energy, b.h, F_TOTAL_ENERGY)
+        return nothing
+    end
+end
+
+"source!(dY, src::PhaseChange, Y, p, model): energy_hydrology.jl:846-906 (adds into dY.soil.ϑ_l, dY.soil.θ_i)"
+function ClimaLand.source!(dY::Fields.FieldVector, src::Soil.PhaseChange, Y::Fields.FieldVector, p::NamedTuple,
+                           b::B200Soil)
+    set_field!(b.h, F_DYE_THETA_L, dY.soil.ϑ_l); set_field!(b.h, F_DYE_THETA_I, dY.soil.θ_i)
+    check(ccall((:clb_phase_change_source, libclb), Cint, (Ptr{Cvoid},), b.h.ptr))
+    get_field!(dY.soil.ϑ_l, b.h, F_DYE_THETA_L); get_field!(dY.soil.θ_i, b.h, F_DYE_THETA_I)
+    return nothing
 end
 
 "compute_imp_tendency!(dY, Y, p, t): rre.jl:161-203, energy_hydrology.jl:363-425"

@@ -100,3 +100,19 @@ def test_shard_ranges_partition_the_columns():
 
 if __name__ == "__main__":
     sys.exit(pytest.main([__file__, "-q"]))
+
+
+def test_julia_binding_matches_header():
+    """julia/ClimaLandB200.jl (the reference-side ccall binding) cannot run here (no Julia): keep its
+    field enum, ABI version and every ccall'ed symbol in step with include/climaland_b200.h."""
+    import re
+    import climaland_b200 as cl
+    src = open(os.path.join(ROOT, "julia", "ClimaLandB200.jl")).read()
+    K = cl._lib.K
+    assert int(re.search(r"const CLB_ABI_VERSION = Int32\((\d+)\)", src).group(1)) == K["CLB_ABI_VERSION"]
+    body = re.search(r"@enum ClbField::Int32 begin(.*?)\nend", src, flags=re.S).group(1)
+    names = [t.split("=")[0].strip() for t in re.split(r"[;\n]", body) if t.strip()]
+    header = sorted((v, k) for k, v in K.items() if k.startswith("CLB_F_") and k not in ("CLB_F_NUM", "CLB_F_NUM_CELL"))
+    assert ["CLB_" + n for n in names] == [k for _, k in header]
+    for sym in set(re.findall(r"ccall\(\(:(clb_\w+)", src)):
+        assert sym in cl._lib.EXPORTS, sym

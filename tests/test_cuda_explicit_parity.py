@@ -113,3 +113,44 @@ def test_errors():
     with pytest.raises(cl.ClbError, match="EnergyHydrology only"):
         r.update_aux()
     r.close()
+
+
+def test_mirror_update_aux_and_phase_change_read_like_the_reference():
+    """test/standalone/Soil/soil_parameterizations.jl:283-430 ("Freezing and Thawing") through the
+    host-side mirror of the reference interface: make_update_aux(model)(p, Y, t), then
+    source!(dY, PhaseChange(), Y, p, model).  Columns hold theta_l = (0.11, 0.15, nu); T = 270 K
+    freezes (source > 0, d theta_l < 0), T = 274 K without ice leaves the state alone."""
+    import oracle as orc
+    import climaland_b200 as C
+    L, E, X = orc.lib(), orc.EARTH, orc.EXPLICIT_SCALARS
+    nu, theta_r, a, n, S_s, K_sat = 0.2, 0.1, 2.0, 1.4, 1e-3, 1e-5
+    m = 1.0 - 1.0 / n
+    rho_c_ds, k_dry, k_u, k_f = 1.8e6, 1.1, 1.4, 2.3
+    params = C.EnergyHydrologyParameters(hydrology_cm=C.vanGenuchten(α=a, n=n), ν=nu, K_sat=K_sat, S_s=S_s, θ_r=theta_r,
+                                         ρc_ds=rho_c_ds, κ_dry=k_dry, κ_sat_unfrozen=k_u, κ_sat_frozen=k_f,
+                                         ν_ss_om=0.1, ν_ss_quartz=0.1, ν_ss_gravel=0.1)
+    zero = C.WaterHeatBC(water=C.WaterFluxBC(0.0), heat=C.HeatFluxBC(0.0))
+    soil = C.EnergyHydrology(parameters=params, domain=C.Column(zlim=(-3.0, 0.0), nelements=3, ncol=3),
+                             boundary_conditions=dict(top=zero, bottom=zero), sources=(C.PhaseChange(),))
+    for T, sign in ((270.0, 1), (274.0, 0)):
+        Y, p, _ = C.initialize(soil)
+        Y.soil.ϑ_l[...] = np.array([0.11, 0.15, nu])[:, None]
+        Y.soil.θ_i[...] = 0.0
+        rc = np.array([L.orc_volumetric_heat_capacity(t, 0.0, rho_c_ds, E["rho_l"], E["cp_l"], E["rho_i"], E["cp_i"])
+                       for t in (0.11, 0.15, nu)])[:, None]
+        Y.soil.ρe_int[...] = rc * (T - E["T_ref"])
+        C.make_update_aux(soil)(p, Y, 0.0)
+        assert np.allclose(p.soil.T, T, rtol=1e-14) and np.allclose(p.soil.θ_l, Y.soil.ϑ_l)
+        dY, _, _ = C.initialize(soil)
+        C.make_phase_change_source(soil)(dY, C.PhaseChange(), Y, p, soil)
+        for c, theta_l in enumerate((0.11, 0.15, nu)):
+            tau = L.orc_thermal_time(rc[c, 0], 1.0, p.soil.κ[c, 0])
+            want = L.orc_phase_change_source(0, a, n, m, theta_l, 0.0, p.soil.T[c, 0], tau, nu, theta_r, E["rho_i"], E["rho_l"],
+                                             E["LH_f0"], X["T_freeze"], X["grav"])
+            assert np.allclose(dY.soil.ϑ_l[c], -want, rtol=1e-12, atol=1e-12 * theta_l / tau)
+            assert np.allclose(dY.soil.θ_i[c], E["rho_l"] / E["rho_i"] * want, rtol=1e-12, atol=1e-12 * theta_l / tau)
+            if sign:
+                assert want > 0.0 and np.all(dY.soil.ϑ_l[c] < 0.0)
+            else:
+                assert abs(want) <= 1.5e-8 * theta_l / tau
+    soil.solver.close()
