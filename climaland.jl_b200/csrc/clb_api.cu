@@ -140,6 +140,11 @@ struct clb_handle_s {
     double *zeros_cell = nullptr, *zeros_col = nullptr;  // stand-ins for fields the configuration does not use
     double *d_stats = nullptr;  // [0] dx^2, [1] non-finite count, [2] norm of the tolerance path, [3..6] balance
     int32_t *d_flags = nullptr; // [0] converged, [1] iterations of the tolerance path
+    // pipelined host-buffer stage (clb_implicit_step_host): copy-in / copy-out streams, per-chunk events, staging
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_in[16] = {}, ev_out[16] = {};
+    double *d_stage_in = nullptr, *d_stage_out = nullptr;
+    size_t stage_in_bytes = 0, stage_out_bytes = 0;
     // explicit stage of EnergyHydrology (soil_explicit.cuh)
     clb::ExplicitConst explicit_k = {};
     bool explicit_set = false;
@@ -318,6 +323,7 @@ clb::PairGrid make_pair_grid(clb_handle h, double dtg)
 {
     const int N = h->cfg.n_levels;
     clb::PairGrid g;
+    g.col0 = 0;
     for (int half = 0; half < 2; ++half) {
         for (int q = 0; q < clb::kPairQ; ++q) {
             const int level = half ? 15 - q : q;
@@ -433,7 +439,7 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::Pa
 //              of shared memory per warp (4 of EnergyHydrology's 18 stage constants stay in registers);
 //   plain      one tile per warp, all constants in shared memory (18 KB per warp), 3 blocks per SM.
 template <int CLOSURE, int MODEL, int N, bool PIPELINED>
-int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0)
 {
     // the pipelined shape is one 8-warp block per SM: 8 x 28 KB of tiles + the 2.5 KB of tables fill the 227 KB
     constexpr int PARTS = 2, BLOCK = PIPELINED ? 256 : 128;
@@ -463,9 +469,12 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
         blocks = std::min<int64_t>(blocks, (int64_t)sms * MINB);
     }
-    const clb::PairGrid g = make_pair_grid(h, dtg);
+    clb::PairGrid g = make_pair_grid(h, dtg);
+    g.col0 = (int)col0;
     clb::PairMaps maps;
-    TRY(make_pair_maps(h, P, CPW, &maps));
+    // the descriptors always describe the whole mirrors (P may be a column sub-range with shifted pointers;
+    // its offset travels as g.col0)
+    TRY(make_pair_maps(h, col0 ? make_view(h) : P, CPW, &maps));
     // programmatic dependent launch: the kernel's prologue (tables, barriers, the first tile's parameter
     // fields) may overlap the tail of the stream's previous kernel unless that kernel may be writing this
     // handle's parameter mirrors
@@ -485,14 +494,15 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 }
 
 template <int N, bool PIPELINED>
-int launch_quad_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+int launch_quad_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0 = 0)
 {
     const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
     const bool vg = h->cfg.closure == CLB_VAN_GENUCHTEN;
     if (eh)
-        return vg ? launch_quad<0, 1, N, PIPELINED>(h, P, dtg, max_iters)
-                  : launch_quad<1, 1, N, PIPELINED>(h, P, dtg, max_iters);
-    return vg ? launch_quad<0, 0, N, PIPELINED>(h, P, dtg, max_iters) : launch_quad<1, 0, N, PIPELINED>(h, P, dtg, max_iters);
+        return vg ? launch_quad<0, 1, N, PIPELINED>(h, P, dtg, max_iters, col0)
+                  : launch_quad<1, 1, N, PIPELINED>(h, P, dtg, max_iters, col0);
+    return vg ? launch_quad<0, 0, N, PIPELINED>(h, P, dtg, max_iters, col0)
+              : launch_quad<1, 0, N, PIPELINED>(h, P, dtg, max_iters, col0);
 }
 
 bool pair_variant_applies(clb_handle h)
@@ -664,6 +674,191 @@ int launch_explicit(clb_handle h, const char *who)
 
 }  // namespace
 
+namespace {
+
+// ---- pipelined host-buffer stage ------------------------------------------------------------------
+// clb_implicit_step_host moves ~70 MB per ~1 degree stage over PCIe while the fused kernel needs ~55 us, so
+// the end-to-end time is the transfers'.  The columns are cut into chunks: the H2D copy of chunk k+1 (copy-in
+// stream) overlaps the relayout + fused kernel of chunk k (the handle's stream) and the D2H copy of chunk k-1
+// (copy-out stream); columns are independent, so a chunk is a complete problem.  Applies to the lane-quad
+// kernels without a land-sea mask; every other configuration takes the field-by-field path.
+
+// every data pointer of a view moved to column c0 of column-fastest mirrors (cell arrays: (i, c) at i*ld + c;
+// column arrays: c); the per-level grid vectors and the statistics do not move
+clb::DevView shift_view(const clb::DevView &V, int64_t c0, int64_t n)
+{
+    clb::DevView P = V;
+    P.ncol = n;
+#define CLB_SHIFT(m) if (P.m) P.m += c0
+    CLB_SHIFT(nu); CLB_SHIFT(theta_r); CLB_SHIFT(K_sat); CLB_SHIFT(S_s); CLB_SHIFT(hcm_a); CLB_SHIFT(hcm_b);
+    CLB_SHIFT(hcm_m); CLB_SHIFT(rho_c_ds); CLB_SHIFT(K_lag); CLB_SHIFT(kappa_lag); CLB_SHIFT(theta_l_lag);
+    CLB_SHIFT(is_sat); CLB_SHIFT(R_ss); CLB_SHIFT(R_ess); CLB_SHIFT(h_grad); CLB_SHIFT(theta_bc_top);
+    CLB_SHIFT(theta_bc_bot); CLB_SHIFT(Y_theta_l); CLB_SHIFT(Y_rho_e); CLB_SHIFT(Y_theta_i); CLB_SHIFT(Y_intF_w);
+    CLB_SHIFT(Y_intF_e); CLB_SHIFT(out_theta_l); CLB_SHIFT(out_rho_e); CLB_SHIFT(out_intF_w); CLB_SHIFT(out_intF_e);
+    CLB_SHIFT(p_K); CLB_SHIFT(p_psi); CLB_SHIFT(p_T); CLB_SHIFT(top_bc_w); CLB_SHIFT(bot_bc_w); CLB_SHIFT(top_bc_h);
+    CLB_SHIFT(bot_bc_h); CLB_SHIFT(dfluxBCdY); CLB_SHIFT(total_water);
+#undef CLB_SHIFT
+    return P;
+}
+
+bool is_step_input(int f)
+{
+    switch (f) {
+    case CLB_F_Y_THETA_L: case CLB_F_Y_RHO_E_INT: case CLB_F_Y_THETA_I: case CLB_F_K_LAG: case CLB_F_KAPPA_LAG:
+    case CLB_F_THETA_L_LAG: case CLB_F_IS_SATURATED: case CLB_F_TOP_BC_W: case CLB_F_BOT_BC_W: case CLB_F_TOP_BC_H:
+    case CLB_F_BOT_BC_H: case CLB_F_R_SS: case CLB_F_R_ESS: case CLB_F_H_GRAD: case CLB_F_Y_INTF_W: case CLB_F_Y_INTF_E:
+        return true;
+    default: return false;
+    }
+}
+
+constexpr int64_t kHostChunkMin = 4096;  // columns; below 2 chunks of this the plain path is as good
+
+// returns 1 when the pipelined path ran, 0 when it does not apply (the caller falls back), < 0 on error
+int step_host_pipelined(clb_handle h, double dtgamma, int32_t max_iters, const int32_t *in_fields,
+                        const double *const *in_ptrs, int32_t n_in, const int32_t *out_fields, double *const *out_ptrs,
+                        int32_t n_out)
+{
+    const int N = h->cfg.n_levels;
+    const int64_t ncol = h->cfg.n_columns;
+    const int kv = h->cfg.kernel_variant;
+    if (h->d_idx || !pair_variant_applies(h) || h->sc != 1 || ncol < 2 * kHostChunkMin) return 0;
+    if (kv != CLB_VARIANT_AUTO && kv != CLB_VARIANT_LANE_QUAD_PIPELINED) return 0;
+    if (n_in > clb::kManyFields + clb::kManyFields || n_out > clb::kManyFields) return 0;
+    int cell_in[clb::kManyFields], col_in[clb::kManyFields], cell_out[clb::kManyFields], col_out[clb::kManyFields];
+    int n_cell_in = 0, n_col_in = 0, n_cell_out = 0, n_col_out = 0;
+    for (int j = 0; j < n_in; ++j) {
+        if (!is_step_input(in_fields[j]) || !in_ptrs[j]) return 0;
+        if (is_cell_field(in_fields[j])) { if (n_cell_in == clb::kManyFields) return 0; cell_in[n_cell_in++] = j; }
+        else { if (n_col_in == clb::kManyFields) return 0; col_in[n_col_in++] = j; }
+    }
+    for (int j = 0; j < n_out; ++j) {
+        if (!(is_cell_field(out_fields[j]) || is_col_field(out_fields[j])) || !out_ptrs[j]) return 0;
+        if (is_cell_field(out_fields[j])) cell_out[n_cell_out++] = j;
+        else col_out[n_col_out++] = j;
+    }
+    for (int j = 0; j < n_in; ++j) {
+        TRY(ensure_field(h, in_fields[j]));
+        h->field_set[in_fields[j]] = true;
+    }
+    TRY(step_inputs_ready(h));
+    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    if (h->out_of_place) {
+        TRY(alloc_fields(h, {CLB_F_U_THETA_L, CLB_F_U_INTF_W}));
+        if (eh) TRY(alloc_fields(h, {CLB_F_U_RHO_E_INT, CLB_F_U_INTF_E}));
+    }
+    for (int j = 0; j < n_out; ++j)
+        if (!h->field[out_fields[j]]) return fail(CLB_ERR_UNSET, "clb_implicit_step_host: output field %d does not exist", out_fields[j]);
+    if (!h->s_in) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+        for (auto &e : h->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : h->ev_out) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // staging in the caller's layout: cell fields (ncol, N) level fastest, column fields (ncol)
+    const size_t cell_b = (size_t)ncol * N * sizeof(double), col_b = (size_t)ncol * sizeof(double);
+    const size_t need_in = n_cell_in * cell_b + n_col_in * col_b, need_out = n_cell_out * cell_b + n_col_out * col_b;
+    if (h->stage_in_bytes < need_in) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaFree(h->d_stage_in));
+        CUDA_TRY(cudaMalloc(&h->d_stage_in, need_in));
+        h->stage_in_bytes = need_in;
+    }
+    if (h->stage_out_bytes < need_out) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaFree(h->d_stage_out));
+        CUDA_TRY(cudaMalloc(&h->d_stage_out, need_out));
+        h->stage_out_bytes = need_out;
+    }
+    double *const st_cell_in = h->d_stage_in, *const st_col_in = h->d_stage_in + (size_t)n_cell_in * ncol * N;
+    double *const st_cell_out = h->d_stage_out, *const st_col_out = h->d_stage_out + (size_t)n_cell_out * ncol * N;
+
+    // chunks of whole 32-column tiles, at most 16 and at least kHostChunkMin columns each
+    static const int want_chunks = getenv("CLB_HOST_CHUNKS") ? atoi(getenv("CLB_HOST_CHUNKS")) : 3;
+    int n_chunks = (int)std::min<int64_t>(std::max(want_chunks, 1), std::min<int64_t>(16, ncol / kHostChunkMin));
+    const int64_t per = (((ncol + n_chunks - 1) / n_chunks) + 31) / 32 * 32;
+    n_chunks = (int)((ncol + per - 1) / per);
+
+    h->last_variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
+    clb::DevView V = make_view(h);
+    V.stats = nullptr;
+    TRY(ensure_prepared(h, V));  // the prepared parameter mirrors cover all columns: once, before the chunks
+    nvtxRangePushA("implicit_step_host (pipelined)");
+    // nothing of this call may overtake what the caller enqueued before it
+    CUDA_TRY(cudaEventRecord(h->ev_start, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_start, 0));
+    // copy-in stream: the small column fields whole, then the cell fields chunk by chunk
+    for (int a = 0; a < n_col_in; ++a)
+        CUDA_TRY(cudaMemcpyAsync(st_col_in + (size_t)a * ncol, in_ptrs[col_in[a]], col_b, cudaMemcpyHostToDevice, h->s_in));
+    for (int k = 0; k < n_chunks; ++k) {
+        const int64_t c0 = k * per, n = std::min(per, ncol - c0);
+        for (int a = 0; a < n_cell_in; ++a)
+            CUDA_TRY(cudaMemcpyAsync(st_cell_in + ((size_t)a * ncol + c0) * N, in_ptrs[cell_in[a]] + (size_t)c0 * N,
+                                     (size_t)n * N * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[k], h->s_in));
+    }
+    const size_t tile_smem = (size_t)N * (clb::kTileCols + 1) * sizeof(double);
+    for (int k = 0; k < n_chunks; ++k) {
+        const int64_t c0 = k * per, n = std::min(per, ncol - c0);
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[k], 0));
+        if (k == 0 && n_col_in) {
+            clb::ManyFields f = {};
+            for (int a = 0; a < n_col_in; ++a) {
+                f.dst[a] = h->field[in_fields[col_in[a]]];
+                f.src[a] = st_col_in + (size_t)a * ncol;
+            }
+            clb::k_copy_many<<<dim3((unsigned)((ncol + 255) / 256), n_col_in), 256, 0, h->stream>>>(f, ncol);
+        }
+        const dim3 tiles((unsigned)((n + clb::kTileCols - 1) / clb::kTileCols), 1);
+        if (n_cell_in) {
+            clb::ManyFields f = {};
+            for (int a = 0; a < n_cell_in; ++a) {
+                f.dst[a] = h->field[in_fields[cell_in[a]]] + c0;
+                f.src[a] = st_cell_in + ((size_t)a * ncol + c0) * N;
+            }
+            clb::k_relayout_many<<<dim3(tiles.x, n_cell_in), 256, tile_smem, h->stream>>>(f, h->sl, h->sc, 1, N, N, n);
+        }
+        const clb::DevView P = shift_view(V, c0, n);
+        if (N == 15) TRY((launch_quad_n<15, true>(h, P, dtgamma, max_iters, c0)));
+        else TRY((launch_quad_n<16, true>(h, P, dtgamma, max_iters, c0)));
+        if (n_cell_out) {
+            clb::ManyFields f = {};
+            for (int a = 0; a < n_cell_out; ++a) {
+                f.dst[a] = st_cell_out + ((size_t)a * ncol + c0) * N;
+                f.src[a] = h->field[out_fields[cell_out[a]]] + c0;
+            }
+            clb::k_relayout_many<<<dim3(tiles.x, n_cell_out), 256, tile_smem, h->stream>>>(f, 1, N, h->sl, h->sc, N, n);
+        }
+        if (k == n_chunks - 1 && n_col_out) {
+            clb::ManyFields f = {};
+            for (int a = 0; a < n_col_out; ++a) {
+                f.dst[a] = st_col_out + (size_t)a * ncol;
+                f.src[a] = h->field[out_fields[col_out[a]]];
+            }
+            clb::k_copy_many<<<dim3((unsigned)((ncol + 255) / 256), n_col_out), 256, 0, h->stream>>>(f, ncol);
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(h->ev_out[k], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_out[k], 0));
+        for (int a = 0; a < n_cell_out; ++a)
+            CUDA_TRY(cudaMemcpyAsync(out_ptrs[cell_out[a]] + (size_t)c0 * N, st_cell_out + ((size_t)a * ncol + c0) * N,
+                                     (size_t)n * N * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+    }
+    for (int a = 0; a < n_col_out; ++a)
+        CUDA_TRY(cudaMemcpyAsync(out_ptrs[col_out[a]], st_col_out + (size_t)a * ncol, col_b, cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaEventRecord(h->ev_done, h->s_out));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_done, 0));  // later work on the handle's stream is ordered after the read-back
+    nvtxRangePop();
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 1;
+}
+
+}  // namespace
+
 extern "C" {
 
 int clb_test_math(int32_t kind, const double *x, const double *y, double *out, int64_t n)
@@ -778,6 +973,14 @@ int clb_destroy(clb_handle h)
     cudaFree(h->d_grid);
     cudaFree(h->d_idx);
     cudaFree(h->d_stage);
+    cudaFree(h->d_stage_in);
+    cudaFree(h->d_stage_out);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (auto &e : h->ev_in) if (e) cudaEventDestroy(e);
+    for (auto &e : h->ev_out) if (e) cudaEventDestroy(e);
     cudaFree(h->d_stats);
     cudaFree(h->d_flags);
     delete h;
@@ -1219,6 +1422,16 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters, cons
                            double *const *out_ptrs, int32_t n_out)
 {
     TRY(check_handle(h));
+    if (max_iters < 1) return fail(CLB_ERR_INVALID, "clb_implicit_step_host: max_iters must be >= 1");
+    if ((n_in > 0 && (!in_fields || !in_ptrs)) || (n_out > 0 && (!out_fields || !out_ptrs)))
+        return fail(CLB_ERR_INVALID, "clb_implicit_step_host: null field list");
+    {
+        DeviceGuard guard(h->cfg.device);
+        static const bool no_pipeline = getenv("CLB_HOST_NO_PIPELINE") != nullptr;
+        const int rc = no_pipeline ? 0 : step_host_pipelined(h, dtgamma, max_iters, in_fields, in_ptrs, n_in, out_fields,
+                                                             out_ptrs, n_out);
+        if (rc != 0) return rc < 0 ? rc : CLB_OK;
+    }
     const int N = h->cfg.n_levels;
     for (int j = 0; j < n_in; ++j) {
         const bool cell = is_cell_field(in_fields[j]);

@@ -41,6 +41,40 @@ __global__ void __launch_bounds__(256) k_relayout(double *__restrict__ dst, int6
     }
 }
 
+// The same for up to kManyFields fields in one launch (blockIdx.y = field): the pipelined host-buffer stage
+// moves a column chunk of every per-step field with one kernel.
+constexpr int kManyFields = 10;
+struct ManyFields {
+    double *dst[kManyFields];
+    const double *src[kManyFields];
+};
+__global__ void __launch_bounds__(256) k_relayout_many(ManyFields f, int64_t dsl, int64_t dsc, int64_t ssl, int64_t ssc,
+                                                       int N, int64_t ncol)
+{
+    extern __shared__ double tile[];  // [N][kTileCols + 1]
+    double *__restrict__ dst = f.dst[blockIdx.y];
+    const double *__restrict__ src = f.src[blockIdx.y];
+    const int64_t c0 = (int64_t)blockIdx.x * kTileCols;
+    const int ncl = (int)min((int64_t)kTileCols, ncol - c0);
+    const bool s_level_fast = ssl <= ssc, d_level_fast = dsl <= dsc;
+    for (int e = threadIdx.x; e < kTileCols * N; e += blockDim.x) {
+        int cl, i;
+        if (s_level_fast) { cl = e / N; i = e - cl * N; } else { i = e / kTileCols; cl = e - i * kTileCols; }
+        if (cl < ncl) tile[i * (kTileCols + 1) + cl] = src[(int64_t)i * ssl + (c0 + cl) * ssc];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTileCols * N; e += blockDim.x) {
+        int cl, i;
+        if (d_level_fast) { cl = e / N; i = e - cl * N; } else { i = e / kTileCols; cl = e - i * kTileCols; }
+        if (cl < ncl) dst[(int64_t)i * dsl + (c0 + cl) * dsc] = tile[i * (kTileCols + 1) + cl];
+    }
+}
+__global__ void __launch_bounds__(256) k_copy_many(ManyFields f, int64_t n)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) f.dst[blockIdx.y][c] = f.src[blockIdx.y][c];
+}
+
 __global__ void __launch_bounds__(256) k_gather_cols(double *__restrict__ mirror, const double *__restrict__ src,
                                                      int64_t sc, const int64_t *__restrict__ idx, int64_t ncol)
 {

@@ -57,6 +57,9 @@ struct PairGrid {
     double z[2][kPairQ];          // z_c of the cell
     double dti[2][kPairQ];        // dtgamma / dz_c of the cell; 0 for pad slots
     double hidzf[2][kPairQ + 1];  // 1/(2 dz_f) of face f (f = q: outer face of slot q, 8: seam); 0 for boundary / pad faces
+    int col0;                     // first column of this launch within the mirrors the TMA descriptors describe
+                                  // (a launch over a column sub-range: the pointers of DevView are shifted, the
+                                  // descriptors are not)
 };
 
 // Stage constants per cell: slots [0, NS) in shared memory, the rest in registers.
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         const bool skip = (CLOSURE != kVanGenuchten) && lane == ((MODEL == 1) ? 5 : 6);  // no m field for Brooks-Corey
         const bool mine = is_param(lane) ? (which & 1) : (which & 2);
         if (lane < NRAW && !skip && mine)
-            tma_load_2d(smem_u32(tiles + buf * kTileBytes) + lane * Gm::kSlotBytes, &M.m[lane], (int)(t * CPW), 0, bar);
+            tma_load_2d(smem_u32(tiles + buf * kTileBytes) + lane * Gm::kSlotBytes, &M.m[lane], G.col0 + (int)(t * CPW), 0, bar);
     };
 
     if (lane == 0) {
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         const int64_t tn = tile_id + nwarps;
         if (tn < ntiles) {
             const bool skip = (CLOSURE != kVanGenuchten) && lane == ((MODEL == 1) ? 5 : 6);
-            if (lane < NRAW && !skip) tma_prefetch_l2_2d(&M.m[lane], (int)(tn * CPW), 0);
+            if (lane < NRAW && !skip) tma_prefetch_l2_2d(&M.m[lane], G.col0 + (int)(tn * CPW), 0);
             if (lane >= 16 && lane < 16 + ((MODEL == 1) ? 9 : 5)) {  // the CPW per-column scalars of an array share a line
                 const int j_ = lane - 16;
                 const double *a_ = P.R_ss;

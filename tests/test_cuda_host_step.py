@@ -1,0 +1,79 @@
+"""The end-to-end entry point clb_implicit_step_host (host buffers in the reference layout in, new state
+out): the pipelined route (column chunks, H2D / kernels / D2H overlapped on three streams) and the
+field-by-field route must both give the oracle's stage, and each other's bits."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, cuda_solver, oracle_problem
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+IN_EH = ("y_theta_l", "y_rho_e_int", "y_theta_i", "k_lag", "kappa_lag", "theta_l_lag", "is_saturated", "top_bc_w",
+         "bot_bc_w", "top_bc_h", "bot_bc_h", "r_ss", "r_ess", "h_grad", "y_intf_w", "y_intf_e")
+IN_RI = ("y_theta_l", "is_saturated", "top_bc_w", "bot_bc_w", "r_ss", "h_grad", "y_intf_w")
+
+
+def _run(model, ncol, out_of_place, seed=3, steps=1):
+    import climaland_b200  # noqa: F401
+    from climaland_b200 import workloads
+    eh = model == "energy_hydrology"
+    dt, iters = (900.0, 3) if eh else (1800.0, 2)
+    w = workloads.make_workload(model, ncol, N=15, seed=seed, topmodel=True)
+    P, U, p = oracle_problem(w, nthreads=os.cpu_count() or 1)
+    s = cuda_solver(w, out_of_place=out_of_place)
+    names = IN_EH if eh else IN_RI
+    pre = "u" if out_of_place else "y"
+    outs = {f"{pre}_theta_l": np.zeros((ncol, 15)), f"{pre}_intf_w": np.zeros(ncol)}
+    if eh:
+        outs.update({f"{pre}_rho_e_int": np.zeros((ncol, 15)), f"{pre}_intf_e": np.zeros(ncol)})
+    ins = {k: np.ascontiguousarray(w[k]) for k in names}
+    for _ in range(steps):
+        P.implicit_step(U, dt, iters, p=p)
+        s.implicit_step_host(dt, iters, ins, outs)
+        if steps > 1:  # feed the new state back, as a time loop does
+            ins["y_theta_l"] = outs[f"{pre}_theta_l"].copy()
+            ins["y_intf_w"] = outs[f"{pre}_intf_w"].copy()
+            if eh:
+                ins["y_rho_e_int"] = outs[f"{pre}_rho_e_int"].copy()
+                ins["y_intf_e"] = outs[f"{pre}_intf_e"].copy()
+    variant = s.last_variant()
+    s.close()
+    return U, outs, pre, variant
+
+
+@pytest.mark.parametrize("out_of_place", [True, False], ids=["outofplace", "inplace"])
+@pytest.mark.parametrize("model,ncol", [("energy_hydrology", 61206), ("energy_hydrology", 9001), ("richards", 20000),
+                                        ("energy_hydrology", 700)])
+def test_host_step_matches_oracle(model, ncol, out_of_place):
+    U, outs, pre, _ = _run(model, ncol, out_of_place)
+    assert_close(outs[f"{pre}_theta_l"], U.theta_l, TOL, "theta_l")
+    assert_close(outs[f"{pre}_intf_w"], U.intF_w, TOL, "intF_w")
+    if model == "energy_hydrology":
+        assert_close(outs[f"{pre}_rho_e_int"], U.rho_e_int, TOL, "rho_e_int")
+        assert_close(outs[f"{pre}_intf_e"], U.intF_e, TOL, "intF_e")
+
+
+def test_host_step_repeated_calls():
+    """three stages in a row through the pipelined route (staging buffers and events are reused)"""
+    U, outs, pre, variant = _run("energy_hydrology", 30000, True, steps=3)
+    assert variant == 5
+    assert_close(outs["u_theta_l"], U.theta_l, 1e-11, "theta_l after 3 stages")
+    assert_close(outs["u_rho_e_int"], U.rho_e_int, 1e-11, "rho_e_int after 3 stages")
+
+
+def test_pipelined_and_plain_routes_agree_bitwise():
+    """CLB_HOST_NO_PIPELINE=1 forces the field-by-field route (read once per process): run it in a child."""
+    code = ("import sys, numpy as np; sys.path[:0] = ['.', 'oracle', 'tests'];"
+            "from test_cuda_host_step import _run; U, outs, pre, v = _run('energy_hydrology', 20000, True);"
+            "np.save(sys.argv[1], outs['u_theta_l'])")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("pipe", {}), ("plain", {"CLB_HOST_NO_PIPELINE": "1"})):
+        path = f"/tmp/clb_host_{tag}.npy"
+        subprocess.run([sys.executable, "-c", code, path], cwd=root, env={**os.environ, **env}, check=True, timeout=600)
+        res[tag] = np.load(path)
+    assert np.array_equal(res["pipe"], res["plain"])
