@@ -176,6 +176,7 @@ KERNEL_NAMES = {
     3: "k_step_warp<vanGenuchten, fast, EnergyHydrology, 16 lanes/column>",
     4: "k_step_lanes<vanGenuchten, EnergyHydrology, 15, quad> (4 lanes/column, twisted Thomas, TMA-staged constants in shared memory)",
     5: "k_step_lanes<vanGenuchten, EnergyHydrology, 15, quad, pipelined> (persistent, 4 lanes/column, twisted Thomas, double-buffered TMA prefetch)",
+    6: "k_step_lanes<vanGenuchten, EnergyHydrology, 15, octet> (persistent, 8 lanes/column x 2 cells, 4 warps per sub-partition, double-buffered TMA prefetch)",
 }
 
 

@@ -7,7 +7,7 @@ from . import _lib
 from ._lib import ClbError
 from .solver import (BOT_FLUX, BOT_FREE_DRAINAGE, BOT_MOISTURE_STATE, BROOKS_COREY, EARTH, ENERGY_HYDROLOGY,
                      FIELDS, MATH_FAST, MATH_LIBM, RICHARDS, TOP_FLUX, TOP_MOISTURE_STATE, VAN_GENUCHTEN,
-                     VARIANT_AUTO, VARIANT_GENERIC, VARIANT_LANE_QUAD, VARIANT_LANE_QUAD_PIPELINED, VARIANT_LANE_PER_CELL, VARIANT_REGISTER_COLUMN, LAYOUT_AUTO,
+                     VARIANT_AUTO, VARIANT_GENERIC, VARIANT_LANE_QUAD, VARIANT_LANE_QUAD_PIPELINED, VARIANT_LANE_OCTET, VARIANT_LANE_PER_CELL, VARIANT_REGISTER_COLUMN, LAYOUT_AUTO,
                      LAYOUT_COLUMN_FASTEST, LAYOUT_LEVEL_FASTEST, SoilColumnSolver)
 
 from .soil import (B200SoilJacobian, BrooksCorey, Column, EnergyHydrology, EnergyHydrologyParameters, FreeDrainage,

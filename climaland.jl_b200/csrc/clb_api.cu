@@ -319,24 +319,28 @@ clb::GridConst<NS> make_grid_const(clb_handle h)
 
 // Grid constants of the lane-quad kernel in its lane-local orientation (soil_pair.cuh):
 // bottom half slot q = level q, top half slot q = level 15 - q (pads for levels >= N).
-clb::PairGrid make_pair_grid(clb_handle h, double dtg)
+// Grid constants of the lane kernels in the lane-local orientation: half 0 holds levels 0 .. HR-1 bottom -> seam,
+// half 1 holds levels NR-1 .. HR top -> seam (NR = 2 HR rows, the rows >= N are pads).
+template <int HR>
+clb::PairGridT<HR> make_pair_grid(clb_handle h, double dtg)
 {
     const int N = h->cfg.n_levels;
-    clb::PairGrid g;
+    constexpr int NR = 2 * HR;
+    clb::PairGridT<HR> g;
     g.col0 = 0;
     for (int half = 0; half < 2; ++half) {
-        for (int q = 0; q < clb::kPairQ; ++q) {
-            const int level = half ? 15 - q : q;
+        for (int q = 0; q < HR; ++q) {
+            const int level = half ? NR - 1 - q : q;
             const bool real = level < N;
             g.z[half][q] = real ? h->z_c[level] : 0.0;
             g.dti[half][q] = real ? dtg * h->inv_dz_c[level] : 0.0;
         }
-        for (int f = 0; f <= clb::kPairQ; ++f) {
+        for (int f = 0; f <= HR; ++f) {
             // face f lies between slots f-1 and f; inv_dz_f[i] is the face between levels i-1 and i
             double v = 0.0;
-            if (f == clb::kPairQ) v = h->inv_dz_f[8];
+            if (f == HR) v = h->inv_dz_f[HR];
             else if (!half && f >= 1) v = h->inv_dz_f[f];
-            else if (half && f >= 1 && 16 - f <= N - 1) v = h->inv_dz_f[16 - f];
+            else if (half && f >= 1 && NR - f <= N - 1) v = h->inv_dz_f[NR - f];
             g.hidzf[half][f] = v / 2.0;
         }
     }
@@ -434,27 +438,22 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::Pa
     return CLB_OK;
 }
 
-// Lane-quad kernel (soil_pair.cuh, four lanes per column, four cells per lane), two launch shapes:
-//   PIPELINED  persistent, 1 block of 256 threads per SM, each warp double-buffers its tiles: 2 x 14 slots x 1 KB
-//              of shared memory per warp (4 of EnergyHydrology's 18 stage constants stay in registers);
-//   plain      one tile per warp, all constants in shared memory (18 KB per warp), 3 blocks per SM.
-template <int CLOSURE, int MODEL, int N, bool PIPELINED>
-int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0)
+// Lane kernels (soil_pair.cuh), launch shapes:
+//   quad, PIPELINED   4 lanes x 4 cells; persistent, 1 block of 256 threads per SM, each warp double-buffers its tiles:
+//                     2 x 14 slots x 1 KB of shared memory per warp (4 of EnergyHydrology's 18 stage constants stay in
+//                     registers); 8 x 28 KB of tiles + the 2.5 KB of tables fill the 227 KB
+//   quad, plain       one tile per warp, all constants in shared memory (18 KB per warp), 3 blocks of 128 per SM
+//   octet, N <= 16    8 lanes x 2 cells; persistent, 1 block of 512 threads per SM (4 warps per sub-partition at <= 128
+//                     registers), double-buffered tiles of 4 columns: 2 x 14 slots x 512 B per warp
+//   octet, N = 50     8 lanes x 7 cells (56 level rows); persistent, single-buffered tiles of 4 columns (1.75 KB per
+//                     slot) with an L2 prefetch of the next tile; 8 (Richards) or 6 (EnergyHydrology) warps per SM
+template <int CLOSURE, int MODEL, int N, int PARTS, int Q, int NS, int NBUF, int BLOCK, int MINB, bool PERSISTENT>
+int launch_lanes(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0)
 {
-    // the pipelined shape is one 8-warp block per SM: 8 x 28 KB of tiles + the 2.5 KB of tables fill the 227 KB
-    constexpr int PARTS = 2, BLOCK = PIPELINED ? 256 : 128;
-#ifndef CLB_QUAD_MINB
-#define CLB_QUAD_MINB 3
-#endif
-#ifndef CLB_QUAD_NS
-#define CLB_QUAD_NS 18
-#endif
-    constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 11;
-    constexpr int NBUF = PIPELINED ? 2 : 1;
-    constexpr int MINB = PIPELINED ? 1 : CLB_QUAD_MINB;
-    constexpr int CPW = clb::LaneGeom<PARTS>::CPW;
-    auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB>;
-    const size_t smem = clb::pair_smem_bytes<PARTS, NS, NBUF, BLOCK>();
+    using Gm = clb::LaneGeom<PARTS, Q>;
+    constexpr int CPW = Gm::CPW;
+    auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB, Q>;
+    const size_t smem = clb::pair_smem_bytes<PARTS, NS, NBUF, BLOCK, Q>();
     static bool configured = false;  // per instantiation
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -464,12 +463,12 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, 
     const int64_t tiles = (P.ncol + CPW - 1) / CPW;
     int64_t blocks = (tiles * 32 + BLOCK - 1) / BLOCK;
     static const bool persist = getenv("CLB_QUAD_PERSIST") != nullptr;
-    if (PIPELINED || persist) {
+    if (PERSISTENT || persist) {
         int sms = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
         blocks = std::min<int64_t>(blocks, (int64_t)sms * MINB);
     }
-    clb::PairGrid g = make_pair_grid(h, dtg);
+    clb::PairGridT<Gm::HR> g = make_pair_grid<Gm::HR>(h, dtg);
     g.col0 = (int)col0;
     clb::PairMaps maps;
     // the descriptors always describe the whole mirrors (P may be a column sub-range with shifted pointers;
@@ -493,6 +492,22 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, 
     return CLB_OK;
 }
 
+#ifndef CLB_QUAD_MINB
+#define CLB_QUAD_MINB 3
+#endif
+#ifndef CLB_QUAD_NS
+#define CLB_QUAD_NS 18
+#endif
+template <int CLOSURE, int MODEL, int N, bool PIPELINED>
+int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0)
+{
+    constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 11;
+    if constexpr (PIPELINED)
+        return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 2, 256, 1, true>(h, P, dtg, max_iters, col0);
+    else
+        return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 1, 128, CLB_QUAD_MINB, false>(h, P, dtg, max_iters, col0);
+}
+
 template <int N, bool PIPELINED>
 int launch_quad_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0 = 0)
 {
@@ -505,10 +520,32 @@ int launch_quad_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters
               : launch_quad<1, 0, N, PIPELINED>(h, P, dtg, max_iters, col0);
 }
 
-bool pair_variant_applies(clb_handle h)
+template <int CLOSURE, int MODEL, int N>
+int launch_octet(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+{
+    if constexpr (N <= 16) {
+        constexpr int NS = (MODEL == 1) ? 14 : 11;
+        return launch_lanes<CLOSURE, MODEL, N, 4, 2, NS, 2, 512, 1, true>(h, P, dtg, max_iters, 0);
+    } else if constexpr (MODEL == 1) {
+        return launch_lanes<CLOSURE, MODEL, N, 4, 7, 18, 1, 192, 1, true>(h, P, dtg, max_iters, 0);
+    } else {
+        return launch_lanes<CLOSURE, MODEL, N, 4, 7, 11, 1, 256, 1, true>(h, P, dtg, max_iters, 0);
+    }
+}
+
+template <int N>
+int launch_octet_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+{
+    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    const bool vg = h->cfg.closure == CLB_VAN_GENUCHTEN;
+    if (eh) return vg ? launch_octet<0, 1, N>(h, P, dtg, max_iters) : launch_octet<1, 1, N>(h, P, dtg, max_iters);
+    return vg ? launch_octet<0, 0, N>(h, P, dtg, max_iters) : launch_octet<1, 0, N>(h, P, dtg, max_iters);
+}
+
+bool pair_variant_applies(clb_handle h, bool octet = false)
 {
     const int N = h->cfg.n_levels;
-    if (N != 15 && N != 16) return false;
+    if (N != 15 && N != 16 && !(octet && N == 50)) return false;
     if (h->cfg.math_mode != CLB_MATH_FAST) return false;
     // a MoistureStateBC top re-evaluates the boundary fluxes every iteration (rre.jl:460-468): lane-per-cell kernel
     if (h->cfg.model == CLB_RICHARDS && h->cfg.top_bc == 1) return false;
@@ -896,7 +933,7 @@ int clb_create(clb_handle *out, const clb_config *cfg)
         return fail(CLB_ERR_INVALID, "clb_create: unknown boundary condition kind");
     if (cfg->layout < CLB_LAYOUT_AUTO || cfg->layout > CLB_LAYOUT_LEVEL_FASTEST)
         return fail(CLB_ERR_INVALID, "clb_create: unknown layout %d", cfg->layout);
-    if (cfg->kernel_variant < CLB_VARIANT_AUTO || cfg->kernel_variant > CLB_VARIANT_LANE_QUAD_PIPELINED)
+    if (cfg->kernel_variant < CLB_VARIANT_AUTO || cfg->kernel_variant > CLB_VARIANT_LANE_OCTET)
         return fail(CLB_ERR_INVALID, "clb_create: unknown kernel_variant %d", cfg->kernel_variant);
     if (cfg->math_mode != CLB_MATH_FAST && cfg->math_mode != CLB_MATH_LIBM)
         return fail(CLB_ERR_INVALID, "clb_create: unknown math_mode %d", cfg->math_mode);
@@ -921,7 +958,8 @@ int clb_create(clb_handle *out, const clb_config *cfg)
         const bool quad_ok = (cfg->n_levels == 15 || cfg->n_levels == 16) && cfg->math_mode == CLB_MATH_FAST &&
                              !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
                              (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_QUAD ||
-                              cfg->kernel_variant == CLB_VARIANT_LANE_QUAD_PIPELINED);
+                              cfg->kernel_variant == CLB_VARIANT_LANE_QUAD_PIPELINED ||
+                              cfg->kernel_variant == CLB_VARIANT_LANE_OCTET);
         const bool lane_per_cell = cfg->n_levels <= 31 && (cfg->kernel_variant == CLB_VARIANT_AUTO ||
                                                            cfg->kernel_variant == CLB_VARIANT_LANE_PER_CELL);
         layout = (!quad_ok && lane_per_cell) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
@@ -1321,6 +1359,8 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     } else if (variant == CLB_VARIANT_AUTO) {
         if (pair_variant_applies(h))
             variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
+        else if (pair_variant_applies(h, true))
+            variant = CLB_VARIANT_LANE_OCTET;  // N = 50
         else if (level_fast && N <= 31)
             variant = CLB_VARIANT_LANE_PER_CELL;
         else if (N == 15)
@@ -1334,6 +1374,10 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
         return fail(CLB_ERR_INVALID,
                     "clb_implicit_step: the lane-quad variants need N = 15 or 16, CLB_MATH_FAST, column-fastest mirrors and flux "
                     "boundary conditions");
+    if (variant == CLB_VARIANT_LANE_OCTET && !pair_variant_applies(h, true))
+        return fail(CLB_ERR_INVALID,
+                    "clb_implicit_step: the lane-octet variant needs N = 15, 16 or 50, CLB_MATH_FAST, column-fastest mirrors and "
+                    "flux boundary conditions");
     if (variant == CLB_VARIANT_LANE_PER_CELL && N > 31)
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the lane-per-cell variant needs N <= 31");
     if (variant == CLB_VARIANT_GENERIC) TRY(ensure_work(h, eh ? 6 : 3));
@@ -1343,7 +1387,8 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
         if (eh) TRY(alloc_fields(h, {CLB_F_U_RHO_E_INT, CLB_F_U_INTF_E}));
     }
     clb::DevView P = make_view(h);
-    const bool quad = variant == CLB_VARIANT_LANE_QUAD || variant == CLB_VARIANT_LANE_QUAD_PIPELINED;
+    const bool quad = variant == CLB_VARIANT_LANE_QUAD || variant == CLB_VARIANT_LANE_QUAD_PIPELINED ||
+                      variant == CLB_VARIANT_LANE_OCTET;
     if (quad && fixed && !stats)
         P.stats = nullptr;  // nobody reads them: no memset between stages, no atomics in the kernel
     else
@@ -1358,6 +1403,10 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
         } else if (variant == CLB_VARIANT_LANE_QUAD_PIPELINED) {
             if (N == 15) TRY((launch_quad_n<15, true>(h, P, dtgamma, max_iters)));
             else TRY((launch_quad_n<16, true>(h, P, dtgamma, max_iters)));
+        } else if (variant == CLB_VARIANT_LANE_OCTET) {
+            if (N == 15) TRY((launch_octet_n<15>(h, P, dtgamma, max_iters)));
+            else if (N == 16) TRY((launch_octet_n<16>(h, P, dtgamma, max_iters)));
+            else TRY((launch_octet_n<50>(h, P, dtgamma, max_iters)));
         } else if (variant == CLB_VARIANT_LANE_PER_CELL) {
             const int cpw = (N <= 15) ? 2 : 1;  // columns per warp (one lane of each segment is a ghost)
             const int64_t warps = (P.ncol + cpw - 1) / cpw;

@@ -39,6 +39,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "soil_device.cuh"
 #include "soil_fused.cuh"
 #include "soil_mathv.cuh"
@@ -53,14 +55,17 @@ constexpr int kPairW = CLB_PAIR_W;  // cells evaluated together (interleaved dep
 
 // Per-launch grid constants in the lane-local orientation, [half][slot]; a kernel
 // parameter (constant bank), indexed with the lane's half at run time.
-struct PairGrid {
-    double z[2][kPairQ];          // z_c of the cell
-    double dti[2][kPairQ];        // dtgamma / dz_c of the cell; 0 for pad slots
-    double hidzf[2][kPairQ + 1];  // 1/(2 dz_f) of face f (f = q: outer face of slot q, 8: seam); 0 for boundary / pad faces
+// HR: cell slots per half column (= PARTS * Q; 8 for the lane pair / quad / octet of 15-16 levels).
+template <int HR>
+struct PairGridT {
+    double z[2][HR];          // z_c of the cell
+    double dti[2][HR];        // dtgamma / dz_c of the cell; 0 for pad slots
+    double hidzf[2][HR + 1];  // 1/(2 dz_f) of face f (f = q: outer face of slot q, HR: seam); 0 for boundary / pad faces
     int col0;                     // first column of this launch within the mirrors the TMA descriptors describe
                                   // (a launch over a column sub-range: the pointers of DevView are shifted, the
                                   // descriptors are not)
 };
+using PairGrid = PairGridT<kPairQ>;
 
 // Stage constants per cell: slots [0, NS) in shared memory, the rest in registers.
 //   Richards (11)         theta_r, nu, ca, ca2, cb, 1/S_s, cc, cd, K_sat, t1, 1/range
@@ -85,8 +90,8 @@ struct PairMaps {
     CUtensorMap m[14];
 };
 
-// Q cells per lane, CPW columns per warp: a slot of the warp tile is [16 level rows][CPW columns].
-template <int NS, int NTOT, int Q, int CPW>
+// Q cells per lane, CPW columns per warp: a slot of the warp tile is [NR level rows][CPW columns].
+template <int NS, int NTOT, int Q, int CPW, int NR = 16>
 struct PairStore {
     double *base;  // warp tile + this lane's column
     int half, r0;  // r0: first slot of this lane within its half (0, or Q for the inner lane of a quad)
@@ -94,8 +99,8 @@ struct PairStore {
     // level row of cell q: slot r0 + q of the half, counted from the column's boundary
     __device__ __forceinline__ double *at(int q, int slot) const
     {
-        const int row = half ? 15 - (r0 + q) : r0 + q;
-        return base + (slot * 16 + row) * CPW;
+        const int row = half ? NR - 1 - (r0 + q) : r0 + q;
+        return base + (slot * NR + row) * CPW;
     }
     template <int SLOT>
     __device__ __forceinline__ double get(int q) const
@@ -213,47 +218,55 @@ __global__ void k_prepare_params(const double *__restrict__ S_s, const double *_
 #define CLB_PAIR_BLOCK 64
 #endif
 
-// Lane geometry of a column split over 2 * PARTS lanes (PARTS = 1: lane pair, 2: lane quad).
+// Lane geometry of a column split over 2 * PARTS lanes (PARTS = 1: lane pair, 2: lane quad, 4: lane octet),
+// Q cells per lane, NR = 2 * PARTS * Q level rows per slot (>= N; the pads sit at the top of the column).
 //   lane = column-in-warp + CPW * (part * 2 + half);  part 0 touches the column boundary,
-//   part PARTS-1 the seam.  xor CPW swaps the halves, xor 2*CPW swaps the two parts of a half.
-//   With the half in the low bit a half-warp (the unit of a 64-bit shared-memory access) holds the
-//   level rows q' and 15 - q' of a slot: opposite parity, i.e. the two 64-byte halves of the 32 banks,
-//   so the slot accesses are conflict-free (half-major order put rows q and q + 4 on the same banks).
-template <int PARTS>
+//   part PARTS-1 the seam.  xor CPW swaps the halves; the previous / next part of a half is 2*CPW lanes
+//   down / up.  With the half in the low bit a half-warp (the unit of a 64-bit shared-memory access) holds the
+//   level rows q' and NR-1 - q' of a slot: opposite parity, i.e. different banks for 8-column rows, so the
+//   slot accesses of the quad are conflict-free (half-major order put rows q and q + 4 on the same banks).
+template <int PARTS, int Q_ = kPairQ / PARTS>
 struct LaneGeom {
-    static_assert(PARTS == 1 || PARTS == 2, "lane pair or lane quad");
+    static_assert(PARTS == 1 || PARTS == 2 || PARTS == 4, "lane pair, quad or octet");
     static constexpr int LPC = 2 * PARTS;     // lanes per column
     static constexpr int CPW = 32 / LPC;      // columns per warp
-    static constexpr int Q = kPairQ / PARTS;  // cells per lane
+    static constexpr int Q = Q_;              // cells per lane
+    static constexpr int HR = PARTS * Q;      // cell slots per half column
+    static constexpr int NR = 2 * HR;         // level rows of a slot
     static constexpr int SEAM = CPW;          // xor mask: the other half of the column
-    static constexpr int PARTX = 2 * CPW;     // xor mask: the other part of this half (lane quad)
-    static constexpr int kSlotBytes = 16 * CPW * 8;  // one slot of a warp tile: 16 level rows x CPW columns
+    static constexpr int PARTD = 2 * CPW;     // lane distance to the next part of this half
+    static constexpr int kSlotBytes = NR * CPW * 8;  // one slot of a warp tile: NR level rows x CPW columns
 };
+
+// value of the previous (outer) / next (inner) part's lane of this half; own value where there is none
+template <int DIST>
+__device__ __forceinline__ double from_prev_part(double v) { return __shfl_up_sync(0xffffffffu, v, DIST); }
+template <int DIST>
+__device__ __forceinline__ double from_next_part(double v) { return __shfl_down_sync(0xffffffffu, v, DIST); }
 
 // Values of the neighbours across lane boundaries: `inner` = neighbour of this lane's last cell
 // (the other half's last cell at the seam, else the first cell of the next part), `outer` =
 // neighbour of its first cell (last cell of the previous part; finite garbage for part 0, whose
 // outer face is the column boundary and carries a zero coefficient).
-template <int PARTS>
+template <class Gm>
 __device__ __forceinline__ void nb_exchange(double first, double last, bool innermost, double &outer, double &inner)
 {
-    using Gm = LaneGeom<PARTS>;
     const double seam = xchg<Gm::SEAM>(last);
-    if (PARTS == 1) {
+    if (Gm::LPC == 2) {
         inner = seam;
         outer = first;
     } else {
-        const double nb_first = xchg<Gm::PARTX>(first), nb_last = xchg<Gm::PARTX>(last);
+        const double nb_first = from_next_part<Gm::PARTD>(first), nb_last = from_prev_part<Gm::PARTD>(last);
         inner = innermost ? seam : nb_first;
         outer = nb_last;
     }
 }
 
 // Dynamic shared memory of a block: the log / exp tables, then NBUF NS-slot tiles and NBUF mbarriers per warp.
-template <int PARTS, int NS, int NBUF, int BLOCK>
+template <int PARTS, int NS, int NBUF, int BLOCK, int Q = kPairQ / PARTS>
 __host__ __device__ constexpr size_t pair_smem_bytes()
 {
-    return (size_t)fmv::kMathTabBytes + (size_t)(BLOCK / 32) * NBUF * (NS * LaneGeom<PARTS>::kSlotBytes + 8);
+    return (size_t)fmv::kMathTabBytes + (size_t)(BLOCK / 32) * NBUF * (NS * LaneGeom<PARTS, Q>::kSlotBytes + 8);
 }
 
 // Per-column scalars of a tile, fetched one tile ahead into registers.
@@ -282,14 +295,17 @@ __device__ __forceinline__ ColScalars load_col_scalars(const DevView &P, int64_t
 // PERSISTENT: every warp walks over tiles (CPW columns each) t = warp, warp + nwarps, ...; with
 // NBUF = 2 the TMA boxes and the per-column scalars of the next tile are requested before the
 // current tile is touched, so HBM latency hides behind a whole tile of FP64 work.
-template <int CLOSURE, int MODEL, int N, int PARTS, int NS, int NBUF, int BLOCK, int MINB>
+template <int CLOSURE, int MODEL, int N, int PARTS, int NS, int NBUF, int BLOCK, int MINB, int QC = kPairQ / PARTS>
 __global__ void __launch_bounds__(BLOCK, MINB)
-    k_step_lanes(const DevView P, const PairGrid G, const __grid_constant__ PairMaps M, double dtg, int max_iters)
+    k_step_lanes(const DevView P, const PairGridT<PARTS * QC> G, const __grid_constant__ PairMaps M, double dtg,
+                 int max_iters)
 {
-    using Gm = LaneGeom<PARTS>;
-    constexpr int Q = Gm::Q, CPW = Gm::CPW, W = (Q < kPairW) ? Q : kPairW;
-    constexpr int Q0T = 16 - N;  // first real slot of the top half (pads before it, all in part 0)
-    static_assert(N <= 16 && Q0T < Q, "lane-pair kernel: 9 <= N <= 16, lane-quad kernel: 13 <= N <= 16");
+    using Gm = LaneGeom<PARTS, QC>;
+    constexpr int Q = Gm::Q, CPW = Gm::CPW, NR = Gm::NR;
+    // cells evaluated together: a divisor of Q close to kPairW (Q = 7 -> one group of 7 would not fit: 4 + 3)
+    constexpr int WFULL = (Q <= kPairW) ? Q : kPairW;
+    constexpr int Q0T = NR - N;  // first real slot of the top half (pads before it, all in part 0)
+    static_assert(N <= NR && Q0T < Q, "the pads must all lie in part 0 of the top half: NR - Q < N <= NR");
     static_assert(NBUF == 1 || NBUF == 2, "single or double buffered");
     constexpr int NTOT = PairSlots<MODEL>::kConst, NRAW = PairSlots<MODEL>::kRaw;
     static_assert(NS >= NRAW && NS <= NTOT, "the raw fields are staged in the shared-memory slots");
@@ -313,10 +329,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     constexpr size_t kTileBytes = (size_t)NS * Gm::kSlotBytes;
     unsigned char *const tiles = pair_sm + (size_t)wib * NBUF * kTileBytes;
     const unsigned bar0 = smem_u32(pair_sm + (size_t)(BLOCK / 32) * NBUF * kTileBytes + (size_t)wib * NBUF * 8);
-    PairStore<NS, NTOT, Q, CPW> S;
+    PairStore<NS, NTOT, Q, CPW, NR> S;
     S.half = half;
     S.r0 = r0;
-    auto level_of = [&](int q) { return half ? 15 - (r0 + q) : r0 + q; };
+    auto level_of = [&](int q) { return half ? NR - 1 - (r0 + q) : r0 + q; };
     auto col_of = [&](int64_t t) { return t * CPW + (lane % CPW); };
     auto col_clamped = [&](int64_t t) { const int64_t c_ = col_of(t); return c_ < P.ncol ? c_ : P.ncol - 1; };
 
@@ -477,9 +493,9 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                                                      real ? S.template get<9>(q) : 1e6, E));
         }
         double K_out, K_in, kap_out, kap_in, rc_out, rc_in;
-        nb_exchange<PARTS>(Kl[0], Kl[Q - 1], innermost, K_out, K_in);
-        nb_exchange<PARTS>(kap[0], kap[Q - 1], innermost, kap_out, kap_in);
-        nb_exchange<PARTS>(rc[0], rc[Q - 1], innermost, rc_out, rc_in);
+        nb_exchange<Gm>(Kl[0], Kl[Q - 1], innermost, K_out, K_in);
+        nb_exchange<Gm>(kap[0], kap[Q - 1], innermost, kap_out, kap_in);
+        nb_exchange<Gm>(rc[0], rc[Q - 1], innermost, rc_out, rc_in);
         aK8 = (Kl[Q - 1] + K_in) * G.hidzf[half][r0 + Q];
         aC8 = (kap[Q - 1] + kap_in) * G.hidzf[half][r0 + Q];
         double aCo[Q], o22[Q], d22[Q], i22[Q];
@@ -548,7 +564,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     Dp = D[q];
                 }
                 if (pass + 1 < PARTS) {
-                    const double rD_ = xchg<Gm::PARTX>(D[Q - 1]), riD_ = xchg<Gm::PARTX>(iD[Q - 1]);
+                    const double rD_ = from_prev_part<Gm::PARTD>(D[Q - 1]), riD_ = from_prev_part<Gm::PARTD>(iD[Q - 1]);
                     Din = outermost ? 1.0 : rD_;
                     iDin = outermost ? 0.0 : riD_;
                 }
@@ -577,8 +593,9 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     for (int it = 0; it < max_iters; ++it) {
         // cache_imp!: closures (and temperature) at the iterate, W cells at a time
         double h[Q], dps[Q], Kc[Q], Td[Q], eK[Q];
-#pragma unroll
-        for (int g = 0; g < Q; g += W) {
+        // one group of WW cells (WW independent dependency chains); Q = WG full groups of W and a tail
+        auto closure_group = [&](auto wtag, const int g) {
+            constexpr int W = decltype(wtag)::value;
             double th[W], thr[W], nue[W], ca[W], ca2[W], cb[W], iSs[W], ccc[W], cd[W], Ksat[W], irg[W];
             double K[W], psi[W], dp[W];
 #pragma unroll
@@ -634,14 +651,17 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 dps[g + j] = dp[j];
                 if (MODEL == 0) Kc[g + j] = K[j];
             }
-        }
+                };
+#pragma unroll
+        for (int g = 0; g + WFULL <= Q; g += WFULL) closure_group(std::integral_constant<int, WFULL>{}, g);
+        if constexpr (Q % WFULL != 0) closure_group(std::integral_constant<int, Q % WFULL>{}, Q - Q % WFULL);
         double h_out, h_in, dps_out, dps_in, K_out = 0.0, K_in = 0.0, T_out = 0.0, T_in = 0.0, eK_out = 0.0, eK_in = 0.0;
-        nb_exchange<PARTS>(h[0], h[Q - 1], innermost, h_out, h_in);
-        nb_exchange<PARTS>(dps[0], dps[Q - 1], innermost, dps_out, dps_in);
-        if (MODEL == 0) nb_exchange<PARTS>(Kc[0], Kc[Q - 1], innermost, K_out, K_in);
+        nb_exchange<Gm>(h[0], h[Q - 1], innermost, h_out, h_in);
+        nb_exchange<Gm>(dps[0], dps[Q - 1], innermost, dps_out, dps_in);
+        if (MODEL == 0) nb_exchange<Gm>(Kc[0], Kc[Q - 1], innermost, K_out, K_in);
         if (MODEL == 1) {
-            nb_exchange<PARTS>(Td[0], Td[Q - 1], innermost, T_out, T_in);
-            nb_exchange<PARTS>(eK[0], eK[Q - 1], innermost, eK_out, eK_in);
+            nb_exchange<Gm>(Td[0], Td[Q - 1], innermost, T_out, T_in);
+            nb_exchange<Gm>(eK[0], eK[Q - 1], innermost, eK_out, eK_in);
         }
 
         // T_imp! and Wfact: face fluxes, residuals and the rows of W11 = dtgamma dT/dtheta - I
@@ -717,7 +737,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     Dp = D[q];
                 }
                 if (pass + 1 < PARTS) {
-                    const double rD_ = xchg<Gm::PARTX>(D[Q - 1]), riD_ = xchg<Gm::PARTX>(iD[Q - 1]), rg_ = xchg<Gm::PARTX>(gam[Q - 1]);
+                    const double rD_ = from_prev_part<Gm::PARTD>(D[Q - 1]), riD_ = from_prev_part<Gm::PARTD>(iD[Q - 1]),
+                                 rg_ = from_prev_part<Gm::PARTD>(gam[Q - 1]);
                     Din = outermost ? 1.0 : rD_;
                     iDin = outermost ? 0.0 : riD_;
                     gin = outermost ? 0.0 : rg_;
@@ -737,7 +758,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 x1[Q - 1] = (pass == 0) ? xs : (innermost ? xs : fma(-c1[Q - 1], xn, g1[Q - 1]));
 #pragma unroll
                 for (int q = Q - 2; q >= 0; --q) x1[q] = fma(-c1[q], x1[q + 1], g1[q]);
-                if (pass + 1 < PARTS) xn = xchg<Gm::PARTX>(x1[0]);
+                if (pass + 1 < PARTS) xn = from_next_part<Gm::PARTD>(x1[0]);
             }
         }
         const bool last = (it == max_iters - 1);
@@ -756,7 +777,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             // W21 = -dtgamma (D . Diag(interp(-e_l K)) . G . Diag(dpsi)) - I  (energy_hydrology.jl:545-556),
             // then the pre-factored W22
             double y_out, y_in;
-            nb_exchange<PARTS>(y[0], y[Q - 1], innermost, y_out, y_in);
+            nb_exchange<Gm>(y[0], y[Q - 1], innermost, y_out, y_in);
             double b2[Q], g2[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -776,7 +797,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     g2[q] = gp;
                 }
                 if (pass + 1 < PARTS) {
-                    const double rg_ = xchg<Gm::PARTX>(gp);
+                    const double rg_ = from_prev_part<Gm::PARTD>(gp);
                     gin = outermost ? 0.0 : rg_;
                 }
             }
@@ -787,7 +808,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 x2[Q - 1] = (pass == 0) ? xs : (innermost ? xs : fma(-c22_last, xn, g2[Q - 1]));
 #pragma unroll
                 for (int q = Q - 2; q >= 0; --q) x2[q] = fma(-S.template get<E_C22>(q), x2[q + 1], g2[q]);
-                if (pass + 1 < PARTS) xn = xchg<Gm::PARTX>(x2[0]);
+                if (pass + 1 < PARTS) xn = from_next_part<Gm::PARTD>(x2[0]);
             }
 #pragma unroll
             for (int q = 0; q < Q; ++q) {

@@ -25,6 +25,7 @@ MATH_FAST, MATH_LIBM = K["CLB_MATH_FAST"], K["CLB_MATH_LIBM"]
 VARIANT_AUTO, VARIANT_REGISTER_COLUMN, VARIANT_GENERIC, VARIANT_LANE_PER_CELL, VARIANT_LANE_QUAD, VARIANT_LANE_QUAD_PIPELINED = (
     K["CLB_VARIANT_AUTO"], K["CLB_VARIANT_REGISTER_COLUMN"], K["CLB_VARIANT_GENERIC"], K["CLB_VARIANT_LANE_PER_CELL"],
     K["CLB_VARIANT_LANE_QUAD"], K["CLB_VARIANT_LANE_QUAD_PIPELINED"])
+VARIANT_LANE_OCTET = K["CLB_VARIANT_LANE_OCTET"]
 LAYOUT_AUTO, LAYOUT_COLUMN_FASTEST, LAYOUT_LEVEL_FASTEST = (K["CLB_LAYOUT_AUTO"], K["CLB_LAYOUT_COLUMN_FASTEST"],
                                                             K["CLB_LAYOUT_LEVEL_FASTEST"])
 
