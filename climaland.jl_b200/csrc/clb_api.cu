@@ -1359,8 +1359,12 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     } else if (variant == CLB_VARIANT_AUTO) {
         if (pair_variant_applies(h))
             variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
-        else if (pair_variant_applies(h, true))
-            variant = CLB_VARIANT_LANE_OCTET;  // N = 50
+        else if (pair_variant_applies(h, true) && (int64_t)h->ld * N * 8 <= (int64_t)80 << 20)
+            // N = 50.  A tile of the octet touches all 50 level rows of every field at once; in column-fastest
+            // mirrors these lie ld * 8 bytes apart, and as the fields grow the tile's ~550 pages fall out of the TLB
+            // (measured against the generic kernel, tools/n50_crossover.py: 2.1x faster at 1e5 columns, 1.2x at
+            // 1.5e5, equal at ~2.2e5 = 88 MB per field, 1.7x slower at 1e6)
+            variant = CLB_VARIANT_LANE_OCTET;
         else if (level_fast && N <= 31)
             variant = CLB_VARIANT_LANE_PER_CELL;
         else if (N == 15)
