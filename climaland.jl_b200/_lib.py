@@ -29,6 +29,10 @@ class ExplicitParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("Omega", "gamma", "gammaT_ref", "alpha", "beta", "T_freeze", "grav")]
 
 
+class RunoffParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("f_over", "R_sb", "depth")]
+
+
 class Stats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("dx_norm", C.c_double),
                 ("nan_count", C.c_int64)]
@@ -94,6 +98,7 @@ def lib():
         "clb_update_implicit_cache": [h], "clb_update_boundary_fluxes": [h],
         "clb_compute_imp_tendency": [h], "clb_compute_jacobian": [h, d], "clb_ldiv": [h],
         "clb_set_explicit_params": [h, C.POINTER(ExplicitParams)],
+        "clb_set_runoff_params": [h, C.POINTER(RunoffParams)], "clb_update_runoff": [h],
         "clb_update_aux": [h], "clb_phase_change_source": [h], "clb_update_aux_and_phase_change": [h],
         "clb_implicit_step": [h, d, i32, d, C.POINTER(Stats)],
         "clb_implicit_step_host": [h, d, i32, C.POINTER(i32), C.POINTER(C.c_void_p), i32,

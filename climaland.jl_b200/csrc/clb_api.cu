@@ -148,6 +148,8 @@ struct clb_handle_s {
     // explicit stage of EnergyHydrology (soil_explicit.cuh)
     clb::ExplicitConst explicit_k = {};
     bool explicit_set = false;
+    clb_runoff_params runoff_k = {};
+    bool runoff_set = false;
     // multi-GPU
     NcclComm comm = nullptr;
     int32_t n_ranks = 1, rank = 0;
@@ -1258,6 +1260,47 @@ int clb_set_explicit_params(clb_handle h, const clb_explicit_params *p)
         return fail(CLB_ERR_INVALID, "clb_set_explicit_params: grav and T_freeze must be positive");
     h->explicit_k = {p->Omega, p->gamma, p->gammaT_ref, p->alpha, p->beta, p->T_freeze, p->grav};
     h->explicit_set = true;
+    return CLB_OK;
+}
+
+int clb_set_runoff_params(clb_handle h, const clb_runoff_params *p)
+{
+    TRY(check_handle(h));
+    if (!p) return fail(CLB_ERR_INVALID, "clb_set_runoff_params: null parameters");
+    if (!(p->depth > 0.0)) return fail(CLB_ERR_INVALID, "clb_set_runoff_params: depth must be positive");
+    h->runoff_k = *p;
+    h->runoff_set = true;
+    return CLB_OK;
+}
+
+int clb_update_runoff(clb_handle h)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
+    if (!h->runoff_set) return fail(CLB_ERR_UNSET, "update_runoff: clb_set_runoff_params was never called");
+    TRY(require(h, {CLB_F_NU, CLB_F_THETA_R, CLB_F_K_SAT, CLB_F_Y_THETA_L, CLB_F_F_MAX, CLB_F_PRECIP}, "update_runoff"));
+    if (eh) {
+        if (!h->explicit_set) return fail(CLB_ERR_UNSET, "update_runoff: clb_set_explicit_params was never called");
+        TRY(require(h, {CLB_F_Y_THETA_I, CLB_F_THETA_L_LAG, CLB_F_P_T}, "update_runoff (call clb_update_aux first)"));
+        TRY(alloc_fields(h, {CLB_F_R_ESS}));
+    }
+    TRY(alloc_fields(h, {CLB_F_IS_SATURATED, CLB_F_H_GRAD, CLB_F_R_SS, CLB_F_INFILTRATION, CLB_F_R_S}));
+    const clb::DevView P = make_view(h);
+    double *const *F = h->field;
+    clb::RunoffView R;
+    R.f_max = F[CLB_F_F_MAX]; R.precip = F[CLB_F_PRECIP];
+    R.is_sat = F[CLB_F_IS_SATURATED]; R.h_grad = F[CLB_F_H_GRAD]; R.infiltration = F[CLB_F_INFILTRATION];
+    R.R_s = F[CLB_F_R_S]; R.R_ss = F[CLB_F_R_SS]; R.R_ess = F[CLB_F_R_ESS];
+    R.p_theta_l = F[CLB_F_THETA_L_LAG]; R.p_T = F[CLB_F_P_T];
+    R.f_over = h->runoff_k.f_over; R.R_sb = h->runoff_k.R_sb; R.depth = h->runoff_k.depth;
+    R.Omega = h->explicit_k.Omega; R.gamma = h->explicit_k.gamma; R.gammaT_ref = h->explicit_k.gammaT_ref;
+    nvtxRangePushA("update_runoff!");
+    if (h->cfg.math_mode == CLB_MATH_FAST) clb::k_update_runoff<0><<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, R);
+    else clb::k_update_runoff<1><<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, R);
+    nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
     return CLB_OK;
 }
 

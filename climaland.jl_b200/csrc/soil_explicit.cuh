@@ -234,4 +234,56 @@ __global__ void __launch_bounds__(128) k_explicit_totals(const DevView P, const 
     X.total_energy[c] = te;
 }
 
+// ---- TOPMODEL runoff -------------------------------------------------------------
+// update_infiltration_water_flux!(p, ::TOPMODELRunoff, input, Y, t, model): Runoff/Runoff.jl:234-283;
+// topmodel_surface_infiltration :373-376, soil_infiltration_capacity :385-410, topmodel_ss_flux :421-423,
+// is_saturated :432-434, update_subsurface_energy_runoff! :266-279.  One thread per column; the three column
+// integrals (ice-inclusive and liquid-only saturated thickness, liquid energy of the saturated layers) share one
+// sweep over the levels.
+struct RunoffView {
+    const double *f_max, *precip;               // per column
+    double *is_sat, *h_grad, *infiltration, *R_s, *R_ss, *R_ess;
+    const double *p_theta_l, *p_T;              // EnergyHydrology: p.soil.theta_l, p.soil.T
+    double f_over, R_sb, depth, Omega, gamma, gammaT_ref;
+};
+
+template <int MATH>
+__global__ void __launch_bounds__(128) k_update_runoff(const DevView P, const RunoffView R)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.ncol) return;
+    const bool eh = P.model == 1;
+    const EarthConst &E = P.earth;
+    double h_all = 0.0, h_liq = 0.0, e_liq = 0.0;
+    for (int i = 0; i < P.N; ++i) {
+        const int64_t q = P.at(i, c);
+        const double th = P.Y_theta_l[q], thi = eh ? P.Y_theta_i[q] : 0.0;
+        const double nu = __ldg(P.nu + q), theta_r = __ldg(P.theta_r + q);
+        const double range = nu - theta_r, dz = P.dz_c[i];
+        const double s_all = heaviside((th + thi - theta_r) - range) * (th + thi - theta_r) / range;
+        const double s_liq = heaviside((th - theta_r) - range) * (th - theta_r) / range;
+        R.is_sat[q] = s_liq;
+        h_all += s_all * dz;
+        h_liq += s_liq * dz;
+        if (eh) e_liq += s_liq * volumetric_internal_energy_liq(R.p_T[q], E) * dz;
+    }
+    const int64_t qt = P.at(P.N - 1, c);
+    double ic = -1 * __ldg(P.K_sat + qt);
+    if (eh) {
+        const double thi = P.Y_theta_i[qt];
+        const double f_i = thi / (R.p_theta_l[qt] + thi - __ldg(P.theta_r + qt));
+        const double imp = (MATH == kMathLibm) ? pow(10.0, -R.Omega * f_i) : texp((-R.Omega * f_i) * 2.302585092994045684);
+        ic = -__ldg(P.K_sat + qt) * imp * ex<MATH>(R.gamma * (R.p_T[qt] - R.gammaT_ref));
+    }
+    const double precip = R.precip[c];
+    const double f_sat = fmin(R.f_max[c] * ex<MATH>(-R.f_over / 2.0 * (R.depth - h_all)), 1.0);
+    const double inf = (1.0 - f_sat) * fmax(ic, precip);
+    const double R_ss = R.R_sb * ex<MATH>(-R.f_over * (R.depth - h_liq));
+    R.infiltration[c] = inf;
+    R.R_s[c] = fabs(precip - inf);
+    R.h_grad[c] = h_liq;
+    R.R_ss[c] = R_ss;
+    if (eh) R.R_ess[c] = e_liq * (R_ss / fmax(h_liq, kEps));
+}
+
 }  // namespace clb

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import K, ClbError, Config, ExplicitParams, Stats, check
+from ._lib import K, ClbError, Config, ExplicitParams, RunoffParams, Stats, check
 
 # LandParameters constants (ClimaParams defaults; passed in as numbers,
 # src/shared_utilities/Parameters.jl:86-105)
@@ -153,6 +153,14 @@ class SoilColumnSolver:
         """Scalars of EnergyHydrologyParameters (energy_hydrology.jl:150-160) + T_freeze, grav."""
         p = ExplicitParams(Omega, gamma, gammaT_ref, alpha, beta, T_freeze, grav)
         check(self.L.clb_set_explicit_params(self.h, C.byref(p)))
+
+    def set_runoff_params(self, *, f_over, R_sb, depth):
+        """TOPMODELRunoff scalars (Runoff/Runoff.jl:190-222) and the domain depth."""
+        p = RunoffParams(f_over, R_sb, depth)
+        check(self.L.clb_set_runoff_params(self.h, C.byref(p)))
+
+    def update_runoff(self):
+        check(self.L.clb_update_runoff(self.h))
 
     def update_aux(self):
         check(self.L.clb_update_aux(self.h))

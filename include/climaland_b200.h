@@ -139,6 +139,8 @@ typedef enum {
     CLB_F_AREA_WEIGHT,                        /* weights of the global balance sums */
     CLB_F_U_INTF_W, CLB_F_U_INTF_E,           /* out-of-place new flux integrals */
     CLB_F_TOTAL_ENERGY,                       /* p.soil.total_energy (explicit update_aux!) */
+    CLB_F_F_MAX, CLB_F_PRECIP,                /* TOPMODELRunoff.f_max; the liquid water input (precipitation + melt, m/s, negative down) */
+    CLB_F_INFILTRATION, CLB_F_R_S,            /* p.soil.infiltration, p.soil.R_s (clb_update_runoff) */
     CLB_F_NUM
 } clb_field;
 
@@ -246,6 +248,18 @@ int clb_phase_change_source(clb_handle h);
 /* Both in one pass over the fields (the source reads the aux values it has just computed): what a
  * resident explicit stage calls. */
 int clb_update_aux_and_phase_change(clb_handle h);
+
+/* TOPMODEL runoff of the explicit stage: update_infiltration_water_flux!(p,
+ * ::TOPMODELRunoff, input, Y, t, model), src/standalone/Soil/Runoff/Runoff.jl:234-283 (+ :373-434).  From
+ * Y, CLB_F_PRECIP (`input`), CLB_F_F_MAX and, for EnergyHydrology, p.soil.{theta_l, T} (clb_update_aux) and
+ * the impedance / viscosity scalars of clb_set_explicit_params, writes the lagged inputs of the implicit
+ * TOPMODELSubsurfaceRunoff source -- CLB_F_IS_SATURATED, CLB_F_H_GRAD, CLB_F_R_SS, CLB_F_R_ESS -- and
+ * CLB_F_INFILTRATION, CLB_F_R_S.  depth: model.domain.depth. */
+typedef struct {
+    double f_over, R_sb, depth;
+} clb_runoff_params;
+int clb_set_runoff_params(clb_handle h, const clb_runoff_params *p);
+int clb_update_runoff(clb_handle h);
 
 /* ---- the fused implicit stage -------------------------------------------- */
 /* One implicit ARS111 stage on the resident state Y (in: U = temp, out: new U):

@@ -55,6 +55,7 @@ const CLB_HOST, CLB_DEVICE = Int32(0), Int32(1)
     F_TOP_BC_W; F_BOT_BC_W; F_TOP_BC_H; F_BOT_BC_H; F_DFLUXBCDY; F_TOTAL_WATER
     F_Y_INTF_W; F_Y_INTF_E; F_DY_INTF_W; F_DY_INTF_E; F_B_INTF_W; F_B_INTF_E; F_X_INTF_W; F_X_INTF_E
     F_AREA_WEIGHT; F_U_INTF_W; F_U_INTF_E; F_TOTAL_ENERGY
+    F_F_MAX; F_PRECIP; F_INFILTRATION; F_R_S
 end
 
 # struct clb_config (same field order and widths as the header)
@@ -173,7 +174,9 @@ struct B200Soil{M}
     model::M
     h::Handle
     energy::Bool
+    runoff_set::Base.RefValue{Bool}   # TOPMODEL parameters uploaded (update_infiltration_water_flux!)
 end
+B200Soil(model, h::Handle, energy::Bool) = B200Soil(model, h, energy, Ref(false))
 
 function B200Soil(model::Union{Soil.RichardsModel, Soil.EnergyHydrology}, Y, p)
     FT = eltype(Y)
@@ -310,6 +313,33 @@ function ClimaLand.source!(dY::Fields.FieldVector, src::Soil.PhaseChange, Y::Fie
     set_field!(b.h, F_DYE_THETA_L, dY.soil.ϑ_l); set_field!(b.h, F_DYE_THETA_I, dY.soil.θ_i)
     check(ccall((:clb_phase_change_source, libclb), Cint, (Ptr{Cvoid},), b.h.ptr))
     get_field!(dY.soil.ϑ_l, b.h, F_DYE_THETA_L); get_field!(dY.soil.θ_i, b.h, F_DYE_THETA_I)
+    return nothing
+end
+
+struct ClbRunoffParams
+    f_over::Float64
+    R_sb::Float64
+    depth::Float64
+end
+
+"""
+update_infiltration_water_flux!(p, runoff::TOPMODELRunoff, input, Y, t, model):
+src/standalone/Soil/Runoff/Runoff.jl:234-283.  Leaves R_ss, R_ess, h∇ and is_saturated in the mirrors the
+implicit TOPMODELSubsurfaceRunoff source reads, and refreshes Julia's copies.
+"""
+function update_infiltration_water_flux!(p, runoff::Soil.Runoff.TOPMODELRunoff, input, Y, t, b::B200Soil, depth)
+    if !b.runoff_set[]
+        r = Ref(ClbRunoffParams(runoff.f_over, runoff.subsurface_source.R_sb, depth))
+        check(ccall((:clb_set_runoff_params, libclb), Cint, (Ptr{Cvoid}, Ref{ClbRunoffParams}), b.h.ptr, r))
+        set_field!(b.h, F_F_MAX, runoff.f_max)
+        b.runoff_set[] = true
+    end
+    set_field!(b.h, F_PRECIP, input)
+    check(ccall((:clb_update_runoff, libclb), Cint, (Ptr{Cvoid},), b.h.ptr))
+    get_field!(p.soil.is_saturated, b.h, F_IS_SATURATED); get_field!(p.soil.h∇, b.h, F_H_GRAD)
+    get_field!(p.soil.R_ss, b.h, F_R_SS); get_field!(p.soil.infiltration, b.h, F_INFILTRATION)
+    get_field!(p.soil.R_s, b.h, F_R_S)
+    b.energy && get_field!(p.soil.R_ess, b.h, F_R_ESS)
     return nothing
 end
 

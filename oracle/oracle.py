@@ -70,6 +70,14 @@ class _Aux(C.Structure):
                                    "total_energy")]
 
 
+class _RunoffParams(C.Structure):
+    _fields_ = [("f_max", _dp), ("f_over", C.c_double), ("R_sb", C.c_double), ("depth", C.c_double)]
+
+
+class _Runoff(C.Structure):
+    _fields_ = [(n, _dp) for n in ("is_saturated", "h_grad", "infiltration", "R_s", "R_ss", "R_ess")]
+
+
 # scalar parameters of the explicit stage: EnergyHydrologyParameters defaults pinned by the reference's
 # test/standalone/Soil/soil_parameterizations.jl:71-76; T_freeze / grav: ClimaParams 1.1.4 defaults
 EXPLICIT_SCALARS = dict(Omega=7.0, gamma=2.64e-2, gammaT_ref=288.0, alpha=0.24, beta=18.3, T_freeze=273.15,
@@ -95,7 +103,8 @@ def lib():
                             ("orc_volumetric_internal_energy_liq", 4), ("orc_heaviside", 2),
                             ("orc_impedance_factor", 2), ("orc_viscosity_factor", 3),
                             ("orc_kappa_sat", 4), ("orc_relative_saturation", 3), ("orc_kersten_number", 7),
-                            ("orc_thermal_conductivity", 3), ("orc_thermal_time", 3)]:
+                            ("orc_thermal_conductivity", 3), ("orc_thermal_time", 3),
+                            ("orc_topmodel_ss_flux", 3), ("orc_topmodel_surface_infiltration", 5)]:
             f = getattr(L, name)
             f.restype = d
             f.argtypes = [d] * nargs
@@ -109,6 +118,8 @@ def lib():
         L.orc_update_aux.restype = None
         L.orc_phase_change.argtypes = [pp, px, ps, pa, _dp, _dp]
         L.orc_phase_change.restype = None
+        L.orc_update_runoff.argtypes = [pp, px, C.POINTER(_RunoffParams), ps, pa, _dp, C.POINTER(_Runoff)]
+        L.orc_update_runoff.restype = None
         L.orc_update_implicit_cache.argtypes = [pp, ps, pc]
         L.orc_update_boundary_fluxes.argtypes = [pp, ps, pc]
         L.orc_compute_imp_tendency.argtypes = [pp, ps, pc, ps]
@@ -235,6 +246,19 @@ class Problem:
         P, x, y, aa = self.c_struct(), X.c_struct(), Y.c_struct(), a.c_struct()
         lib().orc_phase_change(C.byref(P), C.byref(x), C.byref(y), C.byref(aa), _ptr(dtheta_l), _ptr(dtheta_i))
 
+    def update_runoff(self, Y, precip, f_max, f_over, R_sb, depth, X=None, a=None):
+        """update_infiltration_water_flux!(p, ::TOPMODELRunoff, input, Y, t, model) -> Runoff bundle."""
+        out = Runoff(self)
+        fm = np.ascontiguousarray(np.broadcast_to(np.asarray(f_max, dtype=np.float64), (self.ncol,)))
+        pr = np.ascontiguousarray(np.broadcast_to(np.asarray(precip, dtype=np.float64), (self.ncol,)))
+        R = _RunoffParams(_ptr(fm), float(f_over), float(R_sb), float(depth))
+        P, y, o = self.c_struct(), Y.c_struct(), out.c_struct()
+        x = X.c_struct() if X is not None else None
+        aa = a.c_struct() if a is not None else None
+        lib().orc_update_runoff(C.byref(P), C.byref(x) if x is not None else None, C.byref(R), C.byref(y),
+                                C.byref(aa) if aa is not None else None, _ptr(pr), C.byref(o))
+        return out
+
     def column_integral(self, field):
         out = np.zeros(self.ncol)
         P = self.c_struct()
@@ -278,6 +302,10 @@ class Cache(_Bundle):
 class Aux(_Bundle):
     cell = ("theta_l", "kappa", "T", "K", "psi", "Tf_depressed")
     col, ctype = ("total_water", "total_energy"), _Aux
+
+
+class Runoff(_Bundle):
+    cell, col, ctype = ("is_saturated",), ("h_grad", "infiltration", "R_s", "R_ss", "R_ess"), _Runoff
 
 
 class ExplicitParams:

@@ -759,3 +759,57 @@ void orc_phase_change(const orc_problem *P, const orc_explicit_params *X, const 
         }
     }
 }
+
+/* ------------------------------------------------------------------ */
+/* TOPMODEL runoff (explicit stage): produces the lagged inputs of the */
+/* implicit TOPMODELSubsurfaceRunoff source (R_ss, R_ess, h_grad,      */
+/* is_saturated) and the infiltration / surface runoff                 */
+/* ------------------------------------------------------------------ */
+
+/* Runoff.jl:421-423 */
+double orc_topmodel_ss_flux(double R_sb, double f_over, double z_wt) { return R_sb * exp(-f_over * z_wt); }
+
+/* Runoff.jl:373-376 */
+double orc_topmodel_surface_infiltration(double f_max, double f_over, double z_wt, double f_ic, double precip)
+{
+    double f_sat = dmin(f_max * exp(-f_over / 2.0 * z_wt), 1.0);
+    return (1.0 - f_sat) * dmax(f_ic, precip);
+}
+
+/* Runoff.jl:234-283 (+ soil_infiltration_capacity :385-410, is_saturated :432-434,
+ * update_subsurface_energy_runoff! :266-279) */
+void orc_update_runoff(const orc_problem *P, const orc_explicit_params *X, const orc_runoff_params *R, const orc_state *Y,
+                       const orc_aux *a, const double *precip, orc_runoff *out)
+{
+    const int N = P->N;
+    const int eh = P->model == ORC_ENERGY_HYDROLOGY;
+    FOR_COLUMNS(P, c)
+    {
+        double h_all = 0.0, h_liq = 0.0, e_liq = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const int64_t k = c * N + i;
+            const double th = Y->theta_l[k], thi = eh ? Y->theta_i[k] : 0.0;
+            const double nu = P->nu[k], theta_r = P->theta_r[k];
+            /* weighted by how much above saturation, ice included (:251-253) */
+            const double s_all = orc_heaviside((th + thi - theta_r) - (nu - theta_r), 0.0) * (th + thi - theta_r) / (nu - theta_r);
+            /* liquid water only, for the subsurface runoff (:259-261) */
+            const double s_liq = orc_heaviside((th - theta_r) - (nu - theta_r), 0.0) * (th - theta_r) / (nu - theta_r);
+            out->is_saturated[k] = s_liq;
+            h_all += s_all * dz_cell(P, i);
+            h_liq += s_liq * dz_cell(P, i);
+            if (eh) e_liq += s_liq * orc_volumetric_internal_energy_liq(a->T[k], P->rho_l, P->cp_l, P->T_ref) * dz_cell(P, i);
+        }
+        /* infiltration capacity at the top centre (:385-410) */
+        const int64_t kt = c * N + N - 1;
+        double ic = -1 * P->K_sat[kt];
+        if (eh)
+            ic = -P->K_sat[kt] *
+                 orc_impedance_factor(Y->theta_i[kt] / (a->theta_l[kt] + Y->theta_i[kt] - P->theta_r[kt]), X->Omega) *
+                 orc_viscosity_factor(a->T[kt], X->gamma, X->gammaT_ref);
+        out->infiltration[c] = orc_topmodel_surface_infiltration(R->f_max[c], R->f_over, R->depth - h_all, ic, precip[c]);
+        out->R_s[c] = fabs(precip[c] - out->infiltration[c]);
+        out->h_grad[c] = h_liq;
+        out->R_ss[c] = orc_topmodel_ss_flux(R->R_sb, R->f_over, R->depth - h_liq);
+        if (eh && out->R_ess) out->R_ess[c] = e_liq * (out->R_ss[c] / dmax(h_liq, EPS64));
+    }
+}

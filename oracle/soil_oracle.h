@@ -145,6 +145,22 @@ void orc_update_aux(const orc_problem *P, const orc_explicit_params *X, const or
 void orc_phase_change(const orc_problem *P, const orc_explicit_params *X, const orc_state *Y, const orc_aux *a,
                       double *dtheta_l, double *dtheta_i);
 
+/* ---- TOPMODEL runoff of the explicit stage: Runoff/Runoff.jl:234-283, 373-451 */
+double orc_topmodel_ss_flux(double R_sb, double f_over, double z_wt);
+double orc_topmodel_surface_infiltration(double f_max, double f_over, double z_wt, double f_ic, double precip);
+typedef struct {
+    const double *f_max;      /* [ncol] */
+    double f_over, R_sb, depth;
+} orc_runoff_params;
+typedef struct {
+    double *is_saturated;                                   /* [ncol*N] (the liquid-water weighting, :259-260) */
+    double *h_grad, *infiltration, *R_s, *R_ss, *R_ess;     /* [ncol] */
+} orc_runoff;
+/* update_infiltration_water_flux!(p, ::TOPMODELRunoff, input, Y, t, model): Runoff.jl:234-283.  X and a (Omega,
+ * gamma, gammaT_ref; p.soil.theta_l, T) are read for EnergyHydrology only and may be NULL for RichardsModel. */
+void orc_update_runoff(const orc_problem *P, const orc_explicit_params *X, const orc_runoff_params *R, const orc_state *Y,
+                       const orc_aux *a, const double *precip, orc_runoff *out);
+
 /* ---- the hooks (each cites the reference in soil_oracle.c) */
 void orc_update_implicit_cache(const orc_problem *P, const orc_state *Y, orc_cache *p);
 /* explicit-stage flavour of the boundary-flux update: always evaluates (rre.jl:111-149) */

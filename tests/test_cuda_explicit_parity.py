@@ -154,3 +154,45 @@ def test_mirror_update_aux_and_phase_change_read_like_the_reference():
             else:
                 assert abs(want) <= 1.5e-8 * theta_l / tau
     soil.solver.close()
+
+
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["fast", "libm"])
+@pytest.mark.parametrize("model,layout", [("richards", 1), ("energy_hydrology", 1), ("energy_hydrology", 2)])
+def test_topmodel_runoff(model, layout, math_mode):
+    """update_infiltration_water_flux!(p, ::TOPMODELRunoff, ...) (Runoff/Runoff.jl:234-283) against the oracle;
+    its outputs are the lagged inputs of the implicit TOPMODEL source, left in place for the fused stage."""
+    import climaland_b200  # noqa: F401
+    from climaland_b200 import workloads
+    ncol, N, depth = 1500, 15, 50.0
+    w = workloads.make_workload(model, ncol, N=N, seed=21, topmodel=True)
+    rng = np.random.default_rng(2)
+    # saturate the lower part of a third of the columns so that h∇ > 0 there
+    sat = rng.random(ncol) < 0.35
+    w["y_theta_l"][sat, :5] = w["nu"][sat, :5] + 2e-3
+    precip = -rng.uniform(0.0, 2e-6, ncol)
+    f_max = rng.uniform(0.2, 0.6, ncol)
+    f_over, R_sb = 3.28, 1.484e-4 / 1000
+    P, Y, _ = oracle_problem(w, nthreads=4)
+    s = cuda_solver(w, math_mode=math_mode, layout=layout)
+    X = a = None
+    if model == "energy_hydrology":
+        xp = workloads.make_explicit_params(w, 21)
+        X = P.explicit_params(**xp)
+        a = P.new_aux()
+        P.update_aux(X, Y, a)
+        for k, v in xp.items():
+            s.set(k, v)
+        s.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+        s.update_aux()
+    out = P.update_runoff(Y, precip, f_max, f_over, R_sb, depth, X=X, a=a)
+    assert out.h_grad.max() > 0.0
+    s.set("f_max", f_max)
+    s.set("precip", precip)
+    s.set_runoff_params(f_over=f_over, R_sb=R_sb, depth=depth)
+    s.update_runoff()
+    assert_close(s.get("is_saturated"), out.is_saturated, TOL, "is_saturated")
+    for dev, name in (("h_grad", "h_grad"), ("r_ss", "R_ss"), ("infiltration", "infiltration"), ("r_s", "R_s")):
+        assert_close(s.get(dev), getattr(out, name), TOL, name)
+    if model == "energy_hydrology":
+        assert_close(s.get("r_ess"), out.R_ess, TOL, "R_ess")
+    s.close()

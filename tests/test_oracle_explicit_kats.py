@@ -147,3 +147,77 @@ def test_phase_change_conserves_water_mass():
     frozen = (a.T < a.Tf_depressed - 1.0) & (Y.theta_i == 0.0)
     if frozen.any():
         assert np.all(sl[frozen] <= 0.0)
+
+
+# ----------------------------------------------------------------------------
+# TOPMODEL runoff: test/standalone/Soil/runoff.jl
+# ----------------------------------------------------------------------------
+def _runoff_setup(model, ncol=7, N=15):
+    """the reference test's configuration (runoff.jl:91-176): depth 50 m, theta_l = 0.6 - 0.3/50 (z + 50),
+    nu = 0.5, theta_r = 0, K_sat = 1e-6, alpha = 0.2, n = 2.2, f_max = 0.5, f_over = 3.28, R_sb = 1.484e-7"""
+    import climaland_b200  # noqa: F401
+    from climaland_b200 import workloads
+    z_f, z_c = workloads.stretched_grid(N, depth=50.0, dz_top=0.05)
+    lat = np.linspace(-80.0, 80.0, ncol)
+    precip = -1e-6 + 5e-7 * np.sin(lat / (90.0 * 2 * np.pi))
+    fields = dict(nu=0.5, theta_r=0.0, K_sat=1e-6, S_s=1e-3, hcm_a=0.2, hcm_b=2.2, hcm_m=1 - 1 / 2.2)
+    if model == orc.ENERGY_HYDROLOGY:
+        fields["rho_c_ds"] = 2e6 * 0.5
+    P = orc.Problem(model=model, z_f=z_f, z_c=z_c, ncol=ncol, **fields)
+    Y = P.new_state()
+    Y.theta_l[...] = 0.6 - 0.3 / 50.0 * (z_c + 50.0)
+    return P, Y, z_f, z_c, precip
+
+
+def test_topmodel_runoff_richards():
+    """runoff.jl:177-214: h∇ is the column integral of heaviside(theta_l - nu) (theta_l - theta_r)/(nu - theta_r),
+    R_ss = topmodel_ss_flux(R_sb, f_over, depth - h∇), the infiltration capacity is -K_sat, infiltration =
+    topmodel_surface_infiltration(...), R_s = |precip - infiltration|"""
+    P, Y, z_f, z_c, precip = _runoff_setup(orc.RICHARDS)
+    f_max, f_over, R_sb, depth = 0.5, 3.28, 1.484e-4 / 1000, 50.0
+    out = P.update_runoff(Y, precip, f_max, f_over, R_sb, depth)
+    dz = np.diff(z_f)
+    w = np.where(Y.theta_l - 0.5 > EPS, 1.0, 0.0) * (Y.theta_l - 0.0) / (0.5 - 0.0)
+    h = (w * dz).sum(axis=1)
+    assert np.allclose(out.h_grad, h, rtol=1e-15) and np.all(h > 0) and np.all(h < depth)
+    assert np.array_equal(out.is_saturated, w)
+    assert np.array_equal(out.R_ss, [L.orc_topmodel_ss_flux(R_sb, f_over, depth - x) for x in out.h_grad])
+    assert np.allclose(out.R_ss, R_sb * np.exp(-f_over * (depth - out.h_grad)), rtol=1e-15)
+    inf = [L.orc_topmodel_surface_infiltration(f_max, f_over, depth - x, -1e-6, pr) for x, pr in zip(out.h_grad, precip)]
+    assert np.array_equal(out.infiltration, inf)
+    f_sat = np.minimum(f_max * np.exp(-f_over / 2 * (depth - out.h_grad)), 1.0)
+    assert np.allclose(out.infiltration, (1 - f_sat) * np.maximum(-1e-6, precip), rtol=1e-15)
+    assert np.array_equal(out.R_s, np.abs(precip - out.infiltration))
+
+
+def test_topmodel_runoff_energy_hydrology():
+    """runoff.jl:216-300: with ice the surface-runoff saturation counts theta_l + theta_i, the subsurface one
+    only theta_l; the infiltration capacity is -K_sat * impedance * viscosity at the top cell; R_ess is the
+    saturated layers' liquid energy integral times R_ss / max(h∇, eps)."""
+    P, Y, z_f, z_c, precip = _runoff_setup(orc.ENERGY_HYDROLOGY)
+    ncol, N = Y.theta_l.shape
+    Y.theta_i[...] = 0.06                            # ice pushes more levels above saturation, for R_s only
+    xp = dict(kappa_dry=1.0, kappa_sat_unfrozen=1.5, kappa_sat_frozen=2.5, nu_ss_om=0.1, nu_ss_quartz=0.2, nu_ss_gravel=0.1)
+    Xp = P.explicit_params(**xp)
+    rc = 1e6 + np.minimum(0.5 - Y.theta_i, Y.theta_l) * E["rho_l"] * E["cp_l"] + Y.theta_i * E["rho_i"] * E["cp_i"]
+    T = 270.0 + 10.0 * np.linspace(0, 1, N)[None, :] * np.ones((ncol, 1))
+    Y.rho_e_int[...] = rc * (T - E["T_ref"]) - Y.theta_i * E["rho_i"] * E["LH_f0"]
+    a = P.new_aux()
+    P.update_aux(Xp, Y, a)
+    f_max, f_over, R_sb, depth = 0.5, 3.28, 1.484e-4 / 1000, 50.0
+    out = P.update_runoff(Y, precip, f_max, f_over, R_sb, depth, X=Xp, a=a)
+    dz = np.diff(z_f)
+    w_liq = np.where((Y.theta_l - 0.0) - 0.5 > EPS, 1.0, 0.0) * Y.theta_l / 0.5
+    w_all = np.where((Y.theta_l + Y.theta_i) - 0.5 > EPS, 1.0, 0.0) * (Y.theta_l + Y.theta_i) / 0.5
+    assert np.array_equal(out.is_saturated, w_liq)
+    h_liq, h_all = (w_liq * dz).sum(axis=1), (w_all * dz).sum(axis=1)
+    assert np.all(h_all > h_liq)
+    assert np.allclose(out.h_grad, h_liq, rtol=1e-15)
+    top = N - 1
+    ic = np.array([-1e-6 * L.orc_impedance_factor(Y.theta_i[c, top] / (a.theta_l[c, top] + Y.theta_i[c, top] - 0.0), X["Omega"])
+                   * L.orc_viscosity_factor(a.T[c, top], X["gamma"], X["gammaT_ref"]) for c in range(ncol)])
+    f_sat = np.minimum(f_max * np.exp(-f_over / 2 * (depth - h_all)), 1.0)
+    assert np.allclose(out.infiltration, (1 - f_sat) * np.maximum(ic, precip), rtol=1e-14)
+    assert np.array_equal(out.R_s, np.abs(precip - out.infiltration))
+    e_l = E["rho_l"] * E["cp_l"] * (a.T - E["T_ref"])
+    assert np.allclose(out.R_ess, (w_liq * e_l * dz).sum(axis=1) * out.R_ss / np.maximum(h_liq, EPS), rtol=1e-13)
