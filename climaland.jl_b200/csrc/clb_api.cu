@@ -505,7 +505,10 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, 
 {
     constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 11;
     if constexpr (PIPELINED)
-        return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 2, 256, 1, true>(h, P, dtg, max_iters, col0);
+#ifndef CLB_QUAD_BLOCK
+#define CLB_QUAD_BLOCK 256  // 8 warps per SM; 128 = one warp per sub-partition (latency experiment)
+#endif
+        return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 2, CLB_QUAD_BLOCK, 1, true>(h, P, dtg, max_iters, col0);
     else
         return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 1, 128, CLB_QUAD_MINB, false>(h, P, dtg, max_iters, col0);
 }

@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!has_tile) return;  // whole warp
     request_tile(warp0, 0, 2);
+    if (NBUF == 2 && warp0 + nwarps < ntiles) request_tile(warp0 + nwarps, 1, 3);  // untouched buffer: no proxy fence needed
     ColScalars nxt = load_col_scalars<MODEL>(P, col_clamped(warp0));
 
     double dx2_acc = 0.0, bad = 0.0;
@@ -400,16 +401,6 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 a_ = (j_ == 8) ? P.Y_intF_e : a_;
                 prefetch_l2(a_ + tn * CPW);
             }
-        }
-    }
-    if (NBUF == 2) {
-        const int64_t tn = tile_id + nwarps;
-        if (tn < ntiles) {
-            // the other buffer held the previous tile's constants (generic-proxy accesses): order them
-            // before the async-proxy writes of the TMA
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            request_tile(tn, buf ^ 1, 3);
-            nxt = load_col_scalars<MODEL>(P, col_clamped(tn));
         }
     }
     S.base = reinterpret_cast<double *>(tiles + buf * kTileBytes) + (lane % CPW);
@@ -581,6 +572,15 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             }
         }
         r22 = fm::rcp(fma(-c22_last, xchg<Gm::SEAM>(c22_last), 1.0));
+    }
+
+    // The next tile's per-column scalars are fetched only now, after everything that consumes this tile's has
+    // been issued: fetched at the top of the tile, their loads shared a scoreboard with `cur` and the first use of
+    // `cur` waited for them (a full HBM latency per tile); here they have the whole Newton loop to land.  (The
+    // next tile's boxes were requested when the tile before this one finished its Newton loop, below.)
+    if (NBUF == 2) {
+        const int64_t tn = tile_id + nwarps;
+        if (tn < ntiles) nxt = load_col_scalars<MODEL>(P, col_clamped(tn));
     }
 
     // ---- Newton iterations -----------------------------------------------------------------
@@ -818,6 +818,20 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         }
     }
 
+    // ---- this tile's constants are dead: hand its buffer to the TMA ------------------------------------
+    // BEFORE the global stores below: fence.proxy.async carries a MEMBAR.ALL.CTA, which would otherwise wait
+    // for those stores to be acknowledged (~900 cycles per tile when the request sat at the top of the loop).
+    {
+        const int64_t tr = tile_id + NBUF * nwarps;  // double-buffered: the tile after next lands in this buffer
+        if (tr < ntiles) {
+            __syncwarp();
+            // generic-proxy accesses of this buffer are ordered before the async-proxy writes of the TMA
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            request_tile(tr, buf, 3);
+            if (NBUF == 1) nxt = load_col_scalars<MODEL>(P, col_clamped(tr));
+        }
+    }
+
     // ---- write the new state -----------------------------------------------------------------
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -835,11 +849,6 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     if (col_ok) dx2_acc += dx2 + dx2_int;
     if (NBUF == 2) buf ^= 1;
     else __syncwarp();
-    if (NBUF == 1 && tile_id + nwarps < ntiles) {  // single buffer: the next tile is requested only now
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        request_tile(tile_id + nwarps, 0, 3);
-        nxt = load_col_scalars<MODEL>(P, col_clamped(tile_id + nwarps));
-    }
     }  // tiles
     if (P.stats) accumulate_stats(P, dx2_acc, bad);  // only when the caller asked for clb_stats
 }
