@@ -99,6 +99,8 @@ def lib():
         "clb_compute_imp_tendency": [h], "clb_compute_jacobian": [h, d], "clb_ldiv": [h],
         "clb_set_explicit_params": [h, C.POINTER(ExplicitParams)],
         "clb_set_runoff_params": [h, C.POINTER(RunoffParams)], "clb_update_runoff": [h],
+        "clb_soilco2_update_boundary_fluxes": [h], "clb_soilco2_compute_imp_tendency": [h],
+        "clb_soilco2_compute_jacobian": [h, d], "clb_soilco2_implicit_step": [h, d, i32],
         "clb_update_aux": [h], "clb_phase_change_source": [h], "clb_update_aux_and_phase_change": [h],
         "clb_implicit_step": [h, d, i32, d, C.POINTER(Stats)],
         "clb_implicit_step_host": [h, d, i32, C.POINTER(i32), C.POINTER(C.c_void_p), i32,

@@ -22,6 +22,7 @@
 #include "soil_warp.cuh"
 #include "soil_pair.cuh"
 #include "soil_explicit.cuh"
+#include "soil_co2.cuh"
 
 namespace {
 
@@ -150,6 +151,7 @@ struct clb_handle_s {
     bool explicit_set = false;
     clb_runoff_params runoff_k = {};
     bool runoff_set = false;
+    bool co2_top_state[2] = {false, false};  // SoilCO2Model: AtmosCO2StateBC / AtmosO2StateBC at the top
     // multi-GPU
     NcclComm comm = nullptr;
     int32_t n_ranks = 1, rank = 0;
@@ -901,6 +903,61 @@ int step_host_pipelined(clb_handle h, double dtgamma, int32_t max_iters, const i
 
 }  // namespace
 
+// ---- SoilCO2Model implicit diffusion (soil_co2.cuh) ----------------------------------------------------
+namespace {
+
+// mode: 0 boundary fluxes, 1 tendency, 2 Jacobian, 3 fused stage
+int co2_launch(clb_handle h, int mode, double dtg, int max_iters, const char *who)
+{
+    TRY(check_handle(h));
+    DeviceGuard guard(h->cfg.device);
+    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
+    if (h->cfg.n_levels > clb::kCo2MaxLevels)
+        return fail(CLB_ERR_INVALID, "%s: at most %d levels", who, clb::kCo2MaxLevels);
+    static const int Y[2] = {CLB_F_CO2_Y, CLB_F_O2_Y}, D[2] = {CLB_F_CO2_D, CLB_F_O2_D};
+    static const int TH[2] = {CLB_F_CO2_THETA_EFF, CLB_F_O2_THETA_EFF}, DY[2] = {CLB_F_CO2_DY, CLB_F_O2_DY};
+    static const int TOP[2] = {CLB_F_CO2_TOP_BC, CLB_F_O2_TOP_BC}, BOT[2] = {CLB_F_CO2_BOT_BC, CLB_F_O2_BOT_BC};
+    static const int ATM[2] = {CLB_F_CO2_C_ATM, CLB_F_O2_C_ATM}, DFL[2] = {CLB_F_CO2_DFLUXBCDY, CLB_F_O2_DFLUXBCDY};
+    static const int LO[2] = {CLB_F_CO2_W_LO, CLB_F_O2_W_LO}, DI[2] = {CLB_F_CO2_W_DI, CLB_F_O2_W_DI};
+    static const int UP[2] = {CLB_F_CO2_W_UP, CLB_F_O2_W_UP};
+    clb::Co2View V;
+    for (int k = 0; k < 2; ++k) {
+        TRY(require(h, {Y[k], D[k], TH[k]}, who));
+        TRY(alloc_fields(h, {TOP[k], BOT[k]}));  // flux values default to zero
+        if (h->co2_top_state[k]) {
+            TRY(require(h, {ATM[k]}, who));
+            TRY(alloc_fields(h, {DFL[k]}));
+            if (mode == 2 && !h->field_set[DFL[k]]) return fail(CLB_ERR_UNSET, "%s: call clb_soilco2_update_boundary_fluxes first", who);
+        }
+        if (mode == 1) TRY(alloc_fields(h, {DY[k]}));
+        if (mode == 2) TRY(alloc_fields(h, {LO[k], DI[k], UP[k]}));
+        double *const *F = h->field;
+        clb::Co2Species &S = V.s[k];
+        S.C = F[Y[k]]; S.D = F[D[k]]; S.theta_eff = F[TH[k]];
+        S.top_bc = F[TOP[k]]; S.bot_bc = F[BOT[k]];
+        S.c_atm = h->co2_top_state[k] ? F[ATM[k]] : nullptr;
+        S.dflux = F[DFL[k]]; S.dC = F[DY[k]];
+        S.lo = F[LO[k]]; S.di = F[DI[k]]; S.up = F[UP[k]];
+    }
+    const clb::DevView P = make_view(h);
+    const dim3 grid(grid_for(P.ncol), 2);
+    nvtxRangePushA(who);
+    switch (mode) {
+    case 0: clb::k_co2<0, 0><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters); break;
+    case 1: clb::k_co2<1, 0><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters); break;
+    case 2: clb::k_co2<2, 0><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters); break;
+    default:
+        if (P.N == 15) clb::k_co2<3, 15><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters);  // column in registers
+        else clb::k_co2<3, 0><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters);
+        break;
+    }
+    nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int clb_test_math(int32_t kind, const double *x, const double *y, double *out, int64_t n)
@@ -1053,6 +1110,12 @@ int clb_set_option(clb_handle h, int32_t option, int64_t value)
     switch (option) {
     case CLB_OPT_OUT_OF_PLACE:
         h->out_of_place = value != 0;
+        return CLB_OK;
+    case CLB_OPT_CO2_TOP_STATE:
+        h->co2_top_state[0] = value != 0;
+        return CLB_OK;
+    case CLB_OPT_O2_TOP_STATE:
+        h->co2_top_state[1] = value != 0;
         return CLB_OK;
     default:
         return fail(CLB_ERR_INVALID, "clb_set_option: unknown option %d", option);
@@ -1264,6 +1327,15 @@ int clb_set_explicit_params(clb_handle h, const clb_explicit_params *p)
     h->explicit_k = {p->Omega, p->gamma, p->gammaT_ref, p->alpha, p->beta, p->T_freeze, p->grav};
     h->explicit_set = true;
     return CLB_OK;
+}
+
+int clb_soilco2_update_boundary_fluxes(clb_handle h) { return co2_launch(h, 0, 0.0, 0, "soilco2 update_boundary_fluxes!"); }
+int clb_soilco2_compute_imp_tendency(clb_handle h) { return co2_launch(h, 1, 0.0, 0, "soilco2 compute_imp_tendency!"); }
+int clb_soilco2_compute_jacobian(clb_handle h, double dtgamma) { return co2_launch(h, 2, dtgamma, 0, "soilco2 compute_jacobian!"); }
+int clb_soilco2_implicit_step(clb_handle h, double dtgamma, int32_t max_iters)
+{
+    if (max_iters < 1) return fail(CLB_ERR_INVALID, "clb_soilco2_implicit_step: max_iters must be >= 1");
+    return co2_launch(h, 3, dtgamma, max_iters, "soilco2 implicit_step!");
 }
 
 int clb_set_runoff_params(clb_handle h, const clb_runoff_params *p)

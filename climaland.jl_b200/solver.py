@@ -154,6 +154,24 @@ class SoilColumnSolver:
         p = ExplicitParams(Omega, gamma, gammaT_ref, alpha, beta, T_freeze, grav)
         check(self.L.clb_set_explicit_params(self.h, C.byref(p)))
 
+    # ---- SoilCO2Model implicit diffusion ---------------------
+    def set_co2_top_state(self, co2=False, o2=False):
+        """AtmosCO2StateBC / AtmosO2StateBC at the top (values co2_c_atm / o2_c_atm) instead of flux values."""
+        check(self.L.clb_set_option(self.h, K["CLB_OPT_CO2_TOP_STATE"], int(co2)))
+        check(self.L.clb_set_option(self.h, K["CLB_OPT_O2_TOP_STATE"], int(o2)))
+
+    def soilco2_update_boundary_fluxes(self):
+        check(self.L.clb_soilco2_update_boundary_fluxes(self.h))
+
+    def soilco2_compute_imp_tendency(self):
+        check(self.L.clb_soilco2_compute_imp_tendency(self.h))
+
+    def soilco2_compute_jacobian(self, dtgamma):
+        check(self.L.clb_soilco2_compute_jacobian(self.h, float(dtgamma)))
+
+    def soilco2_implicit_step(self, dtgamma, max_iters):
+        check(self.L.clb_soilco2_implicit_step(self.h, float(dtgamma), int(max_iters)))
+
     def set_runoff_params(self, *, f_over, R_sb, depth):
         """TOPMODELRunoff scalars (Runoff/Runoff.jl:190-222) and the domain depth."""
         p = RunoffParams(f_over, R_sb, depth)

@@ -47,7 +47,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define CLB_ABI_VERSION 2
+#define CLB_ABI_VERSION 3
 
 typedef struct clb_handle_s *clb_handle;
 
@@ -92,7 +92,9 @@ enum { CLB_LAYOUT_AUTO = 0,
        CLB_LAYOUT_COLUMN_FASTEST = 1,   /* element (i, c) at i*ld + c                              */
        CLB_LAYOUT_LEVEL_FASTEST = 2     /* element (i, c) at c*N + i: the reference's own layout    */ };
 /* clb_set_option */
-enum { CLB_OPT_OUT_OF_PLACE = 1 };      /* fused stage reads Y (= temp) and writes the U fields */
+enum { CLB_OPT_OUT_OF_PLACE = 1,        /* fused stage reads Y (= temp) and writes the U fields */
+       CLB_OPT_CO2_TOP_STATE = 2,       /* SoilCO2Model: the top BC of CO2 is AtmosCO2StateBC (value CLB_F_CO2_C_ATM) */
+       CLB_OPT_O2_TOP_STATE = 3 };      /* ... of O2 is AtmosO2StateBC (value CLB_F_O2_C_ATM); 0 = flux values */
 
 /* Field ids.  "cell" fields are N x ncol, "col" fields are ncol. */
 typedef enum {
@@ -127,6 +129,13 @@ typedef enum {
     CLB_F_NU_SS_OM, CLB_F_NU_SS_QUARTZ, CLB_F_NU_SS_GRAVEL,
     CLB_F_P_TF_DEPRESSED,                    /* p.soil.Tf_depressed */
     CLB_F_DYE_THETA_L, CLB_F_DYE_THETA_I,    /* explicit tendency the PhaseChange source adds into */
+    /* ---- SoilCO2Model implicit diffusion (Biogeochemistry.jl:320-413, 1119-1195) -- cell */
+    CLB_F_CO2_Y, CLB_F_O2_Y,                 /* Y.soilco2.{CO2, O2} */
+    CLB_F_CO2_D, CLB_F_O2_D,                 /* lagged p.soilco2.{D, D_o2} */
+    CLB_F_CO2_THETA_EFF, CLB_F_O2_THETA_EFF, /* lagged p.soilco2.{theta_eff, theta_eff_o2} */
+    CLB_F_CO2_DY, CLB_F_O2_DY,               /* implicit tendency */
+    CLB_F_CO2_W_LO, CLB_F_CO2_W_DI, CLB_F_CO2_W_UP,   /* (CO2, CO2) Jacobian rows */
+    CLB_F_O2_W_LO, CLB_F_O2_W_DI, CLB_F_O2_W_UP,      /* (O2, O2) Jacobian rows  */
     CLB_F_NUM_CELL,
     /* ---- per-column fields */
     CLB_F_R_SS = CLB_F_NUM_CELL, CLB_F_R_ESS, CLB_F_H_GRAD,     /* lagged TOPMODEL */
@@ -141,6 +150,9 @@ typedef enum {
     CLB_F_TOTAL_ENERGY,                       /* p.soil.total_energy (explicit update_aux!) */
     CLB_F_F_MAX, CLB_F_PRECIP,                /* TOPMODELRunoff.f_max; the liquid water input (precipitation + melt, m/s, negative down) */
     CLB_F_INFILTRATION, CLB_F_R_S,            /* p.soil.infiltration, p.soil.R_s (clb_update_runoff) */
+    CLB_F_CO2_TOP_BC, CLB_F_CO2_BOT_BC, CLB_F_O2_TOP_BC, CLB_F_O2_BOT_BC,   /* p.soilco2.{top,bottom}_bc(_o2) */
+    CLB_F_CO2_C_ATM, CLB_F_O2_C_ATM,          /* air-equivalent concentration of the atmosphere (state BC value) */
+    CLB_F_CO2_DFLUXBCDY, CLB_F_O2_DFLUXBCDY,  /* p.soilco2.dfluxBCdY(_o2) */
     CLB_F_NUM
 } clb_field;
 
@@ -260,6 +272,22 @@ typedef struct {
 } clb_runoff_params;
 int clb_set_runoff_params(clb_handle h, const clb_runoff_params *p);
 int clb_update_runoff(clb_handle h);
+
+/* ---- SoilCO2Model: implicit CO2 / O2 diffusion ---------- */
+/* Two more independent per-column tridiagonals with lagged coefficients, on the same columns and grid as the
+ * soil handle (src/standalone/Soil/Biogeochemistry/Biogeochemistry.jl).  With CLB_OPT_*_TOP_STATE the top
+ * boundary flux is diffusive_flux(D_N, c_atm, max(C_N / theta_N, 0), dz_top) (:932-957, :1078-1111) and its
+ * derivative enters the Jacobian (:1152-1166); otherwise CLB_F_*_TOP_BC holds a flux value.
+ *   clb_soilco2_update_boundary_fluxes   make_update_implicit_boundary_fluxes, :320-357
+ *   clb_soilco2_compute_imp_tendency     make_compute_imp_tendency, :371-413      -> CLB_F_{CO2,O2}_DY
+ *   clb_soilco2_compute_jacobian         make_compute_jacobian, :1119-1195        -> CLB_F_{CO2,O2}_W_*
+ *   clb_soilco2_implicit_step            the ARS111 stage (Simulations.jl:127-135): max_iters x (boundary
+ *                                        fluxes, Jacobian, tendency, residual, Thomas, update) in one kernel,
+ *                                        on CLB_F_{CO2,O2}_Y in place (SOC has no implicit piece, :411) */
+int clb_soilco2_update_boundary_fluxes(clb_handle h);
+int clb_soilco2_compute_imp_tendency(clb_handle h);
+int clb_soilco2_compute_jacobian(clb_handle h, double dtgamma);
+int clb_soilco2_implicit_step(clb_handle h, double dtgamma, int32_t max_iters);
 
 /* ---- the fused implicit stage -------------------------------------------- */
 /* One implicit ARS111 stage on the resident state Y (in: U = temp, out: new U):

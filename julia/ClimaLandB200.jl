@@ -32,7 +32,7 @@ import CUDA
 const libclb = get(ENV, "CLIMALAND_B200_LIB", "libclimaland_b200.so")
 
 # ---- enums of include/climaland_b200.h ------------------------------------------------------
-const CLB_ABI_VERSION = Int32(2)
+const CLB_ABI_VERSION = Int32(3)
 const CLB_RICHARDS, CLB_ENERGY_HYDROLOGY = Int32(0), Int32(1)
 const CLB_VAN_GENUCHTEN, CLB_BROOKS_COREY = Int32(0), Int32(1)
 const CLB_TOP_FLUX, CLB_TOP_MOISTURE_STATE = Int32(0), Int32(1)
@@ -51,11 +51,14 @@ const CLB_HOST, CLB_DEVICE = Int32(0), Int32(1)
     F_U_THETA_L; F_U_RHO_E_INT
     F_KAPPA_DRY; F_KAPPA_SAT_UNFROZEN; F_KAPPA_SAT_FROZEN; F_NU_SS_OM; F_NU_SS_QUARTZ; F_NU_SS_GRAVEL
     F_P_TF_DEPRESSED; F_DYE_THETA_L; F_DYE_THETA_I
+    F_CO2_Y; F_O2_Y; F_CO2_D; F_O2_D; F_CO2_THETA_EFF; F_O2_THETA_EFF; F_CO2_DY; F_O2_DY
+    F_CO2_W_LO; F_CO2_W_DI; F_CO2_W_UP; F_O2_W_LO; F_O2_W_DI; F_O2_W_UP
     F_R_SS; F_R_ESS; F_H_GRAD; F_THETA_BC_TOP; F_THETA_BC_BOT
     F_TOP_BC_W; F_BOT_BC_W; F_TOP_BC_H; F_BOT_BC_H; F_DFLUXBCDY; F_TOTAL_WATER
     F_Y_INTF_W; F_Y_INTF_E; F_DY_INTF_W; F_DY_INTF_E; F_B_INTF_W; F_B_INTF_E; F_X_INTF_W; F_X_INTF_E
     F_AREA_WEIGHT; F_U_INTF_W; F_U_INTF_E; F_TOTAL_ENERGY
     F_F_MAX; F_PRECIP; F_INFILTRATION; F_R_S
+    F_CO2_TOP_BC; F_CO2_BOT_BC; F_O2_TOP_BC; F_O2_BOT_BC; F_CO2_C_ATM; F_O2_C_ATM; F_CO2_DFLUXBCDY; F_O2_DFLUXBCDY
 end
 
 # struct clb_config (same field order and widths as the header)
@@ -340,6 +343,28 @@ function update_infiltration_water_flux!(p, runoff::Soil.Runoff.TOPMODELRunoff, 
     get_field!(p.soil.R_ss, b.h, F_R_SS); get_field!(p.soil.infiltration, b.h, F_INFILTRATION)
     get_field!(p.soil.R_s, b.h, F_R_S)
     b.energy && get_field!(p.soil.R_ess, b.h, F_R_ESS)
+    return nothing
+end
+
+"""
+The implicit stage of SoilCO2Model (src/standalone/Soil/Biogeochemistry/Biogeochemistry.jl:320-413, 1119-1195)
+as one call: uploads Y.soilco2.{CO2, O2} and the lagged p.soilco2.{D, D_o2, θ_eff, θ_eff_o2}, boundary values,
+runs max_iters Newton iterations of both tridiagonals in one kernel, downloads the new CO2 / O2.
+`c_atm_co2`, `c_atm_o2`: surface fields of the atmosphere's air-equivalent concentrations
+(`p.drivers.c_co2 * P * M_C / (R * T)`, `O2_f_atm * P * M_O2 / (R * T)`) when the top BCs are the Atmos*StateBC.
+"""
+function soilco2_implicit_step!(Y, p, b::B200Soil, dtγ; max_iters = 3, c_atm_co2 = nothing, c_atm_o2 = nothing)
+    set_field!(b.h, F_CO2_Y, Y.soilco2.CO2); set_field!(b.h, F_O2_Y, Y.soilco2.O2)
+    set_field!(b.h, F_CO2_D, p.soilco2.D); set_field!(b.h, F_O2_D, p.soilco2.D_o2)
+    set_field!(b.h, F_CO2_THETA_EFF, p.soilco2.θ_eff); set_field!(b.h, F_O2_THETA_EFF, p.soilco2.θ_eff_o2)
+    set_field!(b.h, F_CO2_BOT_BC, p.soilco2.bottom_bc); set_field!(b.h, F_O2_BOT_BC, p.soilco2.bottom_bc_o2)
+    for (opt, c, idc, idf, f) in ((Int32(2), c_atm_co2, F_CO2_C_ATM, F_CO2_TOP_BC, p.soilco2.top_bc),
+                                  (Int32(3), c_atm_o2, F_O2_C_ATM, F_O2_TOP_BC, p.soilco2.top_bc_o2))
+        check(ccall((:clb_set_option, libclb), Cint, (Ptr{Cvoid}, Int32, Int64), b.h.ptr, opt, c === nothing ? 0 : 1))
+        c === nothing ? set_field!(b.h, idf, f) : set_field!(b.h, idc, c)
+    end
+    check(ccall((:clb_soilco2_implicit_step, libclb), Cint, (Ptr{Cvoid}, Float64, Int32), b.h.ptr, float(dtγ), Int32(max_iters)))
+    get_field!(Y.soilco2.CO2, b.h, F_CO2_Y); get_field!(Y.soilco2.O2, b.h, F_O2_Y)
     return nothing
 end
 

@@ -70,6 +70,10 @@ class _Aux(C.Structure):
                                    "total_energy")]
 
 
+class _CO2Species(C.Structure):
+    _fields_ = [("D", _dp), ("theta_eff", _dp), ("c_atm", _dp)]
+
+
 class _RunoffParams(C.Structure):
     _fields_ = [("f_max", _dp), ("f_over", C.c_double), ("R_sb", C.c_double), ("depth", C.c_double)]
 
@@ -120,6 +124,14 @@ def lib():
         L.orc_phase_change.restype = None
         L.orc_update_runoff.argtypes = [pp, px, C.POINTER(_RunoffParams), ps, pa, _dp, C.POINTER(_Runoff)]
         L.orc_update_runoff.restype = None
+        pcs = C.POINTER(_CO2Species)
+        L.orc_co2_boundary_flux.argtypes = [pp, pcs, _dp, _dp, _dp]
+        L.orc_co2_imp_tendency.argtypes = [pp, pcs, _dp, _dp, _dp, _dp]
+        L.orc_co2_jacobian.argtypes = [pp, pcs, d, _dp, _dp, _dp, _dp]
+        L.orc_co2_implicit_step.argtypes = [pp, pcs, _dp, _dp, _dp, d, C.c_int]
+        L.orc_co2_implicit_step.restype = C.c_int
+        for n in ("orc_co2_boundary_flux", "orc_co2_imp_tendency", "orc_co2_jacobian"):
+            getattr(L, n).restype = None
         L.orc_update_implicit_cache.argtypes = [pp, ps, pc]
         L.orc_update_boundary_fluxes.argtypes = [pp, ps, pc]
         L.orc_compute_imp_tendency.argtypes = [pp, ps, pc, ps]
@@ -259,6 +271,32 @@ class Problem:
                                 C.byref(aa) if aa is not None else None, _ptr(pr), C.byref(o))
         return out
 
+    # ---- SoilCO2Model implicit diffusion -----------------------------------
+    def co2_species(self, D, theta_eff, c_atm=None):
+        return CO2Species(self, D, theta_eff, c_atm)
+
+    def co2_boundary_flux(self, S, Cc, top_bc, dflux):
+        P, s = self.c_struct(), S.c_struct()
+        lib().orc_co2_boundary_flux(C.byref(P), C.byref(s), _ptr(Cc), _ptr(top_bc), _ptr(dflux))
+
+    def co2_imp_tendency(self, S, Cc, top_bc, bot_bc):
+        out = np.zeros_like(Cc)
+        P, s = self.c_struct(), S.c_struct()
+        lib().orc_co2_imp_tendency(C.byref(P), C.byref(s), _ptr(Cc), _ptr(top_bc), _ptr(bot_bc), _ptr(out))
+        return out
+
+    def co2_jacobian(self, S, dtgamma, dflux=None):
+        lo, di, up = (np.zeros((self.ncol, self.N)) for _ in range(3))
+        P, s = self.c_struct(), S.c_struct()
+        lib().orc_co2_jacobian(C.byref(P), C.byref(s), float(dtgamma), _ptr(dflux), _ptr(lo), _ptr(di), _ptr(up))
+        return lo, di, up
+
+    def co2_implicit_step(self, S, Cc, top_bc, bot_bc, dtgamma, max_iters):
+        """advances Cc (and, for a state BC, top_bc) in place"""
+        P, s = self.c_struct(), S.c_struct()
+        return lib().orc_co2_implicit_step(C.byref(P), C.byref(s), _ptr(Cc), _ptr(top_bc), _ptr(bot_bc),
+                                           float(dtgamma), int(max_iters))
+
     def column_integral(self, field):
         out = np.zeros(self.ncol)
         P = self.c_struct()
@@ -302,6 +340,20 @@ class Cache(_Bundle):
 class Aux(_Bundle):
     cell = ("theta_l", "kappa", "T", "K", "psi", "Tf_depressed")
     col, ctype = ("total_water", "total_energy"), _Aux
+
+
+class CO2Species:
+    def __init__(self, prob, D, theta_eff, c_atm=None):
+        self.D, self.theta_eff = np.empty((prob.ncol, prob.N)), np.empty((prob.ncol, prob.N))
+        self.D[...] = D
+        self.theta_eff[...] = theta_eff
+        self.c_atm = None
+        if c_atm is not None:
+            self.c_atm = np.empty(prob.ncol)
+            self.c_atm[...] = c_atm
+
+    def c_struct(self):
+        return _CO2Species(_ptr(self.D), _ptr(self.theta_eff), _ptr(self.c_atm))
 
 
 class Runoff(_Bundle):

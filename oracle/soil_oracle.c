@@ -813,3 +813,92 @@ void orc_update_runoff(const orc_problem *P, const orc_explicit_params *X, const
         if (eh && out->R_ess) out->R_ess[c] = e_liq * (out->R_ss[c] / dmax(h_liq, EPS64));
     }
 }
+
+/* ------------------------------------------------------------------ */
+/* SoilCO2Model: implicit CO2 / O2 diffusion        */
+/* ------------------------------------------------------------------ */
+
+/* boundary_flux!(..., ::AtmosCO2StateBC / ::AtmosO2StateBC, ::TopBoundary, ...): Biogeochemistry.jl:932-957,
+ * 1078-1111: diffusive_flux(D_N, c_atm, max(C_N / theta_N, 0), dz_top) and dfluxBCdY = D_N / theta_N / dz_top */
+void orc_co2_boundary_flux(const orc_problem *P, const orc_co2_species *S, const double *C, double *top_bc,
+                           double *dfluxBCdY)
+{
+    const int N = P->N;
+    if (!S->c_atm) return;
+    FOR_COLUMNS(P, c)
+    {
+        const int64_t k = c * N + N - 1;
+        const double dz = dz_top(P);
+        top_bc[c] = -S->D[k] * (S->c_atm[c] - dmax(C[k] / S->theta_eff[k], 0.0)) / dz;
+        if (dfluxBCdY) dfluxBCdY[c] = S->D[k] / S->theta_eff[k] / dz;
+    }
+}
+
+/* compute_imp_tendency!: Biogeochemistry.jl:371-413:
+ *   dC = -div(-interp(D) grad(max(C, 0) / theta_eff)), boundary faces = top_bc / bottom_bc */
+void orc_co2_imp_tendency(const orc_problem *P, const orc_co2_species *S, const double *C, const double *top_bc,
+                          const double *bot_bc, double *dC)
+{
+    const int N = P->N;
+    FOR_COLUMNS(P, c)
+    {
+        const int64_t o = c * N;
+        double q_lo = bot_bc[c];
+        for (int i = 0; i < N; ++i) {
+            double q_hi;
+            if (i < N - 1) {
+                const double u0 = dmax(C[o + i], 0.0) / S->theta_eff[o + i];
+                const double u1 = dmax(C[o + i + 1], 0.0) / S->theta_eff[o + i + 1];
+                q_hi = -((S->D[o + i] + S->D[o + i + 1]) / 2.0) * ((u1 - u0) / dz_face(P, i + 1));
+            } else {
+                q_hi = top_bc[c];
+            }
+            dC[o + i] = -((q_hi - q_lo) / dz_cell(P, i));
+            q_lo = q_hi;
+        }
+    }
+}
+
+/* compute_jacobian!: Biogeochemistry.jl:1119-1195: dtgamma (D . (Diag(interp(D)) . G . Diag(1/theta_eff)
+ * - Lower(dfluxBCdY))) - I: the block of column_tridiag_block with A = D, coef = 1/theta_eff */
+void orc_co2_jacobian(const orc_problem *P, const orc_co2_species *S, double dtgamma, const double *dfluxBCdY,
+                      double *lo, double *di, double *up)
+{
+    const int N = P->N;
+    FOR_COLUMNS(P, c)
+    {
+        const int64_t o = c * N;
+        double *coef = (double *)malloc(sizeof(double) * (size_t)N);
+        for (int i = 0; i < N; ++i) coef[i] = 1 / S->theta_eff[o + i];
+        column_tridiag_block(P, S->D + o, coef, dtgamma, (S->c_atm && dfluxBCdY) ? dfluxBCdY[c] : 0.0, lo + o, di + o,
+                             up + o);
+        free(coef);
+    }
+}
+
+int orc_co2_implicit_step(const orc_problem *P, const orc_co2_species *S, double *C, double *top_bc,
+                          const double *bot_bc, double dtgamma, int max_iters)
+{
+    const int N = P->N;
+    const int64_t n3 = P->ncol * (int64_t)N;
+    double *temp = (double *)malloc(sizeof(double) * (size_t)n3 * 6);
+    double *f = temp + n3, *lo = f + n3, *di = lo + n3, *up = di + n3, *x = up + n3;
+    double *dflux = (double *)calloc((size_t)P->ncol, sizeof(double));
+    memcpy(temp, C, sizeof(double) * (size_t)n3);
+    for (int it = 0; it < max_iters; ++it) {
+        orc_co2_boundary_flux(P, S, C, top_bc, dflux);       /* update_implicit_boundary_fluxes! (:320-357) */
+        orc_co2_jacobian(P, S, dtgamma, dflux, lo, di, up);
+        orc_co2_imp_tendency(P, S, C, top_bc, bot_bc, f);
+        for (int64_t k = 0; k < n3; ++k) f[k] = temp[k] + dtgamma * f[k] - C[k];
+        FOR_COLUMNS(P, c)
+        {
+            double *cp = (double *)malloc(sizeof(double) * (size_t)N);
+            thomas(N, lo + c * N, di + c * N, up + c * N, f + c * N, x + c * N, cp);
+            free(cp);
+        }
+        for (int64_t k = 0; k < n3; ++k) C[k] -= x[k];
+    }
+    free(temp);
+    free(dflux);
+    return max_iters;
+}

@@ -161,6 +161,25 @@ typedef struct {
 void orc_update_runoff(const orc_problem *P, const orc_explicit_params *X, const orc_runoff_params *R, const orc_state *Y,
                        const orc_aux *a, const double *precip, orc_runoff *out);
 
+/* ---- SoilCO2Model implicit diffusion: Biogeochemistry.jl:320-413, 1119-1195 ---------- */
+/* One diffusing species (CO2 with p.soilco2.{D, theta_eff}, or O2 with {D_o2, theta_eff_o2}); both have the same
+ * G . Diag . D structure.  c_atm != NULL: the top BC is the atmosphere's state (AtmosCO2StateBC / AtmosO2StateBC,
+ * :932-957, :1078-1111), re-evaluated every Newton iteration together with dfluxBCdY; else top_bc is a flux value. */
+typedef struct {
+    const double *D, *theta_eff;   /* [ncol*N] lagged */
+    const double *c_atm;           /* [ncol] air-equivalent concentration at the surface, or NULL */
+} orc_co2_species;
+void orc_co2_boundary_flux(const orc_problem *P, const orc_co2_species *S, const double *C, double *top_bc,
+                           double *dfluxBCdY);
+void orc_co2_imp_tendency(const orc_problem *P, const orc_co2_species *S, const double *C, const double *top_bc,
+                          const double *bot_bc, double *dC);
+void orc_co2_jacobian(const orc_problem *P, const orc_co2_species *S, double dtgamma, const double *dfluxBCdY,
+                      double *lo, double *di, double *up);
+/* Newton loop of one implicit ARS111 stage on C (in: temp, out: new value); top_bc is updated in place for a
+ * state BC.  Returns the iterations done. */
+int orc_co2_implicit_step(const orc_problem *P, const orc_co2_species *S, double *C, double *top_bc,
+                          const double *bot_bc, double dtgamma, int max_iters);
+
 /* ---- the hooks (each cites the reference in soil_oracle.c) */
 void orc_update_implicit_cache(const orc_problem *P, const orc_state *Y, orc_cache *p);
 /* explicit-stage flavour of the boundary-flux update: always evaluates (rre.jl:111-149) */
