@@ -801,6 +801,90 @@ int step_host_pipelined(clb_handle h, double dtgamma, int32_t max_iters, const i
         for (auto &e : h->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto &e : h->ev_out) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    // chunks of whole 32-column tiles, at most 16 and at least kHostChunkMin columns each
+    static const int want_chunks = getenv("CLB_HOST_CHUNKS") ? atoi(getenv("CLB_HOST_CHUNKS")) : 4;
+    int n_chunks = (int)std::min<int64_t>(std::max(want_chunks, 1), std::min<int64_t>(16, ncol / kHostChunkMin));
+    const int64_t per = (((ncol + n_chunks - 1) / n_chunks) + 31) / 32 * 32;
+    n_chunks = (int)((ncol + per - 1) / per);
+    const size_t tile_smem = (size_t)N * (clb::kTileCols + 1) * sizeof(double);
+
+    // Zero-copy route: when every caller array is pinned host memory the device can address (cudaHostAlloc /
+    // cudaHostRegister under unified addressing: torch pinned tensors, CUDA.jl pinned arrays), the relayout
+    // kernels read and write the host arrays directly over PCIe.  That removes the staging copies and their
+    // per-copy DMA set-up gaps (~30 copies per stage); the write-back of chunk k-1 and the read of chunk k are one
+    // launch (k_relayout_dual), so PCIe carries both directions at once.
+    static const bool no_zero_copy = getenv("CLB_HOST_NO_ZEROCOPY") != nullptr;
+    const double *din[2 * clb::kManyFields];
+    double *dout[clb::kManyFields];
+    bool direct = !no_zero_copy;
+    for (int j = 0; j < n_in + n_out && direct; ++j) {
+        const void *ptr = (j < n_in) ? (const void *)in_ptrs[j] : (const void *)out_ptrs[j - n_in];
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+            cudaGetLastError();
+            direct = false;
+        } else if (j < n_in) {
+            din[j] = (const double *)at.devicePointer;
+        } else {
+            dout[j - n_in] = (double *)at.devicePointer;
+        }
+    }
+    if (direct) {
+        if (n_cell_in + n_cell_out > clb::kManyFields) return 0;
+        h->last_variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
+        clb::DevView V = make_view(h);
+        V.stats = nullptr;
+        TRY(ensure_prepared(h, V));
+        nvtxRangePushA("implicit_step_host (zero-copy)");
+        cudaStream_t const S = h->stream;
+        // the small per-column inputs in one launch for all columns
+        if (n_col_in) {
+            clb::ManyFields f = {};
+            for (int a = 0; a < n_col_in; ++a) {
+                f.dst[a] = h->field[in_fields[col_in[a]]];
+                f.src[a] = din[col_in[a]];
+            }
+            clb::k_copy_many<<<dim3((unsigned)((ncol + 255) / 256), n_col_in), 256, 0, S>>>(f, ncol);
+        }
+        // launch k moves chunk k in and chunk k-1 out together; the stage kernel of chunk k follows it
+        for (int k = 0; k <= n_chunks; ++k) {
+            const int64_t ci = k * per, ni = (k < n_chunks) ? std::min(per, ncol - ci) : 0;
+            const int64_t co = (k - 1) * per, no = (k > 0) ? std::min(per, ncol - co) : 0;
+            clb::ManyFields f = {};
+            int nf = 0;
+            const int n_out_f = (k > 0) ? n_cell_out : 0;
+            for (int a = 0; a < n_out_f; ++a, ++nf) {
+                f.dst[nf] = dout[cell_out[a]] + (size_t)co * N;
+                f.src[nf] = h->field[out_fields[cell_out[a]]] + co;
+            }
+            for (int a = 0; a < ((k < n_chunks) ? n_cell_in : 0); ++a, ++nf) {
+                f.dst[nf] = h->field[in_fields[cell_in[a]]] + ci;
+                f.src[nf] = din[cell_in[a]] + (size_t)ci * N;
+            }
+            if (nf) {
+                const unsigned tiles = (unsigned)((std::max(ni, no) + clb::kTileCols - 1) / clb::kTileCols);
+                clb::k_relayout_dual<<<dim3(nf, tiles), 256, tile_smem, S>>>(f, n_out_f, h->sl, h->sc, N, no, ni);
+            }
+            if (k < n_chunks) {
+                const clb::DevView P = shift_view(V, ci, ni);
+                if (N == 15) TRY((launch_quad_n<15, true>(h, P, dtgamma, max_iters, ci)));
+                else TRY((launch_quad_n<16, true>(h, P, dtgamma, max_iters, ci)));
+            }
+        }
+        if (n_col_out) {
+            clb::ManyFields f = {};
+            for (int a = 0; a < n_col_out; ++a) {
+                f.dst[a] = dout[col_out[a]];
+                f.src[a] = h->field[out_fields[col_out[a]]];
+            }
+            clb::k_copy_many<<<dim3((unsigned)((ncol + 255) / 256), n_col_out), 256, 0, S>>>(f, ncol);
+        }
+        nvtxRangePop();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(S));
+        return 1;
+    }
+
     // staging in the caller's layout: cell fields (ncol, N) level fastest, column fields (ncol)
     const size_t cell_b = (size_t)ncol * N * sizeof(double), col_b = (size_t)ncol * sizeof(double);
     const size_t need_in = n_cell_in * cell_b + n_col_in * col_b, need_out = n_cell_out * cell_b + n_col_out * col_b;
@@ -818,12 +902,6 @@ int step_host_pipelined(clb_handle h, double dtgamma, int32_t max_iters, const i
     }
     double *const st_cell_in = h->d_stage_in, *const st_col_in = h->d_stage_in + (size_t)n_cell_in * ncol * N;
     double *const st_cell_out = h->d_stage_out, *const st_col_out = h->d_stage_out + (size_t)n_cell_out * ncol * N;
-
-    // chunks of whole 32-column tiles, at most 16 and at least kHostChunkMin columns each
-    static const int want_chunks = getenv("CLB_HOST_CHUNKS") ? atoi(getenv("CLB_HOST_CHUNKS")) : 3;
-    int n_chunks = (int)std::min<int64_t>(std::max(want_chunks, 1), std::min<int64_t>(16, ncol / kHostChunkMin));
-    const int64_t per = (((ncol + n_chunks - 1) / n_chunks) + 31) / 32 * 32;
-    n_chunks = (int)((ncol + per - 1) / per);
 
     h->last_variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
     clb::DevView V = make_view(h);
@@ -844,7 +922,6 @@ int step_host_pipelined(clb_handle h, double dtgamma, int32_t max_iters, const i
                                      (size_t)n * N * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
         CUDA_TRY(cudaEventRecord(h->ev_in[k], h->s_in));
     }
-    const size_t tile_smem = (size_t)N * (clb::kTileCols + 1) * sizeof(double);
     for (int k = 0; k < n_chunks; ++k) {
         const int64_t c0 = k * per, n = std::min(per, ncol - c0);
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[k], 0));

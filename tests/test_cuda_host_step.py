@@ -17,7 +17,19 @@ IN_EH = ("y_theta_l", "y_rho_e_int", "y_theta_i", "k_lag", "kappa_lag", "theta_l
 IN_RI = ("y_theta_l", "is_saturated", "top_bc_w", "bot_bc_w", "r_ss", "h_grad", "y_intf_w")
 
 
-def _run(model, ncol, out_of_place, seed=3, steps=1):
+def _pin(a):
+    """a pinned (page-locked) copy: the library then reads / writes the host array directly (zero-copy route)"""
+    import torch
+    t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    t.numpy()[...] = a
+    _pin.keep.append(t)
+    return t.numpy()
+
+
+_pin.keep = []
+
+
+def _run(model, ncol, out_of_place, seed=3, steps=1, pinned=False):
     import climaland_b200  # noqa: F401
     from climaland_b200 import workloads
     eh = model == "energy_hydrology"
@@ -31,25 +43,31 @@ def _run(model, ncol, out_of_place, seed=3, steps=1):
     if eh:
         outs.update({f"{pre}_rho_e_int": np.zeros((ncol, 15)), f"{pre}_intf_e": np.zeros(ncol)})
     ins = {k: np.ascontiguousarray(w[k]) for k in names}
+    if pinned:
+        ins = {k: _pin(v) for k, v in ins.items()}
+        outs = {k: _pin(v) for k, v in outs.items()}
     for _ in range(steps):
         P.implicit_step(U, dt, iters, p=p)
         s.implicit_step_host(dt, iters, ins, outs)
         if steps > 1:  # feed the new state back, as a time loop does
-            ins["y_theta_l"] = outs[f"{pre}_theta_l"].copy()
-            ins["y_intf_w"] = outs[f"{pre}_intf_w"].copy()
+            ins["y_theta_l"][...] = outs[f"{pre}_theta_l"]
+            ins["y_intf_w"][...] = outs[f"{pre}_intf_w"]
             if eh:
-                ins["y_rho_e_int"] = outs[f"{pre}_rho_e_int"].copy()
-                ins["y_intf_e"] = outs[f"{pre}_intf_e"].copy()
+                ins["y_rho_e_int"][...] = outs[f"{pre}_rho_e_int"]
+                ins["y_intf_e"][...] = outs[f"{pre}_intf_e"]
     variant = s.last_variant()
     s.close()
     return U, outs, pre, variant
 
 
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
 @pytest.mark.parametrize("out_of_place", [True, False], ids=["outofplace", "inplace"])
 @pytest.mark.parametrize("model,ncol", [("energy_hydrology", 61206), ("energy_hydrology", 9001), ("richards", 20000),
                                         ("energy_hydrology", 700)])
-def test_host_step_matches_oracle(model, ncol, out_of_place):
-    U, outs, pre, _ = _run(model, ncol, out_of_place)
+def test_host_step_matches_oracle(model, ncol, out_of_place, pinned):
+    """pageable arrays take the staged route (H2D copies into a device staging area), pinned arrays the zero-copy
+    route (the relayout kernels address the host arrays directly)"""
+    U, outs, pre, _ = _run(model, ncol, out_of_place, pinned=pinned)
     assert_close(outs[f"{pre}_theta_l"], U.theta_l, TOL, "theta_l")
     assert_close(outs[f"{pre}_intf_w"], U.intF_w, TOL, "intF_w")
     if model == "energy_hydrology":
@@ -57,23 +75,25 @@ def test_host_step_matches_oracle(model, ncol, out_of_place):
         assert_close(outs[f"{pre}_intf_e"], U.intF_e, TOL, "intF_e")
 
 
-def test_host_step_repeated_calls():
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+def test_host_step_repeated_calls(pinned):
     """three stages in a row through the pipelined route (staging buffers and events are reused)"""
-    U, outs, pre, variant = _run("energy_hydrology", 30000, True, steps=3)
+    U, outs, pre, variant = _run("energy_hydrology", 30000, True, steps=3, pinned=pinned)
     assert variant == 5
     assert_close(outs["u_theta_l"], U.theta_l, 1e-11, "theta_l after 3 stages")
     assert_close(outs["u_rho_e_int"], U.rho_e_int, 1e-11, "rho_e_int after 3 stages")
 
 
 def test_pipelined_and_plain_routes_agree_bitwise():
-    """CLB_HOST_NO_PIPELINE=1 forces the field-by-field route (read once per process): run it in a child."""
+    """CLB_HOST_NO_PIPELINE=1 forces the field-by-field route, CLB_HOST_NO_ZEROCOPY=1 the staged route for pinned
+    arrays (both read once per process): run each in a child."""
     code = ("import sys, numpy as np; sys.path[:0] = ['.', 'oracle', 'tests'];"
-            "from test_cuda_host_step import _run; U, outs, pre, v = _run('energy_hydrology', 20000, True);"
+            "from test_cuda_host_step import _run; U, outs, pre, v = _run('energy_hydrology', 20000, True, pinned=True);"
             "np.save(sys.argv[1], outs['u_theta_l'])")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for tag, env in (("pipe", {}), ("plain", {"CLB_HOST_NO_PIPELINE": "1"})):
+    for tag, env in (("zerocopy", {}), ("staged", {"CLB_HOST_NO_ZEROCOPY": "1"}), ("plain", {"CLB_HOST_NO_PIPELINE": "1"})):
         path = f"/tmp/clb_host_{tag}.npy"
         subprocess.run([sys.executable, "-c", code, path], cwd=root, env={**os.environ, **env}, check=True, timeout=600)
         res[tag] = np.load(path)
-    assert np.array_equal(res["pipe"], res["plain"])
+    assert np.array_equal(res["zerocopy"], res["plain"]) and np.array_equal(res["staged"], res["plain"])
