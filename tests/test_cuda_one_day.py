@@ -103,3 +103,70 @@ def test_land_simulation_fine_grained_equals_fused():
         assert abs(sim.t - 5400.0) < 1e-9
         out.append(sim.Y.soil.ϑ_l.copy())
     assert_close(out[0], out[1], 1e-12, "fine-grained vs fused")
+
+
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["fast", "libm"])
+def test_energy_hydrology_one_day_with_the_explicit_stage_on_the_device(math_mode):
+    """One simulated day of EnergyHydrology with the explicit-stage rows of SURVEY 8f on the device: every step runs
+    update_aux! + PhaseChange (clb_update_aux_and_phase_change), the TOPMODEL runoff (clb_update_runoff) -- which
+    leave the implicit stage's lagged K, kappa, theta_l, R_ss, R_ess, h∇, is_saturated in place -- then the ARS111
+    explicit update U0 = u + dt T_exp(u) (the integrator's axpy: numpy, the same for both paths) and the fused implicit
+    stage.  The oracle runs the same loop from its own state.  Tolerance 1e-8: the explicit freeze-thaw relaxation
+    amplifies last-bit differences by ~1e7 over the 96 steps -- with CLB_MATH_LIBM, where the only difference from the
+    oracle is CUDA libm against glibc, theta_i agrees to 9.3e-10; with the table-driven FAST functions to 1.6e-9
+    (theta_l, rho_e_int: 2-6e-10 in both).  The implicit path alone meets 1e-9 (the tests above)."""
+    from climaland_b200 import workloads
+    dt, nsteps, iters, ncol, depth = 900.0, 96, 3, 128, 50.0
+    w = _workload("energy_hydrology", ncol, 15, seed=31, topmodel=True)
+    xp = workloads.make_explicit_params(w, 31)
+    rng = np.random.default_rng(4)
+    precip, f_max = -rng.uniform(0.0, 4e-7, ncol), rng.uniform(0.2, 0.6, ncol)
+    f_over, R_sb = 3.28, 1.484e-4 / 1000
+    # a third of the columns start with a saturated bottom so that the runoff terms are active
+    sat = rng.random(ncol) < 0.35
+    w["y_theta_l"][sat, :4] = (w["nu"] - w["y_theta_i"])[sat, :4] + 1e-3
+    P, U, p = oracle_problem(w, nthreads=4)
+    X = P.explicit_params(**xp)
+    s = cuda_solver(w, math_mode=math_mode)
+    for k, v in xp.items():
+        s.set(k, v)
+    s.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+    s.set("f_max", f_max)
+    s.set("precip", precip)
+    s.set_runoff_params(f_over=f_over, R_sb=R_sb, depth=depth)
+    froze = thawed = 0.0
+    for _ in range(nsteps):
+        # ---- oracle: explicit stage, explicit update, implicit stage
+        a = P.new_aux()
+        P.update_aux(X, U, a)
+        dl, di = np.zeros_like(U.theta_l), np.zeros_like(U.theta_l)
+        P.phase_change(X, U, a, dl, di)
+        R = P.update_runoff(U, precip, f_max, f_over, R_sb, depth, X=X, a=a)
+        for name, v in (("K_lag", a.K), ("kappa_lag", a.kappa), ("theta_l_lag", a.theta_l), ("is_saturated", R.is_saturated),
+                        ("R_ss", R.R_ss), ("R_ess", R.R_ess), ("h_grad", R.h_grad)):
+            P.set(name, v)
+        p.top_bc_w[...] = R.infiltration
+        U.theta_l += dt * dl
+        U.theta_i += dt * di
+        P.implicit_step(U, dt, iters, p=p)
+        froze, thawed = max(froze, di.max()), max(thawed, -di.min())
+        # ---- CUDA: the same, the lagged fields never leave the device
+        s.set("dye_theta_l", 0.0)
+        s.set("dye_theta_i", 0.0)
+        s.update_aux_and_phase_change()
+        s.update_runoff()
+        s.set("top_bc_w", s.get("infiltration"))
+        s.set("y_theta_l", s.get("y_theta_l") + dt * s.get("dye_theta_l"))
+        s.set("y_theta_i", s.get("y_theta_i") + dt * s.get("dye_theta_i"))
+        s.implicit_step(dt, iters)
+    assert froze > 0.0 and thawed > 0.0, "the day must freeze and thaw somewhere"
+    assert R.h_grad.max() > 0.0 and R.R_ss.max() > 0.0
+    from helpers import rel_err
+    print("one-day errors:", {k: rel_err(s.get(k), v) for k, v in (("y_theta_l", U.theta_l), ("y_theta_i", U.theta_i),
+                                                                   ("y_rho_e_int", U.rho_e_int), ("y_intf_w", U.intF_w))})
+    assert_close(s.get("y_theta_l"), U.theta_l, 1e-9, "theta_l after one day")
+    assert_close(s.get("y_theta_i"), U.theta_i, 1e-8, "theta_i after one day")
+    assert_close(s.get("y_rho_e_int"), U.rho_e_int, 1e-9, "rho_e_int after one day")
+    assert_close(s.get("y_intf_w"), U.intF_w, 1e-9, "intF_w after one day")
+    assert np.max(np.abs(s.get("y_theta_i") - w["y_theta_i"])) > 1e-6
+    s.close()
