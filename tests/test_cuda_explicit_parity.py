@@ -196,3 +196,58 @@ def test_topmodel_runoff(model, layout, math_mode):
     if model == "energy_hydrology":
         assert_close(s.get("r_ess"), out.R_ess, TOL, "R_ess")
     s.close()
+
+
+def test_explicit_rows_respect_the_land_sea_mask():
+    """mask_test.jl:53-61 for the explicit-stage and SoilCO2 entry points: a handle over the active columns of a
+    larger domain reads / writes only those columns of the caller's arrays and gives the compacted problem's
+    values; inactive columns of an output array keep what they held."""
+    import oracle as orc
+    import climaland_b200 as cl
+    from climaland_b200 import workloads
+    ncol_total, N = 400, 15
+    rng = np.random.default_rng(8)
+    active = np.sort(rng.choice(ncol_total, 150, replace=False)).astype(np.int64)
+    w = workloads.make_workload("energy_hydrology", ncol_total, N=N, seed=17, topmodel=False)
+    xp = workloads.make_explicit_params(w, 17)
+    s = cl.SoilColumnSolver(model=cl.ENERGY_HYDROLOGY, n_columns=active.size, n_columns_total=ncol_total, z_f=w["z_f"],
+                            z_c=w["z_c"], active_columns=active)
+    for k, v in {**w, **xp}.items():
+        if k.lower() in cl.FIELDS:
+            s.set(k, v)
+    s.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+    s.update_aux()
+    # the compacted problem on the oracle
+    sub = {k: (v[active] if isinstance(v, np.ndarray) and v.shape[:1] == (ncol_total,) else v) for k, v in w.items()}
+    sub["ncol"] = active.size
+    P, Y, _ = oracle_problem(sub, nthreads=2)
+    X = P.explicit_params(**{k: v[active] for k, v in xp.items()})
+    a = P.new_aux()
+    P.update_aux(X, Y, a)
+    sentinel = -777.0
+    for dev, name in (("kappa_lag", "kappa"), ("k_lag", "K"), ("p_tf_depressed", "Tf_depressed")):
+        out = np.full((ncol_total, N), sentinel)
+        s.get(dev, out)
+        assert_close(out[active], getattr(a, name), TOL, name)
+        inactive = np.setdiff1d(np.arange(ncol_total), active)
+        assert np.all(out[inactive] == sentinel)
+    tw = np.full(ncol_total, sentinel)
+    s.get("total_water", tw)
+    assert_close(tw[active], a.total_water, TOL, "total_water")
+    assert np.all(np.delete(tw, active) == sentinel)
+    # SoilCO2 stage on the same masked handle
+    D, th = rng.uniform(1e-8, 2e-6, (ncol_total, N)), rng.uniform(0.02, 0.45, (ncol_total, N))
+    C0 = rng.uniform(5e-5, 2e-3, (ncol_total, N))
+    for name in ("co2", "o2"):
+        s.set(f"{name}_y", C0)
+        s.set(f"{name}_d", D)
+        s.set(f"{name}_theta_eff", th)
+    s.soilco2_implicit_step(1800.0, 3)
+    S = P.co2_species(D[active], th[active])
+    C = np.ascontiguousarray(C0[active])
+    P.co2_implicit_step(S, C, np.zeros(active.size), np.zeros(active.size), 1800.0, 3)
+    out = np.full((ncol_total, N), sentinel)
+    s.get("co2_y", out)
+    assert_close(out[active], C, TOL, "CO2 after the stage")
+    assert np.all(np.delete(out, active, axis=0) == sentinel)
+    s.close()
