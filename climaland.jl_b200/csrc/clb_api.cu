@@ -656,384 +656,12 @@ __global__ void k_test_math(int kind, const double *x, const double *y, double *
 }  // namespace
 
 // =============================================================================
-// ---- the explicit stage of EnergyHydrology (soil_explicit.cuh) --------------------------------
-namespace {
+#include "clb_api_explicit.inc"
 
-int explicit_ready(clb_handle h, bool aux, bool phase, const char *who)
-{
-    if (h->cfg.model != CLB_ENERGY_HYDROLOGY)
-        return fail(CLB_ERR_INVALID, "%s: EnergyHydrology only (RichardsModel's update_aux! is clb_update_implicit_cache)", who);
-    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
-    if (!h->explicit_set) return fail(CLB_ERR_UNSET, "%s: clb_set_explicit_params was never called", who);
-    TRY(require(h, {CLB_F_NU, CLB_F_THETA_R, CLB_F_K_SAT, CLB_F_S_S, CLB_F_HCM_A, CLB_F_HCM_B, CLB_F_RHO_C_DS,
-                    CLB_F_Y_THETA_L, CLB_F_Y_RHO_E_INT, CLB_F_Y_THETA_I}, who));
-    if (h->cfg.closure == CLB_VAN_GENUCHTEN) TRY(require(h, {CLB_F_HCM_M}, who));
-    if (aux) {
-        TRY(require(h, {CLB_F_KAPPA_DRY, CLB_F_KAPPA_SAT_UNFROZEN, CLB_F_KAPPA_SAT_FROZEN, CLB_F_NU_SS_OM,
-                        CLB_F_NU_SS_QUARTZ, CLB_F_NU_SS_GRAVEL}, who));
-        TRY(alloc_fields(h, {CLB_F_THETA_L_LAG, CLB_F_KAPPA_LAG, CLB_F_K_LAG, CLB_F_P_T, CLB_F_P_PSI,
-                             CLB_F_P_TF_DEPRESSED, CLB_F_TOTAL_WATER, CLB_F_TOTAL_ENERGY}));
-    } else {
-        TRY(require(h, {CLB_F_THETA_L_LAG, CLB_F_KAPPA_LAG, CLB_F_P_T}, who));
-    }
-    if (phase) TRY(alloc_fields(h, {CLB_F_DYE_THETA_L, CLB_F_DYE_THETA_I}));
-    return CLB_OK;
-}
+#include "clb_api_host_step.inc"
 
-clb::ExplicitView make_explicit_view(clb_handle h)
-{
-    clb::ExplicitView X;
-    double *const *F = h->field;
-    X.kappa_dry = F[CLB_F_KAPPA_DRY]; X.kappa_sat_unfrozen = F[CLB_F_KAPPA_SAT_UNFROZEN];
-    X.kappa_sat_frozen = F[CLB_F_KAPPA_SAT_FROZEN];
-    X.nu_ss_om = F[CLB_F_NU_SS_OM]; X.nu_ss_quartz = F[CLB_F_NU_SS_QUARTZ]; X.nu_ss_gravel = F[CLB_F_NU_SS_GRAVEL];
-    X.p_theta_l = F[CLB_F_THETA_L_LAG]; X.p_kappa = F[CLB_F_KAPPA_LAG]; X.p_K = F[CLB_F_K_LAG];
-    X.p_T = F[CLB_F_P_T]; X.p_psi = F[CLB_F_P_PSI]; X.p_Tf = F[CLB_F_P_TF_DEPRESSED];
-    X.total_water = F[CLB_F_TOTAL_WATER]; X.total_energy = F[CLB_F_TOTAL_ENERGY];
-    X.dYe_theta_l = F[CLB_F_DYE_THETA_L]; X.dYe_theta_i = F[CLB_F_DYE_THETA_I];
-    X.k = h->explicit_k;
-    return X;
-}
+#include "clb_api_soilco2.inc"
 
-template <bool AUX, bool PHASE>
-int launch_explicit(clb_handle h, const char *who)
-{
-    TRY(check_handle(h));
-    DeviceGuard guard(h->cfg.device);
-    TRY(explicit_ready(h, AUX, PHASE, who));
-    const clb::DevView P = make_view(h);
-    const clb::ExplicitView X = make_explicit_view(h);
-    const dim3 grid(grid_for(P.ncol), (unsigned)P.N);
-    nvtxRangePushA(who);
-    const int cl = h->cfg.closure, ma = h->cfg.math_mode;
-    if (cl == 0 && ma == 0) clb::k_explicit_cells<0, 0, AUX, PHASE><<<grid, kBlock, 0, h->stream>>>(P, X);
-    else if (cl == 0 && ma == 1) clb::k_explicit_cells<0, 1, AUX, PHASE><<<grid, kBlock, 0, h->stream>>>(P, X);
-    else if (cl == 1 && ma == 0) clb::k_explicit_cells<1, 0, AUX, PHASE><<<grid, kBlock, 0, h->stream>>>(P, X);
-    else clb::k_explicit_cells<1, 1, AUX, PHASE><<<grid, kBlock, 0, h->stream>>>(P, X);
-    if (AUX) clb::k_explicit_totals<<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, X);
-    nvtxRangePop();
-    CUDA_TRY(cudaGetLastError());
-    return CLB_OK;
-}
-
-}  // namespace
-
-namespace {
-
-// ---- pipelined host-buffer stage ------------------------------------------------------------------
-// clb_implicit_step_host moves ~70 MB per ~1 degree stage over PCIe while the fused kernel needs ~55 us, so
-// the end-to-end time is the transfers'.  The columns are cut into chunks: the H2D copy of chunk k+1 (copy-in
-// stream) overlaps the relayout + fused kernel of chunk k (the handle's stream) and the D2H copy of chunk k-1
-// (copy-out stream); columns are independent, so a chunk is a complete problem.  Applies to the lane-quad
-// kernels without a land-sea mask; every other configuration takes the field-by-field path.
-
-// every data pointer of a view moved to column c0 of column-fastest mirrors (cell arrays: (i, c) at i*ld + c;
-// column arrays: c); the per-level grid vectors and the statistics do not move
-clb::DevView shift_view(const clb::DevView &V, int64_t c0, int64_t n)
-{
-    clb::DevView P = V;
-    P.ncol = n;
-#define CLB_SHIFT(m) if (P.m) P.m += c0
-    CLB_SHIFT(nu); CLB_SHIFT(theta_r); CLB_SHIFT(K_sat); CLB_SHIFT(S_s); CLB_SHIFT(hcm_a); CLB_SHIFT(hcm_b);
-    CLB_SHIFT(hcm_m); CLB_SHIFT(rho_c_ds); CLB_SHIFT(K_lag); CLB_SHIFT(kappa_lag); CLB_SHIFT(theta_l_lag);
-    CLB_SHIFT(is_sat); CLB_SHIFT(R_ss); CLB_SHIFT(R_ess); CLB_SHIFT(h_grad); CLB_SHIFT(theta_bc_top);
-    CLB_SHIFT(theta_bc_bot); CLB_SHIFT(Y_theta_l); CLB_SHIFT(Y_rho_e); CLB_SHIFT(Y_theta_i); CLB_SHIFT(Y_intF_w);
-    CLB_SHIFT(Y_intF_e); CLB_SHIFT(out_theta_l); CLB_SHIFT(out_rho_e); CLB_SHIFT(out_intF_w); CLB_SHIFT(out_intF_e);
-    CLB_SHIFT(p_K); CLB_SHIFT(p_psi); CLB_SHIFT(p_T); CLB_SHIFT(top_bc_w); CLB_SHIFT(bot_bc_w); CLB_SHIFT(top_bc_h);
-    CLB_SHIFT(bot_bc_h); CLB_SHIFT(dfluxBCdY); CLB_SHIFT(total_water);
-#undef CLB_SHIFT
-    return P;
-}
-
-bool is_step_input(int f)
-{
-    switch (f) {
-    case CLB_F_Y_THETA_L: case CLB_F_Y_RHO_E_INT: case CLB_F_Y_THETA_I: case CLB_F_K_LAG: case CLB_F_KAPPA_LAG:
-    case CLB_F_THETA_L_LAG: case CLB_F_IS_SATURATED: case CLB_F_TOP_BC_W: case CLB_F_BOT_BC_W: case CLB_F_TOP_BC_H:
-    case CLB_F_BOT_BC_H: case CLB_F_R_SS: case CLB_F_R_ESS: case CLB_F_H_GRAD: case CLB_F_Y_INTF_W: case CLB_F_Y_INTF_E:
-        return true;
-    default: return false;
-    }
-}
-
-constexpr int64_t kHostChunkMin = 4096;  // columns; below 2 chunks of this the plain path is as good
-
-// returns 1 when the pipelined path ran, 0 when it does not apply (the caller falls back), < 0 on error
-int step_host_pipelined(clb_handle h, double dtgamma, int32_t max_iters, const int32_t *in_fields,
-                        const double *const *in_ptrs, int32_t n_in, const int32_t *out_fields, double *const *out_ptrs,
-                        int32_t n_out)
-{
-    const int N = h->cfg.n_levels;
-    const int64_t ncol = h->cfg.n_columns;
-    const int kv = h->cfg.kernel_variant;
-    if (h->d_idx || !pair_variant_applies(h) || h->sc != 1 || ncol < 2 * kHostChunkMin) return 0;
-    if (kv != CLB_VARIANT_AUTO && kv != CLB_VARIANT_LANE_QUAD_PIPELINED) return 0;
-    if (n_in > clb::kManyFields + clb::kManyFields || n_out > clb::kManyFields) return 0;
-    int cell_in[clb::kManyFields], col_in[clb::kManyFields], cell_out[clb::kManyFields], col_out[clb::kManyFields];
-    int n_cell_in = 0, n_col_in = 0, n_cell_out = 0, n_col_out = 0;
-    for (int j = 0; j < n_in; ++j) {
-        if (!is_step_input(in_fields[j]) || !in_ptrs[j]) return 0;
-        if (is_cell_field(in_fields[j])) { if (n_cell_in == clb::kManyFields) return 0; cell_in[n_cell_in++] = j; }
-        else { if (n_col_in == clb::kManyFields) return 0; col_in[n_col_in++] = j; }
-    }
-    for (int j = 0; j < n_out; ++j) {
-        if (!(is_cell_field(out_fields[j]) || is_col_field(out_fields[j])) || !out_ptrs[j]) return 0;
-        if (is_cell_field(out_fields[j])) cell_out[n_cell_out++] = j;
-        else col_out[n_col_out++] = j;
-    }
-    for (int j = 0; j < n_in; ++j) {
-        TRY(ensure_field(h, in_fields[j]));
-        h->field_set[in_fields[j]] = true;
-    }
-    TRY(step_inputs_ready(h));
-    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
-    if (h->out_of_place) {
-        TRY(alloc_fields(h, {CLB_F_U_THETA_L, CLB_F_U_INTF_W}));
-        if (eh) TRY(alloc_fields(h, {CLB_F_U_RHO_E_INT, CLB_F_U_INTF_E}));
-    }
-    for (int j = 0; j < n_out; ++j)
-        if (!h->field[out_fields[j]]) return fail(CLB_ERR_UNSET, "clb_implicit_step_host: output field %d does not exist", out_fields[j]);
-    if (!h->s_in) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
-        for (auto &e : h->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (auto &e : h->ev_out) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
-    // chunks of whole 32-column tiles, at most 16 and at least kHostChunkMin columns each
-    static const int want_chunks = getenv("CLB_HOST_CHUNKS") ? atoi(getenv("CLB_HOST_CHUNKS")) : 4;
-    int n_chunks = (int)std::min<int64_t>(std::max(want_chunks, 1), std::min<int64_t>(16, ncol / kHostChunkMin));
-    const int64_t per = (((ncol + n_chunks - 1) / n_chunks) + 31) / 32 * 32;
-    n_chunks = (int)((ncol + per - 1) / per);
-    const size_t tile_smem = (size_t)N * (clb::kTileCols + 1) * sizeof(double);
-
-    // Zero-copy route: when every caller array is pinned host memory the device can address (cudaHostAlloc /
-    // cudaHostRegister under unified addressing: torch pinned tensors, CUDA.jl pinned arrays), the relayout
-    // kernels read and write the host arrays directly over PCIe.  That removes the staging copies and their
-    // per-copy DMA set-up gaps (~30 copies per stage); the write-back of chunk k-1 and the read of chunk k are one
-    // launch (k_relayout_dual), so PCIe carries both directions at once.
-    static const bool no_zero_copy = getenv("CLB_HOST_NO_ZEROCOPY") != nullptr;
-    const double *din[2 * clb::kManyFields];
-    double *dout[clb::kManyFields];
-    bool direct = !no_zero_copy;
-    for (int j = 0; j < n_in + n_out && direct; ++j) {
-        const void *ptr = (j < n_in) ? (const void *)in_ptrs[j] : (const void *)out_ptrs[j - n_in];
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
-            cudaGetLastError();
-            direct = false;
-        } else if (j < n_in) {
-            din[j] = (const double *)at.devicePointer;
-        } else {
-            dout[j - n_in] = (double *)at.devicePointer;
-        }
-    }
-    if (direct) {
-        if (n_cell_in + n_cell_out > clb::kManyFields) return 0;
-        h->last_variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
-        clb::DevView V = make_view(h);
-        V.stats = nullptr;
-        TRY(ensure_prepared(h, V));
-        nvtxRangePushA("implicit_step_host (zero-copy)");
-        cudaStream_t const S = h->stream;
-        // the small per-column inputs in one launch for all columns
-        if (n_col_in) {
-            clb::ManyFields f = {};
-            for (int a = 0; a < n_col_in; ++a) {
-                f.dst[a] = h->field[in_fields[col_in[a]]];
-                f.src[a] = din[col_in[a]];
-            }
-            clb::k_copy_many<<<dim3((unsigned)((ncol + 255) / 256), n_col_in), 256, 0, S>>>(f, ncol);
-        }
-        // launch k moves chunk k in and chunk k-1 out together; the stage kernel of chunk k follows it
-        for (int k = 0; k <= n_chunks; ++k) {
-            const int64_t ci = k * per, ni = (k < n_chunks) ? std::min(per, ncol - ci) : 0;
-            const int64_t co = (k - 1) * per, no = (k > 0) ? std::min(per, ncol - co) : 0;
-            clb::ManyFields f = {};
-            int nf = 0;
-            const int n_out_f = (k > 0) ? n_cell_out : 0;
-            for (int a = 0; a < n_out_f; ++a, ++nf) {
-                f.dst[nf] = dout[cell_out[a]] + (size_t)co * N;
-                f.src[nf] = h->field[out_fields[cell_out[a]]] + co;
-            }
-            for (int a = 0; a < ((k < n_chunks) ? n_cell_in : 0); ++a, ++nf) {
-                f.dst[nf] = h->field[in_fields[cell_in[a]]] + ci;
-                f.src[nf] = din[cell_in[a]] + (size_t)ci * N;
-            }
-            if (nf) {
-                const unsigned tiles = (unsigned)((std::max(ni, no) + clb::kTileCols - 1) / clb::kTileCols);
-                clb::k_relayout_dual<<<dim3(nf, tiles), 256, tile_smem, S>>>(f, n_out_f, h->sl, h->sc, N, no, ni);
-            }
-            if (k < n_chunks) {
-                const clb::DevView P = shift_view(V, ci, ni);
-                if (N == 15) TRY((launch_quad_n<15, true>(h, P, dtgamma, max_iters, ci)));
-                else TRY((launch_quad_n<16, true>(h, P, dtgamma, max_iters, ci)));
-            }
-        }
-        if (n_col_out) {
-            clb::ManyFields f = {};
-            for (int a = 0; a < n_col_out; ++a) {
-                f.dst[a] = dout[col_out[a]];
-                f.src[a] = h->field[out_fields[col_out[a]]];
-            }
-            clb::k_copy_many<<<dim3((unsigned)((ncol + 255) / 256), n_col_out), 256, 0, S>>>(f, ncol);
-        }
-        nvtxRangePop();
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(S));
-        return 1;
-    }
-
-    // staging in the caller's layout: cell fields (ncol, N) level fastest, column fields (ncol)
-    const size_t cell_b = (size_t)ncol * N * sizeof(double), col_b = (size_t)ncol * sizeof(double);
-    const size_t need_in = n_cell_in * cell_b + n_col_in * col_b, need_out = n_cell_out * cell_b + n_col_out * col_b;
-    if (h->stage_in_bytes < need_in) {
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-        CUDA_TRY(cudaFree(h->d_stage_in));
-        CUDA_TRY(cudaMalloc(&h->d_stage_in, need_in));
-        h->stage_in_bytes = need_in;
-    }
-    if (h->stage_out_bytes < need_out) {
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
-        CUDA_TRY(cudaFree(h->d_stage_out));
-        CUDA_TRY(cudaMalloc(&h->d_stage_out, need_out));
-        h->stage_out_bytes = need_out;
-    }
-    double *const st_cell_in = h->d_stage_in, *const st_col_in = h->d_stage_in + (size_t)n_cell_in * ncol * N;
-    double *const st_cell_out = h->d_stage_out, *const st_col_out = h->d_stage_out + (size_t)n_cell_out * ncol * N;
-
-    h->last_variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
-    clb::DevView V = make_view(h);
-    V.stats = nullptr;
-    TRY(ensure_prepared(h, V));  // the prepared parameter mirrors cover all columns: once, before the chunks
-    nvtxRangePushA("implicit_step_host (pipelined)");
-    // nothing of this call may overtake what the caller enqueued before it
-    CUDA_TRY(cudaEventRecord(h->ev_start, h->stream));
-    CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
-    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_start, 0));
-    // copy-in stream: the small column fields whole, then the cell fields chunk by chunk
-    for (int a = 0; a < n_col_in; ++a)
-        CUDA_TRY(cudaMemcpyAsync(st_col_in + (size_t)a * ncol, in_ptrs[col_in[a]], col_b, cudaMemcpyHostToDevice, h->s_in));
-    for (int k = 0; k < n_chunks; ++k) {
-        const int64_t c0 = k * per, n = std::min(per, ncol - c0);
-        for (int a = 0; a < n_cell_in; ++a)
-            CUDA_TRY(cudaMemcpyAsync(st_cell_in + ((size_t)a * ncol + c0) * N, in_ptrs[cell_in[a]] + (size_t)c0 * N,
-                                     (size_t)n * N * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
-        CUDA_TRY(cudaEventRecord(h->ev_in[k], h->s_in));
-    }
-    for (int k = 0; k < n_chunks; ++k) {
-        const int64_t c0 = k * per, n = std::min(per, ncol - c0);
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[k], 0));
-        if (k == 0 && n_col_in) {
-            clb::ManyFields f = {};
-            for (int a = 0; a < n_col_in; ++a) {
-                f.dst[a] = h->field[in_fields[col_in[a]]];
-                f.src[a] = st_col_in + (size_t)a * ncol;
-            }
-            clb::k_copy_many<<<dim3((unsigned)((ncol + 255) / 256), n_col_in), 256, 0, h->stream>>>(f, ncol);
-        }
-        const dim3 tiles((unsigned)((n + clb::kTileCols - 1) / clb::kTileCols), 1);
-        if (n_cell_in) {
-            clb::ManyFields f = {};
-            for (int a = 0; a < n_cell_in; ++a) {
-                f.dst[a] = h->field[in_fields[cell_in[a]]] + c0;
-                f.src[a] = st_cell_in + ((size_t)a * ncol + c0) * N;
-            }
-            clb::k_relayout_many<<<dim3(tiles.x, n_cell_in), 256, tile_smem, h->stream>>>(f, h->sl, h->sc, 1, N, N, n);
-        }
-        const clb::DevView P = shift_view(V, c0, n);
-        if (N == 15) TRY((launch_quad_n<15, true>(h, P, dtgamma, max_iters, c0)));
-        else TRY((launch_quad_n<16, true>(h, P, dtgamma, max_iters, c0)));
-        if (n_cell_out) {
-            clb::ManyFields f = {};
-            for (int a = 0; a < n_cell_out; ++a) {
-                f.dst[a] = st_cell_out + ((size_t)a * ncol + c0) * N;
-                f.src[a] = h->field[out_fields[cell_out[a]]] + c0;
-            }
-            clb::k_relayout_many<<<dim3(tiles.x, n_cell_out), 256, tile_smem, h->stream>>>(f, 1, N, h->sl, h->sc, N, n);
-        }
-        if (k == n_chunks - 1 && n_col_out) {
-            clb::ManyFields f = {};
-            for (int a = 0; a < n_col_out; ++a) {
-                f.dst[a] = st_col_out + (size_t)a * ncol;
-                f.src[a] = h->field[out_fields[col_out[a]]];
-            }
-            clb::k_copy_many<<<dim3((unsigned)((ncol + 255) / 256), n_col_out), 256, 0, h->stream>>>(f, ncol);
-        }
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(h->ev_out[k], h->stream));
-        CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_out[k], 0));
-        for (int a = 0; a < n_cell_out; ++a)
-            CUDA_TRY(cudaMemcpyAsync(out_ptrs[cell_out[a]] + (size_t)c0 * N, st_cell_out + ((size_t)a * ncol + c0) * N,
-                                     (size_t)n * N * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
-    }
-    for (int a = 0; a < n_col_out; ++a)
-        CUDA_TRY(cudaMemcpyAsync(out_ptrs[col_out[a]], st_col_out + (size_t)a * ncol, col_b, cudaMemcpyDeviceToHost, h->s_out));
-    CUDA_TRY(cudaEventRecord(h->ev_done, h->s_out));
-    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_done, 0));  // later work on the handle's stream is ordered after the read-back
-    nvtxRangePop();
-    CUDA_TRY(cudaStreamSynchronize(h->s_out));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return 1;
-}
-
-}  // namespace
-
-// ---- SoilCO2Model implicit diffusion (soil_co2.cuh) ----------------------------------------------------
-namespace {
-
-// mode: 0 boundary fluxes, 1 tendency, 2 Jacobian, 3 fused stage
-int co2_launch(clb_handle h, int mode, double dtg, int max_iters, const char *who)
-{
-    TRY(check_handle(h));
-    DeviceGuard guard(h->cfg.device);
-    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
-    if (h->cfg.n_levels > clb::kCo2MaxLevels)
-        return fail(CLB_ERR_INVALID, "%s: at most %d levels", who, clb::kCo2MaxLevels);
-    static const int Y[2] = {CLB_F_CO2_Y, CLB_F_O2_Y}, D[2] = {CLB_F_CO2_D, CLB_F_O2_D};
-    static const int TH[2] = {CLB_F_CO2_THETA_EFF, CLB_F_O2_THETA_EFF}, DY[2] = {CLB_F_CO2_DY, CLB_F_O2_DY};
-    static const int TOP[2] = {CLB_F_CO2_TOP_BC, CLB_F_O2_TOP_BC}, BOT[2] = {CLB_F_CO2_BOT_BC, CLB_F_O2_BOT_BC};
-    static const int ATM[2] = {CLB_F_CO2_C_ATM, CLB_F_O2_C_ATM}, DFL[2] = {CLB_F_CO2_DFLUXBCDY, CLB_F_O2_DFLUXBCDY};
-    static const int LO[2] = {CLB_F_CO2_W_LO, CLB_F_O2_W_LO}, DI[2] = {CLB_F_CO2_W_DI, CLB_F_O2_W_DI};
-    static const int UP[2] = {CLB_F_CO2_W_UP, CLB_F_O2_W_UP};
-    clb::Co2View V;
-    for (int k = 0; k < 2; ++k) {
-        TRY(require(h, {Y[k], D[k], TH[k]}, who));
-        TRY(alloc_fields(h, {TOP[k], BOT[k]}));  // flux values default to zero
-        if (h->co2_top_state[k]) {
-            TRY(require(h, {ATM[k]}, who));
-            TRY(alloc_fields(h, {DFL[k]}));
-            if (mode == 2 && !h->field_set[DFL[k]]) return fail(CLB_ERR_UNSET, "%s: call clb_soilco2_update_boundary_fluxes first", who);
-        }
-        if (mode == 1) TRY(alloc_fields(h, {DY[k]}));
-        if (mode == 2) TRY(alloc_fields(h, {LO[k], DI[k], UP[k]}));
-        double *const *F = h->field;
-        clb::Co2Species &S = V.s[k];
-        S.C = F[Y[k]]; S.D = F[D[k]]; S.theta_eff = F[TH[k]];
-        S.top_bc = F[TOP[k]]; S.bot_bc = F[BOT[k]];
-        S.c_atm = h->co2_top_state[k] ? F[ATM[k]] : nullptr;
-        S.dflux = F[DFL[k]]; S.dC = F[DY[k]];
-        S.lo = F[LO[k]]; S.di = F[DI[k]]; S.up = F[UP[k]];
-    }
-    const clb::DevView P = make_view(h);
-    const dim3 grid(grid_for(P.ncol), 2);
-    nvtxRangePushA(who);
-    switch (mode) {
-    case 0: clb::k_co2<0, 0><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters); break;
-    case 1: clb::k_co2<1, 0><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters); break;
-    case 2: clb::k_co2<2, 0><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters); break;
-    default:
-        if (P.N == 15) clb::k_co2<3, 15><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters);  // column in registers
-        else clb::k_co2<3, 0><<<grid, kBlock, 0, h->stream>>>(P, V, dtg, max_iters);
-        break;
-    }
-    nvtxRangePop();
-    CUDA_TRY(cudaGetLastError());
-    return CLB_OK;
-}
-
-}  // namespace
 
 extern "C" {
 
