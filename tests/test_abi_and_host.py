@@ -98,10 +98,6 @@ def test_shard_ranges_partition_the_columns():
             assert max(sizes) - min(sizes) <= 1
 
 
-if __name__ == "__main__":
-    sys.exit(pytest.main([__file__, "-q"]))
-
-
 def test_julia_binding_matches_header():
     """julia/ClimaLandB200.jl (the reference-side ccall binding) cannot run here (no Julia): keep its
     field enum, ABI version and every ccall'ed symbol in step with include/climaland_b200.h."""
@@ -116,3 +112,7 @@ def test_julia_binding_matches_header():
     assert ["CLB_" + n for n in names] == [k for _, k in header]
     for sym in set(re.findall(r"ccall\(\(:(clb_\w+)", src)):
         assert sym in cl._lib.EXPORTS, sym
+
+
+if __name__ == "__main__":
+    sys.exit(pytest.main([__file__, "-q"]))
