@@ -975,6 +975,28 @@ int clb_get_field(clb_handle h, int32_t field, double *dst, int64_t stride_level
     return CLB_OK;
 }
 
+static int field_axpby(clb_handle h, int32_t y, double a, int32_t x, double b, const char *who)
+{
+    TRY(check_handle(h));
+    const bool cell = is_cell_field(y);
+    if (!(cell || is_col_field(y)) || !(is_cell_field(x) || is_col_field(x)) || cell != is_cell_field(x))
+        return fail(CLB_ERR_INVALID, "%s: two per-cell or two per-column field ids expected", who);
+    if (!h->field[x]) return fail(CLB_ERR_UNSET, "%s: field %d was never set or computed", who, x);
+    if (b != 0.0 && !h->field[y]) return fail(CLB_ERR_UNSET, "%s: field %d was never set or computed", who, y);
+    DeviceGuard guard(h->cfg.device);
+    TRY(ensure_field(h, y));
+    const int64_t n = cell ? (int64_t)h->cell_elems : h->ld;
+    clb::k_axpby<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->field[y], h->field[x], a, b, n);
+    CUDA_TRY(cudaGetLastError());
+    h->field_set[y] = true;
+    if (is_closure_param(y)) h->prep_dirty = true;
+    if (is_invariant_param(y)) h->param_write_pending = true;
+    return CLB_OK;
+}
+
+int clb_field_axpy(clb_handle h, int32_t y, double a, int32_t x) { return field_axpby(h, y, a, x, 1.0, "clb_field_axpy"); }
+int clb_field_copy(clb_handle h, int32_t dst, int32_t src) { return field_axpby(h, dst, 1.0, src, 0.0, "clb_field_copy"); }
+
 int clb_fill_field(clb_handle h, int32_t field, double value)
 {
     TRY(check_handle(h));

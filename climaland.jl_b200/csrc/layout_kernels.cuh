@@ -119,6 +119,15 @@ __global__ void __launch_bounds__(256) k_scatter_cols(const double *__restrict__
     if (c < ncol) dst[(idx ? idx[c] : c) * sc] = mirror[c];
 }
 
+// y <- a x + b y over a whole mirror (pads included: they are never read back).  Product and sum are rounded
+// separately, as Julia's broadcast `@. y + a * x` is (no muladd).
+__global__ void __launch_bounds__(256) k_axpby(double *__restrict__ y, const double *__restrict__ x, double a, double b,
+                                               int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) y[k] = (b == 0.0) ? a * x[k] : __dadd_rn(__dmul_rn(b, y[k]), __dmul_rn(a, x[k]));
+}
+
 __global__ void __launch_bounds__(256) k_fill(double *__restrict__ p, int64_t n, double v)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -127,6 +127,13 @@ class SoilColumnSolver:
         check(self.L.clb_get_field(self.h, fid, ptr, 1, sc, mem))
         return out
 
+    def axpy(self, y, a, x):
+        """y <- y + a x on the device mirrors (the integrator's explicit update)."""
+        check(self.L.clb_field_axpy(self.h, field_id(y), float(a), field_id(x)))
+
+    def copy(self, dst, src):
+        check(self.L.clb_field_copy(self.h, field_id(dst), field_id(src)))
+
     def device_ptr(self, name):
         p, sl, sc = C.c_void_p(), C.c_int64(), C.c_int64()
         check(self.L.clb_field_device_ptr(self.h, field_id(name), C.byref(p), C.byref(sl), C.byref(sc)))

@@ -223,6 +223,14 @@ int clb_fill_field(clb_handle h, int32_t field, double value);
 int clb_field_device_ptr(clb_handle h, int32_t field, double **ptr, int64_t *stride_level,
                          int64_t *stride_column);
 
+/* Resident state: with the explicit-stage kernels below, a whole soil step can stay in the
+ * library's mirrors; the integrator's own vector operations on them are these two.
+ *   clb_field_axpy   y <- y + a x   (ARS111's explicit update U0 = u + dt T_exp(u); ClimaTimeSteppers' broadcasts)
+ *   clb_field_copy   dst <- src
+ * x / y / dst / src: two per-cell or two per-column field ids. */
+int clb_field_axpy(clb_handle h, int32_t y, double a, int32_t x);
+int clb_field_copy(clb_handle h, int32_t dst, int32_t src);
+
 /* ---- the hooks, fine-grained (parity-checkable per call) ----------------- */
 /* update_implicit_cache!(p, Y, t): models.jl:238-246.  Richards: K, psi,
  * total_water and, if the top BC is MoistureStateBC, the boundary fluxes and

@@ -150,14 +150,14 @@ def test_energy_hydrology_one_day_with_the_explicit_stage_on_the_device(math_mod
         U.theta_i += dt * di
         P.implicit_step(U, dt, iters, p=p)
         froze, thawed = max(froze, di.max()), max(thawed, -di.min())
-        # ---- CUDA: the same, the lagged fields never leave the device
+        # ---- CUDA: the same; nothing leaves the device during the day (resident state)
         s.set("dye_theta_l", 0.0)
         s.set("dye_theta_i", 0.0)
         s.update_aux_and_phase_change()
         s.update_runoff()
-        s.set("top_bc_w", s.get("infiltration"))
-        s.set("y_theta_l", s.get("y_theta_l") + dt * s.get("dye_theta_l"))
-        s.set("y_theta_i", s.get("y_theta_i") + dt * s.get("dye_theta_i"))
+        s.copy("top_bc_w", "infiltration")
+        s.axpy("y_theta_l", dt, "dye_theta_l")      # the integrator's U0 = u + dt T_exp(u), on the device
+        s.axpy("y_theta_i", dt, "dye_theta_i")
         s.implicit_step(dt, iters)
     assert froze > 0.0 and thawed > 0.0, "the day must freeze and thaw somewhere"
     assert R.h_grad.max() > 0.0 and R.R_ss.max() > 0.0
