@@ -74,6 +74,10 @@ template <int MATH>
 __device__ __forceinline__ double ex(double x) { return (MATH == kMathLibm) ? exp(x) : texp(x); }
 template <int MATH>
 __device__ __forceinline__ double lg(double x) { return (MATH == kMathLibm) ? log(x) : fm::log(x); }
+// a / b: IEEE division (with its slow-path branch) in LIBM mode, the branch-free division of soil_math.cuh
+// (MUFU seed + Newton + residual correction; normal finite b != 0) in FAST mode
+template <int MATH>
+__device__ __forceinline__ double dv(double a, double b) { return (MATH == kMathLibm) ? a / b : fm::div(a, b); }
 
 // soil_hydrology_parameterizations.jl:59-63 / :182-186
 template <int CLOSURE, int MATH>
@@ -82,9 +86,9 @@ __device__ __forceinline__ double matric_potential(const HydroCell &p, double S)
     if (CLOSURE == kVanGenuchten) {
         if (MATH == kMathLibm) return -pw<MATH>((pw<MATH>(S, -1.0 / p.m) - 1.0) * pw<MATH>(p.a, -p.b), 1.0 / p.b);
         // (u alpha^-n)^(1/n) = u^(1/n) / alpha
-        return -(pw<MATH>(pw<MATH>(S, -1.0 / p.m) - 1.0, 1.0 / p.b) / p.a);
+        return -dv<MATH>(pw<MATH>(pw<MATH>(S, -fm::rcp(p.m)) - 1.0, fm::rcp(p.b)), p.a);
     }
-    return p.b * pw<MATH>(S, -1.0 / p.a);
+    return p.b * pw<MATH>(S, -dv<MATH>(1.0, p.a));
 }
 
 // soil_hydrology_parameterizations.jl:72-77 / :195-200 (psi > 0 is an error upstream: NaN here)
@@ -93,14 +97,15 @@ __device__ __forceinline__ double inverse_matric_potential(const HydroCell &p, d
 {
     if (psi > 0.0) return NAN;
     if (CLOSURE == kVanGenuchten) return pw<MATH>(1.0 + pw<MATH>(p.a * fabs(psi), p.b), -p.m);
-    return pw<MATH>(psi / p.b, -p.a);
+    return pw<MATH>(dv<MATH>(psi, p.b), -p.a);
 }
 
+template <int MATH>
 __device__ __forceinline__ double effective_saturation(double nu_eff, double theta, double theta_r)
 {
     const double theta_safe = fmax(theta, theta_r + kSqrtEps);
     const double nu_safe = fmax(nu_eff, theta_r + kSqrtEps);
-    return (theta_safe - theta_r) / (nu_safe - theta_r);
+    return dv<MATH>(theta_safe - theta_r, nu_safe - theta_r);
 }
 
 // soil_heat_parameterizations.jl:35-52; rho_first / rho_second are the positional (_rho_ice, _rho_liq):
@@ -110,9 +115,9 @@ __device__ __forceinline__ double soil_Tf_depressed(const HydroCell &p, double t
                                                     double rho_second, const ExplicitConst &k, double LH_f0,
                                                     double &psi_w0)
 {
-    const double theta_tot = fmin(rho_first / rho_second * theta_i + theta_l, p.nu);
-    psi_w0 = matric_potential<CLOSURE, MATH>(p, effective_saturation(p.nu, theta_tot, p.theta_r));
-    return fmax(k.T_freeze * ex<MATH>(k.grav * psi_w0 / LH_f0), 1.0);
+    const double theta_tot = fmin(rho_first / rho_second * theta_i + theta_l, p.nu);  // uniform operands: hoisted
+    psi_w0 = matric_potential<CLOSURE, MATH>(p, effective_saturation<MATH>(p.nu, theta_tot, p.theta_r));
+    return fmax(k.T_freeze * ex<MATH>(dv<MATH>(k.grav * psi_w0, LH_f0)), 1.0);
 }
 
 // soil_heat_parameterizations.jl:243-254
@@ -123,7 +128,8 @@ __device__ __forceinline__ double kappa_sat(double theta_l, double theta_i, doub
     if (theta_w < kEps) return (ku + kf) / 2.0;
     if (MATH == kMathLibm) return pw<MATH>(ku, theta_l / theta_w) * pw<MATH>(kf, theta_i / theta_w);
     if (theta_i == 0.0) return ku;  // ku^1 * kf^0
-    return texp((theta_l / theta_w) * tlog(ku) + (theta_i / theta_w) * tlog(kf));
+    const double rw = fm::rcp(theta_w);
+    return texp((theta_l * rw) * tlog(ku) + (theta_i * rw) * tlog(kf));
 }
 
 // soil_heat_parameterizations.jl:301-323
@@ -136,7 +142,7 @@ __device__ __forceinline__ double kersten_number(double theta_i, double S_r, dou
             return pw<MATH>(S_r, (1.0 + om - alpha * quartz - gravel) / 2.0) *
                    pw<MATH>(pw<MATH>(1.0 + ex<MATH>(-beta * S_r), -3.0) - pw<MATH>((1.0 - S_r) / 2.0, 3.0), 1.0 - om);
         const double e1 = 1.0 + texp(-beta * S_r), h = (1.0 - S_r) / 2.0;
-        const double base = 1.0 / (e1 * e1 * e1) - h * h * h;
+        const double base = fm::rcp(e1 * e1 * e1) - h * h * h;
         // S_r^a * base^b = exp(a log S_r + b log base)
         if (!(base > 0.0)) return (base == 0.0) ? 0.0 : NAN;  // pow(0, b > 0) = 0; a negative base is a DomainError upstream
         return texp(((1.0 + om - alpha * quartz - gravel) / 2.0) * tlog(S_r) + (1.0 - om) * tlog(base));
@@ -168,12 +174,12 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
             const double nu_safe = fmax(cell.nu - thi, cell.theta_r + kSqrtEps);
             theta_l = (theta_safe < nu_safe) ? theta_safe : nu_safe;
         }
-        const double S_r = (theta_l + thi) / cell.nu;
+        const double S_r = dv<MATH>(theta_l + thi, cell.nu);
         const double K_e = kersten_number<MATH>(thi, S_r, X.k.alpha, X.k.beta, __ldg(X.nu_ss_om + q),
                                                 __ldg(X.nu_ss_quartz + q), __ldg(X.nu_ss_gravel + q));
         const double ks = kappa_sat<MATH>(theta_l, thi, __ldg(X.kappa_sat_unfrozen + q), __ldg(X.kappa_sat_frozen + q));
         kappa = K_e * ks + (1.0 - K_e) * __ldg(X.kappa_dry + q);
-        T = temperature_from_rho_e_int(P.Y_rho_e[q], thi, volumetric_heat_capacity(theta_l, thi, rcds, E), E);
+        T = E.T_ref + dv<MATH>(P.Y_rho_e[q] + thi * E.rho_i * E.LH_f0, volumetric_heat_capacity(theta_l, thi, rcds, E));
         // K = impedance * viscosity * hydraulic_conductivity(effective_saturation(nu, theta_l(Y), theta_r))
         double Kh, psi, d0, d1;
         if (MATH == kMathFast && thi == 0.0) {  // nu - theta_i == nu: one closure evaluation gives K and psi
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
             CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, false, false>(th, Kh, d0, d1);
             CellEval<CLOSURE, MATH>(cell, cell.nu - thi).template eval<false, true, false>(th, d0, psi, d1);
         }
-        const double f_i = thi / (theta_l + thi - cell.theta_r);
+        const double f_i = dv<MATH>(thi, theta_l + thi - cell.theta_r);
         const double imp = (MATH == kMathLibm) ? pow(10.0, -X.k.Omega * f_i)
                                                : ((thi == 0.0) ? 1.0 : texp((-X.k.Omega * f_i) * 2.302585092994045684));
         const double visc = ex<MATH>(X.k.gamma * (T - X.k.gammaT_ref));
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
     }
     if (PHASE) {
         const double dz = P.dz_c[i];
-        const double tau = 3.0 * volumetric_heat_capacity(theta_l, thi, rcds, E) * (dz * dz) / kappa;
+        const double tau = dv<MATH>(3.0 * volumetric_heat_capacity(theta_l, thi, rcds, E) * (dz * dz), kappa);
         double psi_w0, Tf;
         if (AUX && MATH == kMathFast && thi == 0.0) {  // without ice the density ratio does not enter theta_tot
             Tf = Tf_aux;
@@ -208,10 +214,10 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
         } else {
             Tf = soil_Tf_depressed<CLOSURE, MATH>(cell, theta_l, thi, E.rho_i, E.rho_l, X.k, E.LH_f0, psi_w0);
         }
-        const double psi_T = E.LH_f0 / X.k.grav * lg<MATH>(T / Tf) * heaviside(Tf - T);
+        const double psi_T = E.LH_f0 / X.k.grav * lg<MATH>(dv<MATH>(T, Tf)) * heaviside(Tf - T);
         const double theta_star =
             inverse_matric_potential<CLOSURE, MATH>(cell, psi_w0 + psi_T) * (cell.nu - cell.theta_r) + cell.theta_r;
-        const double s = (theta_l - theta_star) / tau;
+        const double s = dv<MATH>(theta_l - theta_star, tau);
         X.dYe_theta_l[q] += -s;
         X.dYe_theta_i[q] += (E.rho_l / E.rho_i) * s;
     }
