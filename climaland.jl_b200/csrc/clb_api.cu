@@ -372,17 +372,25 @@ int encode_tiled_fn(EncodeTiledFn *out)
 
 // TMA descriptor of one column-fastest per-cell mirror: dims {ncol, N} (columns beyond ncol read as 0),
 // row pitch ld doubles, box {columns of one warp, N levels}.
-int encode_field_map(clb_handle h, const double *ptr, int box_columns, CUtensorMap *map)
+int encode_field_map(clb_handle h, const double *ptr, int box_columns, int box_levels_lf, CUtensorMap *map)
 {
     EncodeTiledFn enc;
     TRY(encode_tiled_fn(&enc));
-    const cuuint64_t dims[2] = {(cuuint64_t)h->cfg.n_columns, (cuuint64_t)h->cfg.n_levels};
-    const cuuint64_t strides[1] = {(cuuint64_t)h->ld * sizeof(double)};
-    const cuuint32_t box[2] = {(cuuint32_t)box_columns, (cuuint32_t)h->cfg.n_levels};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (h->sc == 1) {  // column-fastest mirror: dims {columns, levels}, box {box_columns, N}
+        const cuuint64_t dims[2] = {(cuuint64_t)h->cfg.n_columns, (cuuint64_t)h->cfg.n_levels};
+        const cuuint64_t strides[1] = {(cuuint64_t)h->ld * sizeof(double)};
+        const cuuint32_t box[2] = {(cuuint32_t)box_columns, (cuuint32_t)h->cfg.n_levels};
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {  // level-fastest mirror: dims {levels, columns}, box {box_levels_lf >= N (the rest is zero-filled), box_columns}
+        const cuuint64_t dims[2] = {(cuuint64_t)h->cfg.n_levels, (cuuint64_t)h->cfg.n_columns};
+        const cuuint64_t strides[1] = {(cuuint64_t)h->cfg.n_levels * sizeof(double)};
+        const cuuint32_t box[2] = {(cuuint32_t)box_levels_lf, (cuuint32_t)box_columns};
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) return fail(CLB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return CLB_OK;
 }
@@ -420,7 +428,7 @@ int ensure_prepared(clb_handle h, const clb::DevView &P)
 
 // Fields of the lane-quad kernel in the order of its shared-memory slots (soil_pair.cuh); the closure
 // parameters S_s / a / b / m come from the prepared mirrors
-int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::PairMaps *maps)
+int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, int box_levels_lf, clb::PairMaps *maps)
 {
     TRY(ensure_prepared(h, P));
     const double *const *Q = h->prep;
@@ -434,7 +442,7 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::Pa
     h->pair_map_box = box_columns;
     for (int j = 0; j < n; ++j) {
         if (h->pair_map_src[j] != src[j]) {  // descriptors are cached per handle; mirrors rarely move
-            if (src[j]) TRY(encode_field_map(h, src[j], box_columns, &h->pair_maps.m[j]));
+            if (src[j]) TRY(encode_field_map(h, src[j], box_columns, box_levels_lf, &h->pair_maps.m[j]));
             h->pair_map_src[j] = src[j];
         }
     }
@@ -451,13 +459,14 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, clb::Pa
 //                     registers), double-buffered tiles of 4 columns: 2 x 14 slots x 512 B per warp
 //   octet, N = 50     8 lanes x 7 cells (56 level rows); persistent, single-buffered tiles of 4 columns (1.75 KB per
 //                     slot) with an L2 prefetch of the next tile; 8 (Richards) or 6 (EnergyHydrology) warps per SM
-template <int CLOSURE, int MODEL, int N, int PARTS, int Q, int NS, int NBUF, int BLOCK, int MINB, bool PERSISTENT>
+template <int CLOSURE, int MODEL, int N, int PARTS, int Q, int NS, int NBUF, int BLOCK, int MINB, bool PERSISTENT,
+          bool LF = false>
 int launch_lanes(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0)
 {
     using Gm = clb::LaneGeom<PARTS, Q>;
     constexpr int CPW = Gm::CPW;
-    auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB, Q>;
-    const size_t smem = clb::pair_smem_bytes<PARTS, NS, NBUF, BLOCK, Q>();
+    auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB, Q, LF>;
+    const size_t smem = clb::pair_smem_bytes<PARTS, NS, NBUF, BLOCK, Q, LF>();
     static bool configured = false;  // per instantiation
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -477,7 +486,7 @@ int launch_lanes(clb_handle h, const clb::DevView &P, double dtg, int max_iters,
     clb::PairMaps maps;
     // the descriptors always describe the whole mirrors (P may be a column sub-range with shifted pointers;
     // its offset travels as g.col0)
-    TRY(make_pair_maps(h, col0 ? make_view(h) : P, CPW, &maps));
+    TRY(make_pair_maps(h, col0 ? make_view(h) : P, CPW, Gm::kRowsLF, &maps));
     // programmatic dependent launch: the kernel's prologue (tables, barriers, the first tile's parameter
     // fields) may overlap the tail of the stream's previous kernel unless that kernel may be writing this
     // handle's parameter mirrors
@@ -534,8 +543,10 @@ int launch_octet(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
         constexpr int NS = (MODEL == 1) ? 14 : 11;
         return launch_lanes<CLOSURE, MODEL, N, 4, 2, NS, 2, 512, 1, true>(h, P, dtg, max_iters, 0);
     } else if constexpr (MODEL == 1) {
+        if (h->sc != 1) return launch_lanes<CLOSURE, MODEL, N, 4, 7, 18, 1, 192, 1, true, true>(h, P, dtg, max_iters, 0);
         return launch_lanes<CLOSURE, MODEL, N, 4, 7, 18, 1, 192, 1, true>(h, P, dtg, max_iters, 0);
     } else {
+        if (h->sc != 1) return launch_lanes<CLOSURE, MODEL, N, 4, 7, 11, 1, 256, 1, true, true>(h, P, dtg, max_iters, 0);
         return launch_lanes<CLOSURE, MODEL, N, 4, 7, 11, 1, 256, 1, true>(h, P, dtg, max_iters, 0);
     }
 }
@@ -556,8 +567,9 @@ bool pair_variant_applies(clb_handle h, bool octet = false)
     if (h->cfg.math_mode != CLB_MATH_FAST) return false;
     // a MoistureStateBC top re-evaluates the boundary fluxes every iteration (rre.jl:460-468): lane-per-cell kernel
     if (h->cfg.model == CLB_RICHARDS && h->cfg.top_bc == 1) return false;
-    // its TMA boxes are cut from column-fastest mirrors
-    if (h->cfg.layout == CLB_LAYOUT_LEVEL_FASTEST) return false;
+    // the TMA boxes of the N = 15 / 16 kernels are cut from column-fastest mirrors; the N = 50 octet also reads
+    // level-fastest ones (a tile is then one contiguous piece of each field)
+    if (h->cfg.layout == CLB_LAYOUT_LEVEL_FASTEST && !(octet && N == 50)) return false;
     return true;
 }
 
@@ -729,7 +741,12 @@ int clb_create(clb_handle *out, const clb_config *cfg)
                               cfg->kernel_variant == CLB_VARIANT_LANE_OCTET);
         const bool lane_per_cell = cfg->n_levels <= 31 && (cfg->kernel_variant == CLB_VARIANT_AUTO ||
                                                            cfg->kernel_variant == CLB_VARIANT_LANE_PER_CELL);
-        layout = (!quad_ok && lane_per_cell) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
+        // the N = 50 octet reads either layout; level-fastest (the reference's own) keeps a tile's 50 rows of a field
+        // contiguous, so its rate does not depend on the number of columns (column-fastest: rows ld * 8 bytes apart)
+        const bool octet50 = cfg->n_levels == 50 && cfg->math_mode == CLB_MATH_FAST &&
+                             !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
+                             (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_OCTET);
+        layout = ((!quad_ok && lane_per_cell) || octet50) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
     }
     h->cfg.layout = layout;
     if (layout == CLB_LAYOUT_LEVEL_FASTEST) {
@@ -1204,11 +1221,12 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     } else if (variant == CLB_VARIANT_AUTO) {
         if (pair_variant_applies(h))
             variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
-        else if (pair_variant_applies(h, true) && (int64_t)h->ld * N * 8 <= (int64_t)80 << 20)
-            // N = 50.  A tile of the octet touches all 50 level rows of every field at once; in column-fastest
-            // mirrors these lie ld * 8 bytes apart, and as the fields grow the tile's ~550 pages fall out of the TLB
-            // (measured against the generic kernel, tools/n50_crossover.py: 2.1x faster at 1e5 columns, 1.2x at
-            // 1.5e5, equal at ~2.2e5 = 88 MB per field, 1.7x slower at 1e6)
+        else if (pair_variant_applies(h, true) && (level_fast || (int64_t)h->ld * N * 8 <= (int64_t)80 << 20))
+            // N = 50.  A tile of the octet touches all 50 level rows of every field at once.  In level-fastest mirrors
+            // (what CLB_LAYOUT_AUTO picks for N = 50) they are contiguous.  In column-fastest mirrors they lie
+            // ld * 8 bytes apart and, as the fields grow, the tile's ~550 pages fall out of the TLB (measured against
+            // the generic kernel, tools/n50_crossover.py: 2.1x faster at 1e5 columns, equal at ~2.2e5 = 88 MB per
+            // field, 1.7x slower at 1e6): there the generic kernel takes over above 80 MB per field
             variant = CLB_VARIANT_LANE_OCTET;
         else if (level_fast && N <= 31)
             variant = CLB_VARIANT_LANE_PER_CELL;

@@ -28,7 +28,8 @@
 //     tile (14 instructions per warp instead of 1800 per-lane loads), where it is transformed
 //     in place into the stage constants; the new state is written once.
 //
-// Requires the column-fastest mirror layout (sl = ld, sc = 1).
+// Mirror layout: column-fastest (sl = ld, sc = 1) by default; LF = true reads level-fastest mirrors (sl = 1, sc = N,
+// N even: TMA needs 16-byte global strides), where a tile is one contiguous piece of each field.
 //
 // Inward flux convention: F_f is the flux through face f in the direction boundary -> seam
 // (upward in the bottom half, downward in the top half), so for both halves
@@ -90,8 +91,10 @@ struct PairMaps {
     CUtensorMap m[14];
 };
 
-// Q cells per lane, CPW columns per warp: a slot of the warp tile is [NR level rows][CPW columns].
-template <int NS, int NTOT, int Q, int CPW, int NR = 16>
+// Q cells per lane, CPW columns per warp.  A slot of the warp tile is [NR level rows][CPW columns] when the boxes
+// come from column-fastest mirrors (RS = 0), or [CPW columns][RS >= NR level rows] when they come from level-fastest
+// mirrors (the reference's own layout: a tile is then ONE contiguous piece of each field).
+template <int NS, int NTOT, int Q, int CPW, int NR = 16, int RS = 0, int SE = 0>
 struct PairStore {
     double *base;  // warp tile + this lane's column
     int half, r0;  // r0: first slot of this lane within its half (0, or Q for the inner lane of a quad)
@@ -100,7 +103,8 @@ struct PairStore {
     __device__ __forceinline__ double *at(int q, int slot) const
     {
         const int row = half ? NR - 1 - (r0 + q) : r0 + q;
-        return base + (slot * NR + row) * CPW;
+        if constexpr (RS > 0) return base + slot * SE + row;  // base = tile + column * RS; SE doubles per slot
+        return base + (slot * NR + row) * CPW;                        // base = tile + column
     }
     template <int SLOT>
     __device__ __forceinline__ double get(int q) const
@@ -236,6 +240,11 @@ struct LaneGeom {
     static constexpr int SEAM = CPW;          // xor mask: the other half of the column
     static constexpr int PARTD = 2 * CPW;     // lane distance to the next part of this half
     static constexpr int kSlotBytes = NR * CPW * 8;  // one slot of a warp tile: NR level rows x CPW columns
+    // level-fastest tiles: rows per column in shared memory = the TMA box's level extent, >= NR, a multiple of 2
+    // (16-byte box rows) chosen so that the CPW columns of a row fall on different banks (NR = 56 -> 58: column
+    // stride 116 words = 20 mod 32)
+    static constexpr int kRowsLF = NR + 2;
+    static constexpr int kSlotBytesLF = (kRowsLF * CPW * 8 + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
 };
 
 // value of the previous (outer) / next (inner) part's lane of this half; own value where there is none
@@ -263,10 +272,11 @@ __device__ __forceinline__ void nb_exchange(double first, double last, bool inne
 }
 
 // Dynamic shared memory of a block: the log / exp tables, then NBUF NS-slot tiles and NBUF mbarriers per warp.
-template <int PARTS, int NS, int NBUF, int BLOCK, int Q = kPairQ / PARTS>
+template <int PARTS, int NS, int NBUF, int BLOCK, int Q = kPairQ / PARTS, bool LF = false>
 __host__ __device__ constexpr size_t pair_smem_bytes()
 {
-    return (size_t)fmv::kMathTabBytes + (size_t)(BLOCK / 32) * NBUF * (NS * LaneGeom<PARTS, Q>::kSlotBytes + 8);
+    using Gm = LaneGeom<PARTS, Q>;
+    return (size_t)fmv::kMathTabBytes + (size_t)(BLOCK / 32) * NBUF * (NS * (LF ? Gm::kSlotBytesLF : Gm::kSlotBytes) + 8);
 }
 
 // Per-column scalars of a tile, fetched one tile ahead into registers.
@@ -295,7 +305,8 @@ __device__ __forceinline__ ColScalars load_col_scalars(const DevView &P, int64_t
 // PERSISTENT: every warp walks over tiles (CPW columns each) t = warp, warp + nwarps, ...; with
 // NBUF = 2 the TMA boxes and the per-column scalars of the next tile are requested before the
 // current tile is touched, so HBM latency hides behind a whole tile of FP64 work.
-template <int CLOSURE, int MODEL, int N, int PARTS, int NS, int NBUF, int BLOCK, int MINB, int QC = kPairQ / PARTS>
+template <int CLOSURE, int MODEL, int N, int PARTS, int NS, int NBUF, int BLOCK, int MINB, int QC = kPairQ / PARTS,
+          bool LF = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
     k_step_lanes(const DevView P, const PairGridT<PARTS * QC> G, const __grid_constant__ PairMaps M, double dtg,
                  int max_iters)
@@ -326,10 +337,12 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     const EarthConst &E = P.earth;
     const double C1 = E.cp_l * E.rho_l, C2 = E.cp_i * E.rho_i, T_ref = E.T_ref;
 
-    constexpr size_t kTileBytes = (size_t)NS * Gm::kSlotBytes;
+    constexpr int kSlotB = LF ? Gm::kSlotBytesLF : Gm::kSlotBytes;  // one field of a tile
+    constexpr int RS = LF ? Gm::kRowsLF : 0;
+    constexpr size_t kTileBytes = (size_t)NS * kSlotB;
     unsigned char *const tiles = pair_sm + (size_t)wib * NBUF * kTileBytes;
     const unsigned bar0 = smem_u32(pair_sm + (size_t)(BLOCK / 32) * NBUF * kTileBytes + (size_t)wib * NBUF * 8);
-    PairStore<NS, NTOT, Q, CPW, NR> S;
+    PairStore<NS, NTOT, Q, CPW, NR, RS, kSlotB / 8> S;
     S.half = half;
     S.r0 = r0;
     auto level_of = [&](int q) { return half ? NR - 1 - (r0 + q) : r0 + q; };
@@ -345,13 +358,17 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     auto request_tile = [&](int64_t t, int buf, int which) {
         const unsigned bar = bar0 + buf * 8;
         if (which & 1) {
-            if (lane == 0) mbar_expect_tx(bar, (unsigned)(NRAW - ((CLOSURE == kVanGenuchten) ? 0 : 1)) * N * CPW * 8);
+            // bytes of a box: out-of-bounds rows of a level-fastest box (levels >= N, zero-filled) count as well
+            if (lane == 0)
+                mbar_expect_tx(bar, (unsigned)(NRAW - ((CLOSURE == kVanGenuchten) ? 0 : 1)) * (LF ? Gm::kRowsLF : N) * CPW * 8);
             __syncwarp();
         }
         const bool skip = (CLOSURE != kVanGenuchten) && lane == ((MODEL == 1) ? 5 : 6);  // no m field for Brooks-Corey
         const bool mine = is_param(lane) ? (which & 1) : (which & 2);
         if (lane < NRAW && !skip && mine)
-            tma_load_2d(smem_u32(tiles + buf * kTileBytes) + lane * Gm::kSlotBytes, &M.m[lane], G.col0 + (int)(t * CPW), 0, bar);
+            // coordinates in the order of the tensor's dimensions: {column, level} column-fastest, {level, column} level-fastest
+            tma_load_2d(smem_u32(tiles + buf * kTileBytes) + lane * kSlotB, &M.m[lane], LF ? 0 : G.col0 + (int)(t * CPW),
+                        LF ? G.col0 + (int)(t * CPW) : 0, bar);
     };
 
     if (lane == 0) {
@@ -387,7 +404,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         const int64_t tn = tile_id + nwarps;
         if (tn < ntiles) {
             const bool skip = (CLOSURE != kVanGenuchten) && lane == ((MODEL == 1) ? 5 : 6);
-            if (lane < NRAW && !skip) tma_prefetch_l2_2d(&M.m[lane], G.col0 + (int)(tn * CPW), 0);
+            if (lane < NRAW && !skip)
+                tma_prefetch_l2_2d(&M.m[lane], LF ? 0 : G.col0 + (int)(tn * CPW), LF ? G.col0 + (int)(tn * CPW) : 0);
             if (lane >= 16 && lane < 16 + ((MODEL == 1) ? 9 : 5)) {  // the CPW per-column scalars of an array share a line
                 const int j_ = lane - 16;
                 const double *a_ = P.R_ss;
@@ -403,7 +421,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             }
         }
     }
-    S.base = reinterpret_cast<double *>(tiles + buf * kTileBytes) + (lane % CPW);
+    S.base = reinterpret_cast<double *>(tiles + buf * kTileBytes) + (lane % CPW) * (LF ? RS : 1);
 
     const double ld_Rss = cur.Rss, ld_hg = cur.hg;
     const double top_w = cur.top_w, bot_w = cur.bot_w;

@@ -36,7 +36,7 @@ CASES = [
 # (kernel_variant, layout): lane-per-cell on level-fastest mirrors, register-column and generic on
 # column-fastest mirrors, generic on level-fastest mirrors
 VARIANTS = {"lane_per_cell": (3, 2), "register_column": (1, 1), "generic_cf": (2, 1), "generic_lf": (2, 2),
-            "lane_quad": (4, 1), "lane_quad_pipelined": (5, 1), "lane_octet": (6, 1), "auto": (0, 0)}
+            "lane_quad": (4, 1), "lane_quad_pipelined": (5, 1), "lane_octet": (6, 1), "lane_octet_lf": (6, 2), "auto": (0, 0)}
 
 
 def _setup(case):
@@ -76,8 +76,10 @@ def test_fused_step_matches_oracle(case, math_mode, variant):
         pytest.skip("register-column is built for N = 15")
     if variant.startswith("lane_quad") and (N not in (15, 16) or math_mode != 0 or (model == "richards" and top_bc == 1)):
         pytest.skip("lane-quad is built for N = 15 / 16, fast math, flux boundary conditions, column-fastest mirrors")
-    if variant == "lane_octet" and (N not in (15, 16, 50) or math_mode != 0 or (model == "richards" and top_bc == 1)):
-        pytest.skip("lane-octet is built for N = 15 / 16 / 50, fast math, flux boundary conditions, column-fastest mirrors")
+    if variant.startswith("lane_octet") and (N not in (15, 16, 50) or math_mode != 0 or (model == "richards" and top_bc == 1)):
+        pytest.skip("lane-octet is built for N = 15 / 16 / 50, fast math, flux boundary conditions")
+    if variant == "lane_octet_lf" and N != 50:
+        pytest.skip("only the N = 50 octet reads level-fastest mirrors")
     w = _setup(case)
     P, U, p = oracle_problem(w, closure, top_bc, bottom_bc)
     s = cuda_solver(w, closure, top_bc, bottom_bc, math_mode=math_mode, kernel_variant=kv, layout=layout)
