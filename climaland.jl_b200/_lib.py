@@ -93,7 +93,7 @@ def lib():
         "clb_set_field": [h, i32, C.c_void_p, i64, i64, i32],
         "clb_get_field": [h, i32, C.c_void_p, i64, i64, i32],
         "clb_fill_field": [h, i32, d],
-        "clb_field_axpy": [h, i32, d, i32], "clb_field_copy": [h, i32, i32],
+        "clb_field_axpy": [h, i32, d, i32], "clb_field_copy": [h, i32, i32], "clb_ldiv_diagonal": [h, i32, i32, i32],
         "clb_field_device_ptr": [h, i32, C.POINTER(C.c_void_p), C.POINTER(i64), C.POINTER(i64)],
         "clb_set_option": [h, i32, i64],
         "clb_update_implicit_cache": [h], "clb_update_boundary_fluxes": [h],

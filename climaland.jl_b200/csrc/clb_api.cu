@@ -1011,6 +1011,23 @@ static int field_axpby(clb_handle h, int32_t y, double a, int32_t x, double b, c
     return CLB_OK;
 }
 
+int clb_ldiv_diagonal(clb_handle h, int32_t w_field, int32_t b_field, int32_t x_field)
+{
+    TRY(check_handle(h));
+    const int f[3] = {w_field, b_field, x_field};
+    for (int k = 0; k < 3; ++k)
+        if (!(is_cell_field(f[k]) || is_col_field(f[k])) || is_cell_field(f[k]) != is_cell_field(f[0]))
+            return fail(CLB_ERR_INVALID, "clb_ldiv_diagonal: three per-cell or three per-column field ids expected");
+    if (!h->field_set[w_field] || !h->field_set[b_field])
+        return fail(CLB_ERR_UNSET, "clb_ldiv_diagonal: the block (field %d) and the right-hand side (field %d) must be set", w_field, b_field);
+    DeviceGuard guard(h->cfg.device);
+    TRY(alloc_fields(h, {x_field}));
+    const int64_t n = is_cell_field(w_field) ? (int64_t)h->cell_elems : h->ld;
+    clb::k_div<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->field[x_field], h->field[b_field], h->field[w_field], n);
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
 int clb_field_axpy(clb_handle h, int32_t y, double a, int32_t x) { return field_axpby(h, y, a, x, 1.0, "clb_field_axpy"); }
 int clb_field_copy(clb_handle h, int32_t dst, int32_t src) { return field_axpby(h, dst, 1.0, src, 0.0, "clb_field_copy"); }
 

@@ -128,6 +128,14 @@ __global__ void __launch_bounds__(256) k_axpby(double *__restrict__ y, const dou
     if (k < n) y[k] = (b == 0.0) ? a * x[k] : __dadd_rn(__dmul_rn(b, y[k]), __dmul_rn(a, x[k]));
 }
 
+// x <- b / w entry by entry (a DiagonalMatrixRow block)
+__global__ void __launch_bounds__(256) k_div(double *__restrict__ x, const double *__restrict__ b,
+                                             const double *__restrict__ w, int64_t n)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) x[k] = b[k] / w[k];
+}
+
 __global__ void __launch_bounds__(256) k_fill(double *__restrict__ p, int64_t n, double v)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -131,6 +131,10 @@ class SoilColumnSolver:
         """y <- y + a x on the device mirrors (the integrator's explicit update)."""
         check(self.L.clb_field_axpy(self.h, field_id(y), float(a), field_id(x)))
 
+    def ldiv_diagonal(self, w, b, x):
+        """x <- b / w entry by entry: a DiagonalMatrixRow block (surface variables of an integrated model)."""
+        check(self.L.clb_ldiv_diagonal(self.h, field_id(w), field_id(b), field_id(x)))
+
     def copy(self, dst, src):
         check(self.L.clb_field_copy(self.h, field_id(dst), field_id(src)))
 

@@ -153,6 +153,8 @@ typedef enum {
     CLB_F_CO2_TOP_BC, CLB_F_CO2_BOT_BC, CLB_F_O2_TOP_BC, CLB_F_O2_BOT_BC,   /* p.soilco2.{top,bottom}_bc(_o2) */
     CLB_F_CO2_C_ATM, CLB_F_O2_C_ATM,          /* air-equivalent concentration of the atmosphere (state BC value) */
     CLB_F_CO2_DFLUXBCDY, CLB_F_O2_DFLUXBCDY,  /* p.soilco2.dfluxBCdY(_o2) */
+    CLB_F_SFC_W_DI, CLB_F_SFC_B, CLB_F_SFC_X, /* one surface (PointSpace) variable of an integrated model: its
+                                                 DiagonalMatrixRow Jacobian block, right-hand side, solution */
     CLB_F_NUM
 } clb_field;
 
@@ -296,6 +298,14 @@ int clb_soilco2_update_boundary_fluxes(clb_handle h);
 int clb_soilco2_compute_imp_tendency(clb_handle h);
 int clb_soilco2_compute_jacobian(clb_handle h, double dtgamma);
 int clb_soilco2_implicit_step(clb_handle h, double dtgamma, int32_t max_iters);
+
+/* Diagonal Jacobian blocks: the implicit variables of an integrated model that live on the
+ * surface space (canopy.energy.T, src/standalone/Vegetation/canopy_energy.jl:222-250; snow, lake) have
+ * DiagonalMatrixRow blocks (implicit_timestepping.jl:117-121), solved entry by entry: x = b / w.  With this the
+ * whole ldiv! of SoilCanopyModel / LandModel stays on the device: clb_ldiv for the soil blocks,
+ * clb_soilco2_* for CO2 / O2, this for each surface variable (fields CLB_F_SFC_* or any three field ids of
+ * one kind). */
+int clb_ldiv_diagonal(clb_handle h, int32_t w_field, int32_t b_field, int32_t x_field);
 
 /* ---- the fused implicit stage -------------------------------------------- */
 /* One implicit ARS111 stage on the resident state Y (in: U = temp, out: new U):

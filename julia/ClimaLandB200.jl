@@ -59,6 +59,7 @@ const CLB_HOST, CLB_DEVICE = Int32(0), Int32(1)
     F_AREA_WEIGHT; F_U_INTF_W; F_U_INTF_E; F_TOTAL_ENERGY
     F_F_MAX; F_PRECIP; F_INFILTRATION; F_R_S
     F_CO2_TOP_BC; F_CO2_BOT_BC; F_O2_TOP_BC; F_O2_BOT_BC; F_CO2_C_ATM; F_O2_C_ATM; F_CO2_DFLUXBCDY; F_O2_DFLUXBCDY
+    F_SFC_W_DI; F_SFC_B; F_SFC_X
 end
 
 # struct clb_config (same field order and widths as the header)

@@ -132,3 +132,29 @@ def test_hooks_match_oracle(case, math_mode, layout):
         assert_close(s.get("x_theta_i"), x.theta_i, TOL, "x.theta_i")
         assert_close(s.get("x_intf_e"), x.intF_e, TOL, "x.intF_e")
     s.close()
+
+
+def test_diagonal_block_solve_and_resident_vector_ops():
+    """clb_ldiv_diagonal (DiagonalMatrixRow blocks of surface variables, implicit_timestepping.jl:117-121; the canopy
+    temperature block of canopy_energy.jl:222-250), clb_field_axpy and clb_field_copy against numpy"""
+    import climaland_b200 as cl
+    w = _workload("richards", 777, 15, seed=9)
+    s = cuda_solver(w)
+    rng = np.random.default_rng(1)
+    dtg = 450.0
+    # the canopy block: dtgamma (dLW_n/dT - dshf/dT - dlhf/dT) / (ac_canopy max(LAI, eps)) - 1
+    wd = dtg * (-rng.uniform(1.0, 8.0, 777) - rng.uniform(5, 30, 777) - rng.uniform(0, 40, 777)) / (2e3 * np.maximum(rng.uniform(0, 6, 777), 1e-16)) - 1.0
+    b = rng.normal(0, 1.0, 777)
+    s.set("sfc_w_di", wd)
+    s.set("sfc_b", b)
+    s.ldiv_diagonal("sfc_w_di", "sfc_b", "sfc_x")
+    assert np.array_equal(s.get("sfc_x"), b / wd)
+    y0, x0 = s.get("y_theta_l"), rng.normal(0, 1e-7, (777, 15))
+    s.set("dy_theta_l", x0)
+    s.axpy("y_theta_l", 1800.0, "dy_theta_l")
+    assert np.array_equal(s.get("y_theta_l"), y0 + 1800.0 * x0)
+    s.copy("x_theta_l", "y_theta_l")
+    assert np.array_equal(s.get("x_theta_l"), s.get("y_theta_l"))
+    with pytest.raises(cl.ClbError):
+        s.ldiv_diagonal("sfc_w_di", "y_theta_l", "sfc_x")   # mixed kinds
+    s.close()
