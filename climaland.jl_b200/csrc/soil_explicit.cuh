@@ -158,8 +158,18 @@ __device__ __forceinline__ double heaviside(double x) { return (x > kEps) ? 1.0 
 template <int CLOSURE, int MATH, bool AUX, bool PHASE>
 __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const ExplicitView X)
 {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
+    // thread -> cell in the mirrors' memory order, so that a warp's accesses coalesce in either layout:
+    // column-fastest: grid (column blocks, levels); level-fastest: a flat grid over ncol * N
+    int64_t c;
+    int i;
+    if (P.sl == 1) {
+        const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        c = k / P.N;
+        i = (int)(k - c * P.N);
+    } else {
+        c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        i = blockIdx.y;
+    }
     if (c >= P.ncol) return;
     const int64_t q = P.at(i, c);
     const EarthConst &E = P.earth;
