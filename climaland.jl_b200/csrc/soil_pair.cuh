@@ -1,32 +1,31 @@
-// soil_pair.cuh -- lane-pair variant of the fused implicit stage (9 <= N <= 16 levels).
+// soil_pair.cuh -- the lane kernels of the fused implicit stage: a column is split over 2 * PARTS lanes of a warp
+// (PARTS = 1 lane pair, 2 lane QUAD -- the bench kernel, N = 15 / 16 -- , 4 lane OCTET, N = 15 / 16 / 50), Q cells per
+// lane, 32 / (2 PARTS) columns per warp.
 //
-// One column is owned by TWO lanes of a warp (lanes l and l + 16; 16 columns per warp):
-// the "bottom" lane holds levels 0..7, the "top" lane levels N-1 down to 8, each as eight
-// cell slots q = 0..7 ordered from the column's outer boundary towards the seam between
-// levels 7 and 8.  In that orientation both halves run the SAME straight-line code:
+// The lanes of a column form two halves: the "bottom" half holds the levels from the bottom boundary up to the seam,
+// the "top" half the levels from the top boundary down to the seam (NR = 2 PARTS Q level rows; rows >= N are pads at
+// the top).  Each lane holds its Q cells ordered from the column's boundary towards the seam, so both halves run the
+// SAME straight-line code:
 //
-//   * the closures (the FP64-heavy part) are evaluated four cells at a time with the four
-//     dependency chains interleaved statement by statement (soil_mathv.cuh): the FP64 pipe
-//     needs ~4 independent instructions in flight per sub-partition (DFMA: 8 cycles latency,
-//     one warp-instruction per 2 cycles, tools/ubench/fp64_ilp.cu) and gets them from ILP,
-//     not from occupancy;
-//   * the stencil needs no shuffles inside a half; only the seam values cross lanes
-//     (8 double shuffles per Newton iteration against ~150 of the lane-per-cell kernel);
-//   * the tridiagonal systems are solved by the TWISTED (two-sided) Thomas factorisation:
-//     each lane eliminates from its boundary towards the seam, the two seam rows give a
-//     2x2 system solved redundantly by both lanes, and each lane back-substitutes outwards.
-//     That is Thomas' operation count (~9 FP64 per cell against ~70 for 16-lane cyclic
-//     reduction) at half its serial depth;
-//   * per-cell stage constants (prepared closure parameters, lagged face coefficients, the
-//     factored (rho_e, rho_e) block) live in SHARED memory, in a warp-private
-//     [slot][level][column] tile (a lane only ever touches its own column: no barriers, and
-//     a warp's access is two full 128-byte rows: no bank conflicts), so a column costs
-//     ~1.8 KB of shared memory instead of 8 KB of registers; the iterate and the residual's
-//     constant part stay in registers;
-//   * every field is read from HBM once, by TMA: one cp.async.bulk.tensor per field and warp
-//     brings the [N levels x 16 columns] box of the column-fastest mirror straight into that
-//     tile (14 instructions per warp instead of 1800 per-lane loads), where it is transformed
-//     in place into the stage constants; the new state is written once.
+//   * the closures (the FP64-heavy part) are evaluated up to four cells at a time with the dependency chains
+//     interleaved statement by statement (soil_mathv.cuh): a sub-partition issues one instruction per cycle and one
+//     FP64 instruction per 2 cycles (3 for a DFMA with three distinct register operands) with ~8 cycles of latency
+//     (tools/ubench/fp64_*.cu), and gets its independent work from ILP because the registers allow 2 warps;
+//   * the stencil needs no shuffles inside a lane; only the values at lane boundaries cross lanes
+//     (8 double shuffles per Newton iteration in the quad against ~150 of the lane-per-cell kernel);
+//   * the tridiagonal systems are solved by the TWISTED (two-sided) Thomas factorisation: each half eliminates from
+//     its boundary towards the seam (part after part, the carry crossing lanes by shfl_up), the two seam rows give a
+//     2x2 system solved redundantly by both halves, and each half back-substitutes outwards (shfl_down).  The
+//     elimination runs on the leading minors (one fma per cell in the dependency chain, the reciprocals afterwards
+//     and in parallel);
+//   * per-cell stage constants (prepared closure parameters, lagged face coefficients, the factored (rho_e, rho_e)
+//     block) live in SHARED memory, in a warp-private tile (a lane only ever touches its own column: no block
+//     barriers); with the half in the low lane-group bit the quad's slot accesses are bank-conflict free.  The
+//     iterate and the residual's constant part stay in registers;
+//   * every field is read from HBM once, by TMA: one cp.async.bulk.tensor per field and warp brings the
+//     [N levels x CPW columns] box of the mirror straight into that tile, where it is transformed in place into the
+//     stage constants; persistent warps walk over tiles and request the tile after next (double-buffered) or
+//     prefetch the next one to L2 (single-buffered) while they compute; the new state is written once.
 //
 // Mirror layout: column-fastest (sl = ld, sc = 1) by default; LF = true reads level-fastest mirrors (sl = 1, sc = N,
 // N even: TMA needs 16-byte global strides), where a tile is one contiguous piece of each field.
