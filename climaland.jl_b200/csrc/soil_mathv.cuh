@@ -230,14 +230,14 @@ __device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[
     // and == 1 iff num == range, and th_safe - theta_r vs nu_safe - theta_r compare as th_safe vs nu_safe
     // except when both differences round to the same double, which the explicit differences below keep.
     double lo[W], nu_safe[W], range[W], th_safe[W], num[W], S[W], L[W];
-    bool unsat[W], sat1[W];
+    bool unsat[W];
     CLB_V lo[j] = theta_r[j] + kSqrtEps;
     CLB_V nu_safe[j] = max_nn(nu_eff[j], lo[j]);
     CLB_V th_safe[j] = max_nn(theta[j], lo[j]);
     CLB_V range[j] = nu_safe[j] - theta_r[j];
     CLB_V num[j] = th_safe[j] - theta_r[j];
     CLB_V S[j] = num[j] * inv_range[j];
-    CLB_V { unsat[j] = num[j] < range[j]; sat1[j] = num[j] == range[j]; }
+    CLB_V unsat[j] = num[j] < range[j];
     log_any<TAB, W>(T, S, L);
     if (CLOSURE == kVanGenuchten) {
         double Ee[W], A[W], omA[W], arg[W], l1[W], qn[W], den[W], rd[W];
@@ -245,7 +245,8 @@ __device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[
         exp_any<TAB, W>(T, Ee, A);  // S^(1/m)
         CLB_V omA[j] = 1.0 - A[j];
         // 1 - A is 0 only when S^(1/m) rounds to 1; a floor keeps log finite (dpsi is selected below)
-        CLB_V arg[j] = max_nn(omA[j], 1e-300);
+        // 0 <= omA <= 1: adding 1e-300 is the floor max(omA, 1e-300) without a compare and two selects
+        CLB_V arg[j] = omA[j] + 1e-300;
         log_any<TAB, W>(T, arg, l1);
         if (WK) {
             double em[W], t[W], sq[W];
@@ -261,7 +262,9 @@ __device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[
         CLB_V den[j] = omA[j] * S[j];
         rcp<W>(den, rd);
         CLB_V {
-            const double psi_s = sat1[j] ? -0.0 : (th_safe[j] - nu_safe[j]) * inv_Ss[j];
+            // S == 1: the reference's matric potential is -0.0 and this expression +0.0; psi only enters as
+            // psi + z here, where the sign of a zero is lost, so the S == 1 select of CellEval is not needed
+            const double psi_s = (th_safe[j] - nu_safe[j]) * inv_Ss[j];
             psi[j] = unsat[j] ? -(qn[j] * cc[j]) : psi_s;
             double d = (qn[j] * cd[j]) * rd[j];
             d = (omA[j] <= 0.0) ? INFINITY : d;
@@ -279,7 +282,7 @@ __device__ __forceinline__ void closure(const MathTab &T, const double (&theta)[
         exp_any<TAB, W>(T, arg, pw);  // S^(-1/c)
         rcp<W>(S, rS);
         CLB_V {
-            const double psi_s = sat1[j] ? cb[j] : (th_safe[j] - nu_safe[j]) * inv_Ss[j] + cb[j];
+            const double psi_s = (th_safe[j] - nu_safe[j]) * inv_Ss[j] + cb[j];  // S == 1: 0 * inv_Ss + psi_b = psi_b
             psi[j] = unsat[j] ? cb[j] * pw[j] : psi_s;
             dps[j] = unsat[j] ? (cc[j] * pw[j]) * rS[j] : inv_Ss[j];
         }
