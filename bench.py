@@ -11,8 +11,10 @@ update) = ONE fused kernel launch (clb_implicit_step).
 
   value     column-steps/s with every input resident in HBM (library mirrors).
   e2e       the same stage through the host-buffer C-ABI call (clb_implicit_step_host):
-            pinned host arrays in the reference layout, H2D of the per-step inputs, the
-            fused kernel, D2H of the new state, inside the timed region.
+            pinned host arrays in the reference layout; the 16 per-step inputs cross PCIe
+            (the library reads pinned arrays in place, column chunk by column chunk), the
+            fused kernel runs per chunk, the 4 outputs are written back to the host arrays;
+            all inside the timed region, one synchronising call per step.
   roofline  algorithmic bytes (2008 B per column-step) / kernel time against the
             measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline / --impl reference: the CPU oracle (our C restatement of the reference path;
