@@ -9,7 +9,7 @@
 //
 //   * the closures (the FP64-heavy part) are evaluated up to four cells at a time with the dependency chains
 //     interleaved statement by statement (soil_mathv.cuh): a sub-partition issues one instruction per cycle and one
-//     FP64 instruction per 2 cycles (3 for a DFMA with three distinct register operands) with ~8 cycles of latency
+//     FP64 instruction per 2 cycles with ~8 cycles of latency
 //     (tools/ubench/fp64_*.cu), and gets its independent work from ILP because the registers allow 2 warps;
 //   * the stencil needs no shuffles inside a lane; only the values at lane boundaries cross lanes
 //     (8 double shuffles per Newton iteration in the quad against ~150 of the lane-per-cell kernel);
