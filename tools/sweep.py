@@ -55,6 +55,7 @@ def main():
                 cases.append(("richards", N, ncol, False, 1800.0, 2))
     for ncol in (61_206, 64_800):
         cases.append(("energy_hydrology", 15, ncol, True, 900.0, 3))
+    cases.append(("energy_hydrology", 50, 100_000, True, 900.0, 3))
     cases.append(("richards", 15, 61_206, True, 1800.0, 2))
     stream = torch.cuda.Stream()
     print(f"# peak = {peak} GB/s (measured copy bandwidth); columns tiled from a {BASE}-column block")
@@ -67,6 +68,8 @@ def main():
         P.implicit_step(U, dt, iters, p=p)
         bytes_cs = workloads.algorithmic_bytes(model, N, topmodel=topm)
         per_handle = ncol * N * (10 if model == "richards" else 17) * 8
+        if args.cases != "all" and args.cases not in f"{model}-{N}":
+            continue
         replicas = int(max(1, min(16, -(-160e6 // per_handle))))
         solvers = []
         mdl = cl.RICHARDS if model == "richards" else cl.ENERGY_HYDROLOGY
