@@ -153,6 +153,58 @@ __device__ __forceinline__ double kersten_number(double theta_i, double S_r, dou
 // heaviside(x): src/shared_utilities/utils.jl:83-99 (1 if x > eps, else 0)
 __device__ __forceinline__ double heaviside(double x) { return (x > kEps) ? 1.0 : 0.0; }
 
+// K (saturation against nu_K) and psi (saturation against nu_psi) of one cell in FAST arithmetic with the table-driven
+// log / exp: the same formulas as CellEval<., kMathFast> (soil_closures.cuh; hydraulic_conductivity
+// soil_hydrology_parameterizations.jl:161-173 / 239-251, pressure_head :109-127 / 270-289).  When the two porosities
+// coincide (no ice) the logarithms and the inner exponential are shared.
+template <int CLOSURE>
+__device__ __forceinline__ void closure_K_psi_fast(const HydroCell &p, double th, double nu_K, double nu_psi, double &K,
+                                                   double &psi)
+{
+    const double lo = p.theta_r + kSqrtEps;
+    const double th_s = fmax(th, lo), num = th_s - p.theta_r;
+    const bool shared = (nu_K == nu_psi);
+    const double inv_m = (CLOSURE == kVanGenuchten) ? fm::rcp(p.m) : 0.0;
+    double L_K = 0.0, E_K = 0.0, l1_K = 0.0;
+    {
+        const double nu_s = fmax(nu_K, lo), range = nu_s - p.theta_r;
+        const double S = fm::div(num, range);
+        if (num < range) {
+            L_K = tlog(S);
+            if (CLOSURE == kVanGenuchten) {
+                E_K = L_K * inv_m;
+                const double omA = 1.0 - texp(E_K);   // 1 - S^(1/m)
+                l1_K = tlog(omA + 1e-300);
+                const double t = 1.0 - texp(p.m * l1_K);
+                K = (fm::sqrt(S) * (t * t)) * p.K_sat;
+            } else {
+                K = texp((2.0 * fm::rcp(p.a) + 3.0) * L_K) * p.K_sat;
+            }
+        } else {
+            K = p.K_sat;
+        }
+    }
+    {
+        const double nu_s = fmax(nu_psi, lo), range = nu_s - p.theta_r;
+        if (num < range) {
+            double L = L_K, E = E_K, l1 = l1_K;
+            if (!shared) {
+                L = tlog(fm::div(num, range));
+                if (CLOSURE == kVanGenuchten) {
+                    E = L * inv_m;
+                    l1 = tlog((1.0 - texp(E)) + 1e-300);
+                }
+            }
+            if (CLOSURE == kVanGenuchten) psi = -(texp((l1 - E) * fm::rcp(p.b)) * fm::rcp(p.a));  // -((S^(-1/m) - 1)^(1/n)) / alpha
+            else psi = p.b * texp(-L * fm::rcp(p.a));
+        } else {
+            const double sat = (th_s - nu_s) * fm::rcp(p.S_s);
+            if (CLOSURE == kVanGenuchten) psi = (num == range) ? -0.0 : sat;
+            else psi = (num == range) ? p.b : sat + p.b;
+        }
+    }
+}
+
 // AUX: update_aux! for the cell; PHASE: the PhaseChange source of the cell.  With both, the source uses the
 // freshly computed theta_l, kappa, T (what the reference reads back from p), so no field is read twice.
 template <int CLOSURE, int MATH, bool AUX, bool PHASE>
@@ -192,8 +244,8 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
         T = E.T_ref + dv<MATH>(P.Y_rho_e[q] + thi * E.rho_i * E.LH_f0, volumetric_heat_capacity(theta_l, thi, rcds, E));
         // K = impedance * viscosity * hydraulic_conductivity(effective_saturation(nu, theta_l(Y), theta_r))
         double Kh, psi, d0, d1;
-        if (MATH == kMathFast && thi == 0.0) {  // nu - theta_i == nu: one closure evaluation gives K and psi
-            CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, true, false>(th, Kh, psi, d0);
+        if (MATH == kMathFast) {
+            closure_K_psi_fast<CLOSURE>(cell, th, cell.nu, cell.nu - thi, Kh, psi);
         } else {
             CellEval<CLOSURE, MATH>(cell, cell.nu).template eval<true, false, false>(th, Kh, d0, d1);
             CellEval<CLOSURE, MATH>(cell, cell.nu - thi).template eval<false, true, false>(th, d0, psi, d1);
