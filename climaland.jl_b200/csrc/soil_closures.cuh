@@ -146,7 +146,11 @@ __device__ __forceinline__ void closure_eval(const HydroCell &p, double theta, d
 // depend on the iterate is prepared once: clips, 1/m, 1/n, 1/alpha, the dpsi prefactor.
 //   LIBM mode: holds the raw parameters and evaluates the reference's pow expressions.
 //   FAST mode: one log(S) shared by all powers, soil_math.cuh functions, no division by a
-//              stage constant inside the loop.  S itself is an exactly rounded-or-exact
+//              stage constant inside the loop.  The logarithm here is the series version with a
+//              RELATIVE error bound (log_pos), not the cheaper table-driven one of the lane and
+//              explicit-stage kernels (absolute bound): the reference's hydrostatic test
+//              (test/standalone/Soil/soiltest.jl:15-90) asks psi + z to be constant to 2 eps, which
+//              the hooks meet and a table logarithm near S = 1 would not (measured).  S itself is an exactly rounded-or-exact
 //              quotient (fm::div reproduces exact quotients), so the S < 1 / S <= 1 branches
 //              agree with the reference.
 template <int CLOSURE, int MATH>
