@@ -332,6 +332,7 @@ clb::PairGridT<HR> make_pair_grid(clb_handle h, double dtg)
     constexpr int NR = 2 * HR;
     clb::PairGridT<HR> g;
     g.col0 = 0;
+    g.nlev = N;
     for (int half = 0; half < 2; ++half) {
         for (int q = 0; q < HR; ++q) {
             const int level = half ? NR - 1 - q : q;
@@ -551,6 +552,24 @@ int launch_octet(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
     }
 }
 
+// Octet with the level count taken at run time (template N = 0): Q cells per lane, NR = 8 Q level rows, for
+// NR - 8 < N <= NR; single-buffered persistent tiles of 4 columns cut from column-fastest mirrors.
+template <int CLOSURE, int MODEL, int Q>
+int launch_octet_rt(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+{
+    if constexpr (MODEL == 1) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 18, 1, 192, 1, true>(h, P, dtg, max_iters, 0);
+    else return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 11, 1, 256, 1, true>(h, P, dtg, max_iters, 0);
+}
+
+template <int Q>
+int launch_octet_rt_q(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
+{
+    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    const bool vg = h->cfg.closure == CLB_VAN_GENUCHTEN;
+    if (eh) return vg ? launch_octet_rt<0, 1, Q>(h, P, dtg, max_iters) : launch_octet_rt<1, 1, Q>(h, P, dtg, max_iters);
+    return vg ? launch_octet_rt<0, 0, Q>(h, P, dtg, max_iters) : launch_octet_rt<1, 0, Q>(h, P, dtg, max_iters);
+}
+
 template <int N>
 int launch_octet_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 {
@@ -563,7 +582,8 @@ int launch_octet_n(clb_handle h, const clb::DevView &P, double dtg, int max_iter
 bool pair_variant_applies(clb_handle h, bool octet = false)
 {
     const int N = h->cfg.n_levels;
-    if (N != 15 && N != 16 && !(octet && N == 50)) return false;
+    // octet: N = 15 / 16 / 50 as template instantiations, 17 .. 48 with the level count at run time
+    if (N != 15 && N != 16 && !(octet && (N == 50 || (N >= 17 && N <= 48)))) return false;
     if (h->cfg.math_mode != CLB_MATH_FAST) return false;
     // a MoistureStateBC top re-evaluates the boundary fluxes every iteration (rre.jl:460-468): lane-per-cell kernel
     if (h->cfg.model == CLB_RICHARDS && h->cfg.top_bc == 1) return false;
@@ -746,7 +766,17 @@ int clb_create(clb_handle *out, const clb_config *cfg)
         const bool octet50 = cfg->n_levels == 50 && cfg->math_mode == CLB_MATH_FAST &&
                              !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
                              (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_OCTET);
-        layout = ((!quad_ok && lane_per_cell) || octet50) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
+        // 17 <= N <= 48: the octet with the level count at run time reads column-fastest mirrors; it is the choice
+        // while a field stays below 80 MB (beyond that its tiles fall out of the TLB, see clb_implicit_step).  Measured
+        // at 1e5 columns (tools/time_other_n.py): faster than the lane-per-cell / generic kernels everywhere except
+        // EnergyHydrology with 25 <= N <= 31 (Q = 4: 316 us against the lane-per-cell kernel's 290 us)
+        const int64_t ld0 = (cfg->n_columns + 31) / 32 * 32;
+        const bool octet_rt = cfg->n_levels >= 17 && cfg->n_levels <= 48 && cfg->math_mode == CLB_MATH_FAST &&
+                              !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
+                              (cfg->kernel_variant == CLB_VARIANT_LANE_OCTET ||
+                               (cfg->kernel_variant == CLB_VARIANT_AUTO && ld0 * cfg->n_levels * 8 <= ((int64_t)80 << 20) &&
+                                !(cfg->model == CLB_ENERGY_HYDROLOGY && cfg->n_levels >= 25 && cfg->n_levels <= 31)));
+        layout = (((!quad_ok && lane_per_cell) && !octet_rt) || octet50) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
     }
     h->cfg.layout = layout;
     if (layout == CLB_LAYOUT_LEVEL_FASTEST) {
@@ -1239,7 +1269,7 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
         if (pair_variant_applies(h))
             variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
         else if (pair_variant_applies(h, true) && (level_fast || (int64_t)h->ld * N * 8 <= (int64_t)80 << 20))
-            // N = 50.  A tile of the octet touches all 50 level rows of every field at once.  In level-fastest mirrors
+            // N = 50 (and 17 .. 48 on column-fastest mirrors).  A tile of the octet touches all 50 level rows of every field at once.  In level-fastest mirrors
             // (what CLB_LAYOUT_AUTO picks for N = 50) they are contiguous.  In column-fastest mirrors they lie
             // ld * 8 bytes apart and, as the fields grow, the tile's ~550 pages fall out of the TLB (measured against
             // the generic kernel, tools/n50_crossover.py: 2.1x faster at 1e5 columns, equal at ~2.2e5 = 88 MB per
@@ -1260,7 +1290,7 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
                     "boundary conditions");
     if (variant == CLB_VARIANT_LANE_OCTET && !pair_variant_applies(h, true))
         return fail(CLB_ERR_INVALID,
-                    "clb_implicit_step: the lane-octet variant needs N = 15, 16 or 50, CLB_MATH_FAST, column-fastest mirrors and "
+                    "clb_implicit_step: the lane-octet variant needs 15 <= N <= 48 on column-fastest mirrors or N = 50, CLB_MATH_FAST and "
                     "flux boundary conditions");
     if (variant == CLB_VARIANT_LANE_PER_CELL && N > 31)
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the lane-per-cell variant needs N <= 31");
@@ -1290,7 +1320,11 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
         } else if (variant == CLB_VARIANT_LANE_OCTET) {
             if (N == 15) TRY((launch_octet_n<15>(h, P, dtgamma, max_iters)));
             else if (N == 16) TRY((launch_octet_n<16>(h, P, dtgamma, max_iters)));
-            else TRY((launch_octet_n<50>(h, P, dtgamma, max_iters)));
+            else if (N == 50) TRY((launch_octet_n<50>(h, P, dtgamma, max_iters)));
+            else if (N <= 24) TRY((launch_octet_rt_q<3>(h, P, dtgamma, max_iters)));
+            else if (N <= 32) TRY((launch_octet_rt_q<4>(h, P, dtgamma, max_iters)));
+            else if (N <= 40) TRY((launch_octet_rt_q<5>(h, P, dtgamma, max_iters)));
+            else TRY((launch_octet_rt_q<6>(h, P, dtgamma, max_iters)));
         } else if (variant == CLB_VARIANT_LANE_PER_CELL) {
             const int cpw = (N <= 15) ? 2 : 1;  // columns per warp (one lane of each segment is a ghost)
             const int64_t warps = (P.ncol + cpw - 1) / cpw;

@@ -61,6 +61,7 @@ struct PairGridT {
     double z[2][HR];          // z_c of the cell
     double dti[2][HR];        // dtgamma / dz_c of the cell; 0 for pad slots
     double hidzf[2][HR + 1];  // 1/(2 dz_f) of face f (f = q: outer face of slot q, HR: seam); 0 for boundary / pad faces
+    int nlev;                     // N, for the instantiations that take the level count at run time (template N = 0)
     int col0;                     // first column of this launch within the mirrors the TMA descriptors describe
                                   // (a launch over a column sub-range: the pointers of DevView are shifted, the
                                   // descriptors are not)
@@ -304,7 +305,9 @@ __device__ __forceinline__ ColScalars load_col_scalars(const DevView &P, int64_t
 // PERSISTENT: every warp walks over tiles (CPW columns each) t = warp, warp + nwarps, ...; with
 // NBUF = 2 the TMA boxes and the per-column scalars of the next tile are requested before the
 // current tile is touched, so HBM latency hides behind a whole tile of FP64 work.
-template <int CLOSURE, int MODEL, int N, int PARTS, int NS, int NBUF, int BLOCK, int MINB, int QC = kPairQ / PARTS,
+// NT: the level count as a template parameter (the N = 15 / 16 / 50 instantiations: every `level < N` and the position
+// of the top boundary fold at compile time), or 0: N is read from G.nlev (NR - 8 < N <= NR, any parity).
+template <int CLOSURE, int MODEL, int NT, int PARTS, int NS, int NBUF, int BLOCK, int MINB, int QC = kPairQ / PARTS,
           bool LF = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
     k_step_lanes(const DevView P, const PairGridT<PARTS * QC> G, const __grid_constant__ PairMaps M, double dtg,
@@ -314,8 +317,11 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     constexpr int Q = Gm::Q, CPW = Gm::CPW, NR = Gm::NR;
     // cells evaluated together: a divisor of Q close to kPairW (Q = 7 -> one group of 7 would not fit: 4 + 3)
     constexpr int WFULL = (Q <= kPairW) ? Q : kPairW;
-    constexpr int Q0T = NR - N;  // first real slot of the top half (pads before it, all in part 0)
-    static_assert(N <= NR && Q0T < Q, "the pads must all lie in part 0 of the top half: NR - Q < N <= NR");
+    static_assert(NT <= NR, "N <= NR level rows");
+    const int N = (NT > 0) ? NT : G.nlev;
+    // The NR - N pad rows sit at the top of the column, i.e. at the outer end of the top half: its first real slot is
+    // slot qT of part pT (all lanes of parts < pT hold pads only: identity rows, zero face coefficients).
+    const int Q0T = NR - N, pT = Q0T / Q, qT = Q0T % Q;
     static_assert(NBUF == 1 || NBUF == 2, "single or double buffered");
     constexpr int NTOT = PairSlots<MODEL>::kConst, NRAW = PairSlots<MODEL>::kRaw;
     static_assert(NS >= NRAW && NS <= NTOT, "the raw fields are staged in the shared-memory slots");
@@ -430,9 +436,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     // boundary flux of this half in the inward convention; it enters at face 0 of part 0 (bottom
     // half, top half when N == 16) or at face Q0T of part 0 (top half with pads)
     const double bin_w = half ? -top_w : bot_w, bin_e = half ? -top_h : bot_h;
-    const bool at0 = outermost && !(half && Q0T > 0), atT = outermost && half;
+    const bool top_lane = half && part == pT;  // the lane of the top half that holds the top cell
+    const bool at0 = half ? (top_lane && qT == 0) : outermost, atT = top_lane && qT > 0;
     const double b0_w = at0 ? bin_w : 0.0, b0_e = at0 ? bin_e : 0.0;
-    const double bT_w = atT ? bin_w : 0.0, bT_e = atT ? bin_e : 0.0;  // used at face Q0T > 0 only
+    const double bT_w = atT ? bin_w : 0.0, bT_e = atT ? bin_e : 0.0;  // enters at the lane's face qT > 0
 
     // flux integrals (W = -I, lagged boundary fluxes): their Newton recurrence does not depend on
     // the iterate, so it runs here, off the hot loop (one lane per column stores it)
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 aK_in = (Kc[q] + ((q < Q - 1) ? Kc[q + 1] : K_in)) * hid_in;
             }
             double Fw_in = -(aK_in * dh);
-            if (Q0T > 0 && q + 1 == Q0T) Fw_in += bT_w;
+            if (q + 1 == qT) Fw_in += bT_w;  // bT is zero in every lane but the top cell's
             double t1;
             if (MODEL == 0) t1 = S.template get<R_T1>(q);
             else t1 = S.template get<E_T1>(q);
@@ -726,7 +733,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 const double aE_in = (eK[q] + eKn) * hid_in;
                 aE[q + 1] = aE_in;
                 double Fe_in = fma(-aC_in, Tn - Td[q], -(aE_in * dh));
-                if (Q0T > 0 && q + 1 == Q0T) Fe_in += bT_e;
+                if (q + 1 == qT) Fe_in += bT_e;
                 f2[q] = fma(Fe_o - Fe_in, dti, S.template get<E_T2>(q)) - U2[q];
                 Fe_o = Fe_in;
             }

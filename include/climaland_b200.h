@@ -85,8 +85,9 @@ enum { CLB_VARIANT_AUTO = 0,
                                            CLB_MATH_FAST, flux BCs, column-fastest mirrors               */
        CLB_VARIANT_LANE_QUAD_PIPELINED = 5, /* the same as a persistent kernel whose warps prefetch their next
                                            tile (double-buffered shared memory)                          */
-       CLB_VARIANT_LANE_OCTET = 6       /* eight lanes per column: 2 cells each for N = 15 / 16 (4 warps per
-                                           sub-partition), 7 cells each for N = 50; otherwise as the quad   */ };
+       CLB_VARIANT_LANE_OCTET = 6       /* eight lanes per column, Q cells each: 15 <= N <= 48 (Q = ceil(N / 8);
+                                           N = 15 / 16 compiled in, the others read at run time) on column-fastest
+                                           mirrors, N = 50 (Q = 7) on either layout; otherwise as the quad */ };
 /* layout of the library's per-cell mirrors (0 = let the library choose) */
 enum { CLB_LAYOUT_AUTO = 0,
        CLB_LAYOUT_COLUMN_FASTEST = 1,   /* element (i, c) at i*ld + c                              */

@@ -73,8 +73,15 @@ def test_variant_requests_that_do_not_apply_are_refused():
     from climaland_b200 import workloads
     from helpers import cuda_solver
     w = workloads.make_workload("richards", 32, N=20, seed=1)
-    for kv in (cl.VARIANT_REGISTER_COLUMN, cl.VARIANT_LANE_QUAD, cl.VARIANT_LANE_QUAD_PIPELINED, cl.VARIANT_LANE_OCTET):
+    for kv in (cl.VARIANT_REGISTER_COLUMN, cl.VARIANT_LANE_QUAD, cl.VARIANT_LANE_QUAD_PIPELINED):
         s = cuda_solver(w, kernel_variant=kv)
+        with pytest.raises(cl.ClbError) as e:
+            s.implicit_step(1800.0, 2)
+        assert e.value.code == cl._lib.K["CLB_ERR_INVALID"]
+        s.close()
+    # the lane octet covers 15 <= N <= 48 and N = 50
+    for N in (10, 49, 60):
+        s = cuda_solver(workloads.make_workload("richards", 32, N=N, seed=1), kernel_variant=cl.VARIANT_LANE_OCTET)
         with pytest.raises(cl.ClbError) as e:
             s.implicit_step(1800.0, 2)
         assert e.value.code == cl._lib.K["CLB_ERR_INVALID"]

@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""What CLB_VARIANT_AUTO gives for level counts other than the three the lane kernels are instantiated for."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import numpy as np, torch
+import climaland_b200 as cl  # noqa: F401
+from climaland_b200 import workloads
+from helpers import cuda_solver
+VAR = {1: "thread/column registers", 2: "thread/column generic", 3: "lane per cell", 4: "lane quad", 5: "lane quad pipelined", 6: "lane octet"}
+for model, iters, dt in (("richards", 2, 1800.0), ("energy_hydrology", 3, 900.0)):
+    for N in (10, 15, 16, 20, 30, 40, 50):  # AUTO: lane per cell (N <= 16 other than 15, 16), octet (17..48, 50)
+        ncol = 100_000
+        w = workloads.make_workload(model, ncol, N=N, seed=1, topmodel=True)
+        ss = [cuda_solver(w, out_of_place=True) for _ in range(2)]
+        for s in ss: s.implicit_step(dt, iters)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(40): ss[k % 2].implicit_step(dt, iters)
+        e1.record(); torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / 40
+        print(f"{model:17s} N={N:3d} {VAR[ss[0].last_variant()]:24s} {us:8.1f} us  {ncol/(us*1e-6):.3e} column-steps/s  "
+              f"{ncol*N*iters/(us*1e-6):.3e} cell-iterations/s", flush=True)
+        for s in ss: s.close()
