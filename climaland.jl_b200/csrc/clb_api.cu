@@ -116,8 +116,15 @@ struct clb_handle_s {
     clb::PairMaps pair_maps;   // TMA descriptors of the lane-pair kernel's inputs and the mirrors they describe
     const double *pair_map_src[14] = {};
     int pair_map_box = 0;      // columns per TMA box those descriptors were encoded for
+    const double *arena_map_src = nullptr;  // the same for the two 3-D descriptors (box columns * 1000 + level rows)
+    int arena_map_box = 0;
     // prepared (reciprocal) mirrors of S_s / a / b / m read by the lane-quad kernels (soil_pair.cuh: k_prepare_params)
     double *prep[4] = {};
+    // The raw per-cell inputs of the lane kernels live at a uniform stride in ONE allocation, in the kernels' slot
+    // order (arena_slot), so that a tile of all of them is two TMA boxes of a 3-D tensor {columns, levels, fields}
+    // instead of one box per field (soil_pair.cuh: request_tile).  Column-fastest mirrors only.
+    double *arena = nullptr;
+    int arena_fields = 0;
     bool prep_dirty = true;     // a parameter field changed since they were written
     bool prep_volatile = false; // the caller holds a device pointer to a parameter mirror: re-prepare every stage
     // this handle's last enqueued operation wrote a time-invariant parameter mirror: the next stage kernel must
@@ -174,10 +181,53 @@ struct DeviceGuard {
     }
 };
 
+// slot of a field (prep = false) or of prepared mirror k (prep = true) in the arena, -1: not an arena field.  The order
+// is the slot order of make_pair_maps / soil_pair.cuh.
+int arena_slot(clb_handle h, int f, bool prep)
+{
+    if (h->cfg.model == CLB_ENERGY_HYDROLOGY) {
+        if (prep) return 2 + f;
+        switch (f) {
+        case CLB_F_NU: return 0; case CLB_F_THETA_R: return 1; case CLB_F_Y_THETA_L: return 6;
+        case CLB_F_IS_SATURATED: return 7; case CLB_F_Y_THETA_I: return 8; case CLB_F_RHO_C_DS: return 9;
+        case CLB_F_K_LAG: return 10; case CLB_F_KAPPA_LAG: return 11; case CLB_F_THETA_L_LAG: return 12;
+        case CLB_F_Y_RHO_E_INT: return 13; default: return -1;
+        }
+    }
+    if (prep) return 3 + f;
+    switch (f) {
+    case CLB_F_NU: return 0; case CLB_F_THETA_R: return 1; case CLB_F_K_SAT: return 2; case CLB_F_Y_THETA_L: return 7;
+    case CLB_F_IS_SATURATED: return 8; default: return -1;
+    }
+}
+
+int arena_pointer(clb_handle h, int slot, double **out)
+{
+    *out = nullptr;
+    if (slot < 0 || h->sc != 1) return CLB_OK;
+    if (!h->arena) {
+        h->arena_fields = (h->cfg.model == CLB_ENERGY_HYDROLOGY) ? 14 : 9;
+        const size_t bytes = (size_t)h->arena_fields * h->cell_elems * sizeof(double);
+        CUDA_TRY(cudaMalloc(&h->arena, bytes));
+        CUDA_TRY(cudaMemsetAsync(h->arena, 0, bytes, h->stream));
+    }
+    *out = h->arena + (size_t)slot * h->cell_elems;
+    return CLB_OK;
+}
+
+inline bool in_arena(clb_handle h, const double *p)
+{
+    return h->arena && p >= h->arena && p < h->arena + (size_t)h->arena_fields * h->cell_elems;
+}
+
 int ensure_field(clb_handle h, int f)
 {
     if (h->field[f]) return CLB_OK;
     const size_t n = is_cell_field(f) ? h->cell_elems : (size_t)h->ld;
+    if (is_cell_field(f)) {
+        TRY(arena_pointer(h, arena_slot(h, f, false), &h->field[f]));
+        if (h->field[f]) return CLB_OK;  // zeroed with the arena
+    }
     CUDA_TRY(cudaMalloc(&h->field[f], n * sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(h->field[f], 0, n * sizeof(double), h->stream));
     return CLB_OK;
@@ -246,6 +296,9 @@ clb::DevView make_view(clb_handle h)
     P.R_ss = F[CLB_F_R_SS]; P.R_ess = F[CLB_F_R_ESS]; P.h_grad = F[CLB_F_H_GRAD];
     if (!c.has_topmodel_source) {  // the lane-per-cell kernel loads these unconditionally
         P.is_sat = h->zeros_cell;
+        // the arena's own (never written, zero) slot keeps the lane kernels' inputs equally spaced: two TMA boxes per tile
+        if (h->arena && !F[CLB_F_IS_SATURATED])
+            P.is_sat = h->arena + (size_t)arena_slot(h, CLB_F_IS_SATURATED, false) * h->cell_elems;
         P.R_ss = P.R_ess = P.h_grad = h->zeros_col;
     } else if (!P.R_ess) {
         P.R_ess = h->zeros_col;
@@ -411,8 +464,11 @@ inline bool is_invariant_param(int field)
 int ensure_prepared(clb_handle h, const clb::DevView &P)
 {
     if (!h->prep_dirty && !h->prep_volatile) return CLB_OK;
-    for (auto &p : h->prep)
+    for (int k = 0; k < 4; ++k) {
+        double *&p = h->prep[k];
+        if (!p) TRY(arena_pointer(h, arena_slot(h, k, true), &p));
         if (!p) CUDA_TRY(cudaMalloc(&p, h->cell_elems * sizeof(double)));
+    }
     const int64_t n = (int64_t)h->cell_elems;
     const unsigned grid = (unsigned)((n + 255) / 256);
     if (h->cfg.closure == CLB_VAN_GENUCHTEN)
@@ -429,7 +485,26 @@ int ensure_prepared(clb_handle h, const clb::DevView &P)
 
 // Fields of the lane-quad kernel in the order of its shared-memory slots (soil_pair.cuh); the closure
 // parameters S_s / a / b / m come from the prepared mirrors
-int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, int box_levels_lf, clb::PairMaps *maps)
+// 3-D tensor {columns, levels, fields} over `nf` mirrors `stride` doubles apart, box {box_columns, box_levels, box_fields}
+int encode_arena_map(clb_handle h, const double *ptr, size_t stride, int nf, int box_columns, int box_levels, int box_fields,
+                     CUtensorMap *map)
+{
+    EncodeTiledFn enc;
+    TRY(encode_tiled_fn(&enc));
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint64_t dims[3] = {(cuuint64_t)h->cfg.n_columns, (cuuint64_t)h->cfg.n_levels, (cuuint64_t)nf};
+    const cuuint64_t strides[2] = {(cuuint64_t)h->ld * sizeof(double), (cuuint64_t)stride * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_columns, (cuuint32_t)box_levels, (cuuint32_t)box_fields};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)ptr, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CLB_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+    return CLB_OK;
+}
+
+// box_levels_arena > 0: the kernel takes the two-box form when the mirrors are equally spaced (the handle's arena)
+int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, int box_levels_lf, clb::PairMaps *maps,
+                   int box_levels_arena = 0)
 {
     TRY(ensure_prepared(h, P));
     const double *const *Q = h->prep;
@@ -447,6 +522,20 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, int box
             h->pair_map_src[j] = src[j];
         }
     }
+    static const bool no_arena = getenv("CLB_NO_ARENA_BOX") != nullptr;
+    bool spaced = box_levels_arena > 0 && h->sc == 1 && !no_arena;
+    for (int j = 1; j < n && spaced; ++j) spaced = src[j] == src[0] + (size_t)j * h->cell_elems;
+    if (spaced && (h->arena_map_src != src[0] || h->arena_map_box != box_columns * 1000 + box_levels_arena)) {
+        // the parameter fields come first in the box order of Richards (slots 0-6); EnergyHydrology's rho_c_ds (slot 9)
+        // rides with the stage inputs
+        const int fa = is_eh ? 6 : 7;
+        TRY(encode_arena_map(h, src[0], h->cell_elems, n, box_columns, box_levels_arena, fa, &h->pair_maps.a));
+        TRY(encode_arena_map(h, src[0], h->cell_elems, n, box_columns, box_levels_arena, n - fa, &h->pair_maps.b));
+        h->pair_maps.fa = fa;
+        h->arena_map_src = src[0];
+        h->arena_map_box = box_columns * 1000 + box_levels_arena;
+    }
+    h->pair_maps.arena = spaced ? 1 : 0;
     *maps = h->pair_maps;
     return CLB_OK;
 }
@@ -487,7 +576,7 @@ int launch_lanes(clb_handle h, const clb::DevView &P, double dtg, int max_iters,
     clb::PairMaps maps;
     // the descriptors always describe the whole mirrors (P may be a column sub-range with shifted pointers;
     // its offset travels as g.col0)
-    TRY(make_pair_maps(h, col0 ? make_view(h) : P, CPW, Gm::kRowsLF, &maps));
+    TRY(make_pair_maps(h, col0 ? make_view(h) : P, CPW, Gm::kRowsLF, &maps, LF ? 0 : Gm::NR));
     // programmatic dependent launch: the kernel's prologue (tables, barriers, the first tile's parameter
     // fields) may overlap the tail of the stream's previous kernel unless that kernel may be writing this
     // handle's parameter mirrors
@@ -517,10 +606,14 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, 
 {
     constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 11;
     if constexpr (PIPELINED)
+#ifndef CLB_QUAD_BLOCK_R
+#define CLB_QUAD_BLOCK_R 256
+#endif
 #ifndef CLB_QUAD_BLOCK
 #define CLB_QUAD_BLOCK 256  // 8 warps per SM; 128 = one warp per sub-partition (latency experiment)
 #endif
-        return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 2, CLB_QUAD_BLOCK, 1, true>(h, P, dtg, max_iters, col0);
+        return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 2, (MODEL == 0) ? CLB_QUAD_BLOCK_R : CLB_QUAD_BLOCK, 1, true>(h, P, dtg, max_iters,
+                                                                                                                col0);
     else
         return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 1, 128, CLB_QUAD_MINB, false>(h, P, dtg, max_iters, col0);
 }
@@ -816,9 +909,10 @@ int clb_destroy(clb_handle h)
     DeviceGuard guard(h->cfg.device);
     cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    for (auto &p : h->field) cudaFree(p);
+    for (auto &p : h->field) if (!in_arena(h, p)) cudaFree(p);
     for (auto &p : h->work) cudaFree(p);
-    for (auto &p : h->prep) cudaFree(p);
+    for (auto &p : h->prep) if (!in_arena(h, p)) cudaFree(p);
+    cudaFree(h->arena);
     cudaFree(h->carry);
     cudaFree(h->zeros_cell);
     cudaFree(h->zeros_col);
@@ -1411,6 +1505,18 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters, cons
     }
     return clb_sync(h);
 }
+
+#ifdef CLB_PHASE_CLOCKS
+// tuning builds only: the lane kernels' phase clocks summed over warps since the last call (then reset)
+__attribute__((visibility("default"))) int clb_debug_phase_clocks(unsigned long long *out12)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out12, clb::g_phase_clk, sizeof(unsigned long long) * 12);
+    unsigned long long zero[12] = {};
+    cudaMemcpyToSymbol(clb::g_phase_clk, zero, sizeof(zero));
+    return CLB_OK;
+}
+#endif
 
 int clb_last_variant(clb_handle h, int32_t *variant)
 {

@@ -89,6 +89,11 @@ enum { E_THETA_R = 0, E_NU_EFF, E_ICE, E_RCBASE, E_CA, E_KC, E_CB, E_INV_SS, E_C
 // TMA descriptors of the raw fields (column-fastest mirrors: dims {ncol, N}, box {16, N})
 struct PairMaps {
     CUtensorMap m[14];
+    // When the raw fields lie at a uniform stride in one allocation (the handle's arena) a tile is two boxes of a
+    // 3-D tensor {columns, levels, fields}: a = the fa time-invariant parameter fields, b = the others (box {CPW, NR, .}:
+    // level rows >= N are zero-filled, so a box lands as whole [NR][CPW] slots).
+    CUtensorMap a, b;
+    int arena, fa;
 };
 
 // Q cells per lane, CPW columns per warp.  A slot of the warp tile is [NR level rows][CPW columns] when the boxes
@@ -155,6 +160,14 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
         "l"(map), "r"(c0), "r"(l0), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int c0, int l0, int f0, unsigned bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(l0), "r"(f0), "r"(bar)
         : "memory");
 }
 
@@ -307,6 +320,18 @@ __device__ __forceinline__ ColScalars load_col_scalars(const DevView &P, int64_t
 // current tile is touched, so HBM latency hides behind a whole tile of FP64 work.
 // NT: the level count as a template parameter (the N = 15 / 16 / 50 instantiations: every `level < N` and the position
 // of the top boundary fold at compile time), or 0: N is read from G.nlev (NR - 8 < N <= NR, any parity).
+// Phase clocks (tuning builds only, -DCLB_PHASE_CLOCKS; tools/phase_clocks.py): lane 0 of every warp adds the SM
+// clock ticks it spent in each phase of a tile; read back through clb_debug_phase_clocks.
+#ifdef CLB_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[12];
+#define CLB_PC_DECL unsigned pc_[12] = {}; unsigned pc_t_ = (unsigned)clock();
+#define CLB_PC(k) { const unsigned now_ = (unsigned)clock(); pc_[k] += now_ - pc_t_; pc_t_ = now_; }
+#define CLB_PC_FLUSH if (lane == 0) { _Pragma("unroll") for (int k_ = 0; k_ < 12; ++k_) atomicAdd(&g_phase_clk[k_], (unsigned long long)pc_[k_]); }
+#else
+#define CLB_PC_DECL
+#define CLB_PC(k)
+#define CLB_PC_FLUSH
+#endif
 template <int CLOSURE, int MODEL, int NT, int PARTS, int NS, int NBUF, int BLOCK, int MINB, int QC = kPairQ / PARTS,
           bool LF = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
@@ -362,18 +387,33 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     };
     auto request_tile = [&](int64_t t, int buf, int which) {
         const unsigned bar = bar0 + buf * 8;
-        if (which & 1) {
+        // One lane issues the boxes back to back.  (One box per lane -- lane j fetching field j -- costs ~1 000 cycles
+        // per tile: UTMALDG takes its operands from uniform registers, so the divergent form becomes a loop over the
+        // active lanes, ELECT + R2UR + UTMALDG each time; tools/phase_clocks.py.)
+        if (!LF && M.arena) {
+            // Two boxes instead of one per field: a UTMALDG blocks the issuing warp for ~75 cycles (measured,
+            // tools/phase_clocks.py: 1 050 ticks per tile for 14 boxes).
+            if (lane == 0) {
+                if (which & 1) mbar_expect_tx(bar, (unsigned)NRAW * kSlotB);
+                const unsigned dst0 = smem_u32(tiles + buf * kTileBytes);
+                const int cc_ = G.col0 + (int)(t * CPW);
+                if (which & 1) tma_load_3d(dst0, &M.a, cc_, 0, 0, bar);
+                if (which & 2) tma_load_3d(dst0 + M.fa * kSlotB, &M.b, cc_, 0, M.fa, bar);
+            }
+        } else if (lane == 0) {
             // bytes of a box: out-of-bounds rows of a level-fastest box (levels >= N, zero-filled) count as well
-            if (lane == 0)
+            if (which & 1)
                 mbar_expect_tx(bar, (unsigned)(NRAW - ((CLOSURE == kVanGenuchten) ? 0 : 1)) * (LF ? Gm::kRowsLF : N) * CPW * 8);
-            __syncwarp();
+            const unsigned dst0 = smem_u32(tiles + buf * kTileBytes);
+            const int cc_ = G.col0 + (int)(t * CPW);
+#pragma unroll
+            for (int j = 0; j < NRAW; ++j) {
+                const bool skip = (CLOSURE != kVanGenuchten) && j == ((MODEL == 1) ? 5 : 6);  // no m field for Brooks-Corey
+                const bool mine = is_param(j) ? (which & 1) : (which & 2);
+                // coordinates in the order of the tensor's dimensions: {column, level} column-fastest, {level, column} level-fastest
+                if (!skip && mine) tma_load_2d(dst0 + j * kSlotB, &M.m[j], LF ? 0 : cc_, LF ? cc_ : 0, bar);
+            }
         }
-        const bool skip = (CLOSURE != kVanGenuchten) && lane == ((MODEL == 1) ? 5 : 6);  // no m field for Brooks-Corey
-        const bool mine = is_param(lane) ? (which & 1) : (which & 2);
-        if (lane < NRAW && !skip && mine)
-            // coordinates in the order of the tensor's dimensions: {column, level} column-fastest, {level, column} level-fastest
-            tma_load_2d(smem_u32(tiles + buf * kTileBytes) + lane * kSlotB, &M.m[lane], LF ? 0 : G.col0 + (int)(t * CPW),
-                        LF ? G.col0 + (int)(t * CPW) : 0, bar);
     };
 
     if (lane == 0) {
@@ -396,6 +436,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     ColScalars nxt = load_col_scalars<MODEL>(P, col_clamped(warp0));
 
     double dx2_acc = 0.0, bad = 0.0;
+    CLB_PC_DECL
     unsigned phase = 0;  // bit b: parity the next wait on buffer b expects
     int buf = 0;
 #pragma unroll 1
@@ -441,8 +482,14 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     const double b0_w = at0 ? bin_w : 0.0, b0_e = at0 ? bin_e : 0.0;
     const double bT_w = atT ? bin_w : 0.0, bT_e = atT ? bin_e : 0.0;  // enters at the lane's face qT > 0
 
+    CLB_PC(0)  // tile prologue (column scalars, flux integrals)
+    mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u);
+    phase ^= 1u << buf;
+    CLB_PC(1)  // waiting for the tile
+
     // flux integrals (W = -I, lagged boundary fluxes): their Newton recurrence does not depend on
-    // the iterate, so it runs here, off the hot loop (one lane per column stores it)
+    // the iterate, so it runs here, off the hot loop (one lane per column stores it); placed after the wait so that
+    // its dependent chain interleaves with the set-up below
     double dx2_int = 0.0;
     {
         const double tiw = cur.intF_w, tie = cur.intF_e;
@@ -461,8 +508,6 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         }
     }
 
-    mbar_wait(bar0 + buf * 8, (phase >> buf) & 1u);
-    phase ^= 1u << buf;
 
     // ---- set-up: transform the raw fields in place into the stage constants ------------------
     double U1[Q], U2[Q];
@@ -607,6 +652,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         if (tn < ntiles) nxt = load_col_scalars<MODEL>(P, col_clamped(tn));
     }
 
+    CLB_PC(2)  // set-up
     // ---- Newton iterations -----------------------------------------------------------------
     double dx2 = 0.0;
 #ifndef CLB_NEWTON_UNROLL
@@ -679,6 +725,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 #pragma unroll
         for (int g = 0; g + WFULL <= Q; g += WFULL) closure_group(std::integral_constant<int, WFULL>{}, g);
         if constexpr (Q % WFULL != 0) closure_group(std::integral_constant<int, Q % WFULL>{}, Q - Q % WFULL);
+        CLB_PC(3)  // closures + T
         double h_out, h_in, dps_out, dps_in, K_out = 0.0, K_in = 0.0, T_out = 0.0, T_in = 0.0, eK_out = 0.0, eK_in = 0.0;
         nb_exchange<Gm>(h[0], h[Q - 1], innermost, h_out, h_in);
         nb_exchange<Gm>(dps[0], dps[Q - 1], innermost, dps_out, dps_in);
@@ -688,6 +735,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             nb_exchange<Gm>(eK[0], eK[Q - 1], innermost, eK_out, eK_in);
         }
 
+        CLB_PC(4)  // neighbour exchange
         // T_imp! and Wfact: face fluxes, residuals and the rows of W11 = dtgamma dT/dtheta - I
         double o1[Q], d1[Q], i1[Q], f1[Q], f2[Q], aE[Q + 1];
         double Fw_o, Fe_o = 0.0, aK_o;
@@ -741,6 +789,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             aK_o = aK_in;
         }
 
+        CLB_PC(5)  // faces, residuals, rows
         // ldiv! of W11: twisted Thomas, eliminated boundary -> seam (once per part, the carry crossing
         // lanes in between), 2x2 seam system, back substitution seam -> boundary
         double c1[Q], g1[Q], x1[Q], y[Q];
@@ -785,6 +834,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 if (pass + 1 < PARTS) xn = from_next_part<Gm::PARTD>(x1[0]);
             }
         }
+        CLB_PC(6)  // W11 solve
         const bool last = (it == max_iters - 1);
         if (last) {
             dx2 = 0.0;
@@ -796,6 +846,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             U1[q] -= x1[q];
             y[q] = dps[q] * x1[q];
         }
+        CLB_PC(7)  // update of theta
         if (MODEL == 1) {
             // ldiv!: BlockLowerTriangularSolve(theta_l): b2 = f2 - W21 x1 with
             // W21 = -dtgamma (D . Diag(interp(-e_l K)) . G . Diag(dpsi)) - I  (energy_hydrology.jl:545-556),
@@ -840,6 +891,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 if (last) dx2 = fma(x2[q], x2[q], dx2);
             }
         }
+        CLB_PC(8)  // W21 x1, W22 solve, update of rho_e
     }
 
     // ---- this tile's constants are dead: hand its buffer to the TMA ------------------------------------
@@ -851,11 +903,13 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             __syncwarp();
             // generic-proxy accesses of this buffer are ordered before the async-proxy writes of the TMA
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            CLB_PC(11)  // of the request: __syncwarp + proxy fence
             request_tile(tr, buf, 3);
             if (NBUF == 1) nxt = load_col_scalars<MODEL>(P, col_clamped(tr));
         }
     }
 
+    CLB_PC(9)  // next tile's request
     // ---- write the new state -----------------------------------------------------------------
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -873,7 +927,9 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     if (col_ok) dx2_acc += dx2 + dx2_int;
     if (NBUF == 2) buf ^= 1;
     else __syncwarp();
+    CLB_PC(10)  // stores
     }  // tiles
+    CLB_PC_FLUSH
     if (P.stats) accumulate_stats(P, dx2_acc, bad);  // only when the caller asked for clb_stats
 }
 

@@ -86,14 +86,18 @@ def test_host_step_repeated_calls(pinned):
 
 def test_pipelined_and_plain_routes_agree_bitwise():
     """CLB_HOST_NO_PIPELINE=1 forces the field-by-field route, CLB_HOST_NO_ZEROCOPY=1 the staged route for pinned
-    arrays (both read once per process): run each in a child."""
+    arrays, CLB_NO_ARENA_BOX=1 the lane kernel's one-box-per-field tile requests (all read once per process): run each
+    in a child."""
     code = ("import sys, numpy as np; sys.path[:0] = ['.', 'oracle', 'tests'];"
             "from test_cuda_host_step import _run; U, outs, pre, v = _run('energy_hydrology', 20000, True, pinned=True);"
             "np.save(sys.argv[1], outs['u_theta_l'])")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for tag, env in (("zerocopy", {}), ("staged", {"CLB_HOST_NO_ZEROCOPY": "1"}), ("plain", {"CLB_HOST_NO_PIPELINE": "1"})):
+    for tag, env in (("zerocopy", {}), ("staged", {"CLB_HOST_NO_ZEROCOPY": "1"}), ("plain", {"CLB_HOST_NO_PIPELINE": "1"}),
+                     ("boxes_per_field", {"CLB_NO_ARENA_BOX": "1"})):
         path = f"/tmp/clb_host_{tag}.npy"
         subprocess.run([sys.executable, "-c", code, path], cwd=root, env={**os.environ, **env}, check=True, timeout=600)
         res[tag] = np.load(path)
     assert np.array_equal(res["zerocopy"], res["plain"]) and np.array_equal(res["staged"], res["plain"])
+    # CLB_NO_ARENA_BOX=1: one TMA box per field instead of the two boxes of the arena's 3-D tensor
+    assert np.array_equal(res["boxes_per_field"], res["zerocopy"])
