@@ -576,7 +576,7 @@ int launch_lanes(clb_handle h, const clb::DevView &P, double dtg, int max_iters,
     clb::PairMaps maps;
     // the descriptors always describe the whole mirrors (P may be a column sub-range with shifted pointers;
     // its offset travels as g.col0)
-    TRY(make_pair_maps(h, col0 ? make_view(h) : P, CPW, Gm::kRowsLF, &maps, LF ? 0 : Gm::NR));
+    TRY(make_pair_maps(h, col0 ? make_view(h) : P, CPW, Gm::kRowsLF, &maps, (LF || NBUF != 2) ? 0 : Gm::NR));
     // programmatic dependent launch: the kernel's prologue (tables, barriers, the first tile's parameter
     // fields) may overlap the tail of the stream's previous kernel unless that kernel may be writing this
     // handle's parameter mirrors

@@ -390,9 +390,11 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         // One lane issues the boxes back to back.  (One box per lane -- lane j fetching field j -- costs ~1 000 cycles
         // per tile: UTMALDG takes its operands from uniform registers, so the divergent form becomes a loop over the
         // active lanes, ELECT + R2UR + UTMALDG each time; tools/phase_clocks.py.)
-        if (!LF && M.arena) {
+        if (!LF && NBUF == 2 && M.arena) {
             // Two boxes instead of one per field: a UTMALDG blocks the issuing warp for ~75 cycles (measured,
-            // tools/phase_clocks.py: 1 050 ticks per tile for 14 boxes).
+            // tools/phase_clocks.py: 1 050 ticks per tile for 14 boxes).  Double-buffered kernels only: a box is
+            // fetched row by row, and where the warp waits for the tile it has just requested (NBUF = 1) the many
+            // small boxes land sooner than two large ones (measured: the run-time-N octet 8-20 % slower with two).
             if (lane == 0) {
                 if (which & 1) mbar_expect_tx(bar, (unsigned)NRAW * kSlotB);
                 const unsigned dst0 = smem_u32(tiles + buf * kTileBytes);
