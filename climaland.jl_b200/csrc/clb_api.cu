@@ -650,7 +650,13 @@ int launch_octet(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 template <int CLOSURE, int MODEL, int Q>
 int launch_octet_rt(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 {
-    if constexpr (MODEL == 1) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 18, 1, 192, 1, true>(h, P, dtg, max_iters, 0);
+    // double-buffered (and then two TMA boxes of the arena per tile) where two tiles per warp fit the 227 KB and, for
+    // EnergyHydrology, 4 of the 18 slots fit the registers: N <= 40 (Richards), N <= 32 (EnergyHydrology).  Measured at
+    // 1e5 columns against the single-buffered form: Richards N = 20 / 30 / 40: 95 / 122 / 133 us against 109 / 141 /
+    // 182 us, EnergyHydrology N = 20: 190 against 244 us
+    if constexpr (MODEL == 1 && Q <= 4) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 14, 2, 192, 1, true>(h, P, dtg, max_iters, 0);
+    else if constexpr (MODEL == 0 && Q <= 5) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 11, 2, 256, 1, true>(h, P, dtg, max_iters, 0);
+    else if constexpr (MODEL == 1) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 18, 1, 192, 1, true>(h, P, dtg, max_iters, 0);
     else return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 11, 1, 256, 1, true>(h, P, dtg, max_iters, 0);
 }
 
@@ -861,14 +867,12 @@ int clb_create(clb_handle *out, const clb_config *cfg)
                              (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_OCTET);
         // 17 <= N <= 48: the octet with the level count at run time reads column-fastest mirrors; it is the choice
         // while a field stays below 80 MB (beyond that its tiles fall out of the TLB, see clb_implicit_step).  Measured
-        // at 1e5 columns (tools/time_other_n.py): faster than the lane-per-cell / generic kernels everywhere except
-        // EnergyHydrology with 25 <= N <= 31 (Q = 4: 316 us against the lane-per-cell kernel's 290 us)
+        // at 1e5 columns (tools/time_other_n.py): faster than the lane-per-cell / generic kernels at every N
         const int64_t ld0 = (cfg->n_columns + 31) / 32 * 32;
         const bool octet_rt = cfg->n_levels >= 17 && cfg->n_levels <= 48 && cfg->math_mode == CLB_MATH_FAST &&
                               !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
                               (cfg->kernel_variant == CLB_VARIANT_LANE_OCTET ||
-                               (cfg->kernel_variant == CLB_VARIANT_AUTO && ld0 * cfg->n_levels * 8 <= ((int64_t)80 << 20) &&
-                                !(cfg->model == CLB_ENERGY_HYDROLOGY && cfg->n_levels >= 25 && cfg->n_levels <= 31)));
+                               (cfg->kernel_variant == CLB_VARIANT_AUTO && ld0 * cfg->n_levels * 8 <= ((int64_t)80 << 20)));
         layout = (((!quad_ok && lane_per_cell) && !octet_rt) || octet50) ? CLB_LAYOUT_LEVEL_FASTEST : CLB_LAYOUT_COLUMN_FASTEST;
     }
     h->cfg.layout = layout;

@@ -9,7 +9,7 @@ from climaland_b200 import workloads
 from helpers import cuda_solver
 VAR = {1: "thread/column registers", 2: "thread/column generic", 3: "lane per cell", 4: "lane quad", 5: "lane quad pipelined", 6: "lane octet"}
 for model, iters, dt in (("richards", 2, 1800.0), ("energy_hydrology", 3, 900.0)):
-    for N in (10, 15, 16, 20, 30, 40, 50):  # AUTO: lane per cell (N <= 16 other than 15, 16), octet (17..48, 50)
+    for N in (10, 15, 16, 20, 25, 30, 40, 50):  # AUTO: lane per cell (N < 15), quad (15, 16), octet (17..48, 50)
         ncol = 100_000
         w = workloads.make_workload(model, ncol, N=N, seed=1, topmodel=True)
         ss = [cuda_solver(w, out_of_place=True) for _ in range(2)]
