@@ -646,7 +646,7 @@ int launch_octet(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 }
 
 // Octet with the level count taken at run time (template N = 0): Q cells per lane, NR = 8 Q level rows, for
-// NR - 8 < N <= NR; single-buffered persistent tiles of 4 columns cut from column-fastest mirrors.
+// NR - 8 < N <= NR; persistent tiles of 4 columns cut from column-fastest mirrors.
 template <int CLOSURE, int MODEL, int Q>
 int launch_octet_rt(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 {

@@ -1,6 +1,6 @@
 // soil_pair.cuh -- the lane kernels of the fused implicit stage: a column is split over 2 * PARTS lanes of a warp
-// (PARTS = 1 lane pair, 2 lane QUAD -- the bench kernel, N = 15 / 16 -- , 4 lane OCTET, N = 15 / 16 / 50), Q cells per
-// lane, 32 / (2 PARTS) columns per warp.
+// (PARTS = 1 lane pair, 2 lane QUAD -- the bench kernel, N = 15 / 16 -- , 4 lane OCTET, N = 15 / 16 / 50 compiled in
+// and 17 .. 48 read at run time), Q cells per lane, 32 / (2 PARTS) columns per warp.
 //
 // The lanes of a column form two halves: the "bottom" half holds the levels from the bottom boundary up to the seam,
 // the "top" half the levels from the top boundary down to the seam (NR = 2 PARTS Q level rows; rows >= N are pads at
@@ -22,10 +22,13 @@
 //     block) live in SHARED memory, in a warp-private tile (a lane only ever touches its own column: no block
 //     barriers); with the half in the low lane-group bit the quad's slot accesses are bank-conflict free.  The
 //     iterate and the residual's constant part stay in registers;
-//   * every field is read from HBM once, by TMA: one cp.async.bulk.tensor per field and warp brings the
-//     [N levels x CPW columns] box of the mirror straight into that tile, where it is transformed in place into the
-//     stage constants; persistent warps walk over tiles and request the tile after next (double-buffered) or
-//     prefetch the next one to L2 (single-buffered) while they compute; the new state is written once.
+//   * every field is read from HBM once, by TMA, straight into that tile, where it is transformed in place into the
+//     stage constants: the double-buffered kernels fetch a tile of ALL fields with two cp.async.bulk.tensor.3d boxes
+//     [fields x NR level rows x CPW columns] of the handle's arena of equally spaced mirrors (a UTMALDG costs the
+//     issuing warp ~75 cycles, so one box per field was 7 % of a tile's time), the single-buffered ones and
+//     level-fastest mirrors with one [N levels x CPW columns] box per field; persistent warps walk over tiles and
+//     request the tile after next (double-buffered) or prefetch the next one to L2 (single-buffered) while they
+//     compute; the new state is written once.
 //
 // Mirror layout: column-fastest (sl = ld, sc = 1) by default; LF = true reads level-fastest mirrors (sl = 1, sc = N,
 // N even: TMA needs 16-byte global strides), where a tile is one contiguous piece of each field.
