@@ -573,48 +573,56 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         aK8 = (Kl[Q - 1] + K_in) * G.hidzf[half][r0 + Q];
         aC8 = (kap[Q - 1] + kap_in) * G.hidzf[half][r0 + Q];
         double aCo[Q], o22[Q], d22[Q], i22[Q];
-        double nu[Q], theta_r[Q], iSs[Q], pa[Q], pb[Q], pm[Q], theta[Q], sat[Q], theta_i[Q], rcds[Q], rho_e[Q];
+        // CH cells at a time: all Q of them up to 4 cells per lane; one by one beyond (11 raw values per cell: with
+        // Q = 7 the N = 50 kernel, already at 254 registers, spills -- measured 498 against 456 us)
+        constexpr int CH = (Q <= 4) ? Q : 1;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const bool real = level_of(q) < N;
-            nu[q] = S.template get<0>(q); theta_r[q] = S.template get<1>(q);
-            iSs[q] = S.template get<2>(q); pa[q] = S.template get<3>(q); pb[q] = S.template get<4>(q);
-            pm[q] = (CLOSURE == kVanGenuchten) ? S.template get<5>(q) : 0.0;
-            theta[q] = S.template get<6>(q); sat[q] = S.template get<7>(q); theta_i[q] = S.template get<8>(q);
-            rcds[q] = S.template get<9>(q); rho_e[q] = S.template get<13>(q);
-            if (!real) {
-                nu[q] = 0.5; theta_r[q] = 0.1; iSs[q] = 1e3; pb[q] = (CLOSURE == kVanGenuchten) ? 0.5 : 2.0;
-                pa[q] = (CLOSURE == kVanGenuchten) ? 1.0 : -1.0; pm[q] = 2.0;
-                theta[q] = 0.3; sat[q] = 0.0; theta_i[q] = 0.0; rcds[q] = 1e6; rho_e[q] = 0.0;
+        for (int q0 = 0; q0 < Q; q0 += CH) {
+            double nu[CH], theta_r[CH], iSs[CH], pa[CH], pb[CH], pm[CH], theta[CH], sat[CH], theta_i[CH], rcds[CH], rho_e[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int q = q0 + j;
+                const bool real = level_of(q) < N;
+                nu[j] = S.template get<0>(q); theta_r[j] = S.template get<1>(q);
+                iSs[j] = S.template get<2>(q); pa[j] = S.template get<3>(q); pb[j] = S.template get<4>(q);
+                pm[j] = (CLOSURE == kVanGenuchten) ? S.template get<5>(q) : 0.0;
+                theta[j] = S.template get<6>(q); sat[j] = S.template get<7>(q); theta_i[j] = S.template get<8>(q);
+                rcds[j] = S.template get<9>(q); rho_e[j] = S.template get<13>(q);
+                if (!real) {
+                    nu[j] = 0.5; theta_r[j] = 0.1; iSs[j] = 1e3; pb[j] = (CLOSURE == kVanGenuchten) ? 0.5 : 2.0;
+                    pa[j] = (CLOSURE == kVanGenuchten) ? 1.0 : -1.0; pm[j] = 2.0;
+                    theta[j] = 0.3; sat[j] = 0.0; theta_i[j] = 0.0; rcds[j] = 1e6; rho_e[j] = 0.0;
+                }
             }
-        }
-        ClosureConst cc[Q];
+            ClosureConst cc[CH];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) cc[q] = pair_prepare<CLOSURE, false>(iSs[q], pa[q], pb[q], pm[q], theta_r[q], nu[q] - theta_i[q]);
+            for (int j = 0; j < CH; ++j) cc[j] = pair_prepare<CLOSURE, false>(iSs[j], pa[j], pb[j], pm[j], theta_r[j], nu[j] - theta_i[j]);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const double nu_eff = nu[q] - theta_i[q];
-            U1[q] = theta[q];
-            U2[q] = rho_e[q];
-            // lagged coefficients of the cell's outer face (zero table entry at the column boundary)
-            const double hid_o = G.hidzf[half][r0 + q];
-            const double aK_o = (Kl[q] + ((q == 0) ? K_out : Kl[q - 1])) * hid_o;
-            aCo[q] = (kap[q] + ((q == 0) ? kap_out : kap[q - 1])) * hid_o;
-            S.template put<E_THETA_R>(q, theta_r[q]);
-            S.template put<E_NU_EFF>(q, nu_eff);
-            S.template put<E_ICE>(q, theta_i[q] * E.rho_i * E.LH_f0);
-            S.template put<E_RCBASE>(q, fma(theta_i[q], C2, rcds[q]));
-            S.template put<E_CA>(q, cc[q].ca);
-            S.template put<E_KC>(q, Kl[q] * C1);
-            S.template put<E_CB>(q, cc[q].cb);
-            S.template put<E_INV_SS>(q, cc[q].inv_Ss);
-            S.template put<E_CC>(q, cc[q].cc);
-            S.template put<E_CD>(q, cc[q].cd);
-            S.template put<E_AK>(q, aK_o);
-            S.template put<E_AC>(q, aCo[q]);
-            S.template put<E_T1>(q, fma(-dtg, src_w * sat[q], theta[q]));
-            S.template put<E_T2>(q, fma(-dtg, src_e * sat[q], rho_e[q]));
-            S.template put<E_IRANGE>(q, cc[q].inv_range);
+            for (int j = 0; j < CH; ++j) {
+                const int q = q0 + j;
+                const double nu_eff = nu[j] - theta_i[j];
+                U1[q] = theta[j];
+                U2[q] = rho_e[j];
+                // lagged coefficients of the cell's outer face (zero table entry at the column boundary)
+                const double hid_o = G.hidzf[half][r0 + q];
+                const double aK_o = (Kl[q] + ((q == 0) ? K_out : Kl[q - 1])) * hid_o;
+                aCo[q] = (kap[q] + ((q == 0) ? kap_out : kap[q - 1])) * hid_o;
+                S.template put<E_THETA_R>(q, theta_r[j]);
+                S.template put<E_NU_EFF>(q, nu_eff);
+                S.template put<E_ICE>(q, theta_i[j] * E.rho_i * E.LH_f0);
+                S.template put<E_RCBASE>(q, fma(theta_i[j], C2, rcds[j]));
+                S.template put<E_CA>(q, cc[j].ca);
+                S.template put<E_KC>(q, Kl[q] * C1);
+                S.template put<E_CB>(q, cc[j].cb);
+                S.template put<E_INV_SS>(q, cc[j].inv_Ss);
+                S.template put<E_CC>(q, cc[j].cc);
+                S.template put<E_CD>(q, cc[j].cd);
+                S.template put<E_AK>(q, aK_o);
+                S.template put<E_AC>(q, aCo[q]);
+                S.template put<E_T1>(q, fma(-dtg, src_w * sat[j], theta[j]));
+                S.template put<E_T2>(q, fma(-dtg, src_e * sat[j], rho_e[j]));
+                S.template put<E_IRANGE>(q, cc[j].inv_range);
+            }
         }
         // rows of W22 = dtgamma d(T_rho_e)/d(rho_e) - I and their elimination, boundary -> seam
 #pragma unroll
