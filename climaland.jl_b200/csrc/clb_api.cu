@@ -6,6 +6,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -102,6 +103,7 @@ bool is_col_field(int f) { return f >= CLB_F_NUM_CELL && f < CLB_F_NUM; }
 
 constexpr int kBlock = 128;
 constexpr int kMaxLevels = 512;
+constexpr int kMaxDevices = 64;  // device ordinals with a cached per-device kernel configuration
 
 }  // namespace
 
@@ -159,6 +161,7 @@ struct clb_handle_s {
     clb_runoff_params runoff_k = {};
     bool runoff_set = false;
     bool co2_top_state[2] = {false, false};  // SoilCO2Model: AtmosCO2StateBC / AtmosO2StateBC at the top
+    int host_route = 0, host_chunks = 0, tile_boxes = 0;  // CLB_OPT_HOST_ROUTE / _HOST_CHUNKS / _TILE_BOXES
     // multi-GPU
     NcclComm comm = nullptr;
     int32_t n_ranks = 1, rank = 0;
@@ -522,8 +525,7 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, int box
             h->pair_map_src[j] = src[j];
         }
     }
-    static const bool no_arena = getenv("CLB_NO_ARENA_BOX") != nullptr;
-    bool spaced = box_levels_arena > 0 && h->sc == 1 && !no_arena;
+    bool spaced = box_levels_arena > 0 && h->sc == 1 && h->tile_boxes == 0;
     for (int j = 1; j < n && spaced; ++j) spaced = src[j] == src[0] + (size_t)j * h->cell_elems;
     if (spaced && (h->arena_map_src != src[0] || h->arena_map_box != box_columns * 1000 + box_levels_arena)) {
         // the parameter fields come first in the box order of Richards (slots 0-6); EnergyHydrology's rho_c_ds (slot 9)
@@ -557,16 +559,18 @@ int launch_lanes(clb_handle h, const clb::DevView &P, double dtg, int max_iters,
     constexpr int CPW = Gm::CPW;
     auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB, Q, LF>;
     const size_t smem = clb::pair_smem_bytes<PARTS, NS, NBUF, BLOCK, Q, LF>();
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    // Function attributes are per DEVICE (and per instantiation): one flag per device ordinal, so that a process
+    // holding handles on several GPUs opts every one of them in to the > 48 KB of dynamic shared memory.
+    static std::atomic<bool> configured[kMaxDevices];
+    const int dev = h->cfg.device;
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev].load(std::memory_order_acquire)) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev].store(true, std::memory_order_release);
     }
     const int64_t tiles = (P.ncol + CPW - 1) / CPW;
     int64_t blocks = (tiles * 32 + BLOCK - 1) / BLOCK;
-    static const bool persist = getenv("CLB_QUAD_PERSIST") != nullptr;
-    if (PERSISTENT || persist) {
+    if (PERSISTENT) {
         int sms = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
         blocks = std::min<int64_t>(blocks, (int64_t)sms * MINB);
@@ -967,6 +971,17 @@ int clb_set_option(clb_handle h, int32_t option, int64_t value)
     case CLB_OPT_O2_TOP_STATE:
         h->co2_top_state[1] = value != 0;
         return CLB_OK;
+    case CLB_OPT_HOST_ROUTE:
+        if (value < 0 || value > 2) return fail(CLB_ERR_INVALID, "clb_set_option: CLB_OPT_HOST_ROUTE takes 0, 1 or 2");
+        h->host_route = (int)value;
+        return CLB_OK;
+    case CLB_OPT_HOST_CHUNKS:
+        if (value < 0 || value > 16) return fail(CLB_ERR_INVALID, "clb_set_option: CLB_OPT_HOST_CHUNKS takes 0 .. 16");
+        h->host_chunks = (int)value;
+        return CLB_OK;
+    case CLB_OPT_TILE_BOXES:
+        h->tile_boxes = value != 0;
+        return CLB_OK;
     default:
         return fail(CLB_ERR_INVALID, "clb_set_option: unknown option %d", option);
     }
@@ -1055,6 +1070,9 @@ int clb_set_field(clb_handle h, int32_t field, const double *src, int64_t stride
     if (mem == CLB_HOST) {
         TRY(ensure_stage(h, (size_t)extent * sizeof(double)));
         CUDA_TRY(cudaMemcpyAsync(h->d_stage, src, (size_t)extent * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        // a pinned source makes that copy truly asynchronous: wait for it, so that the caller may reuse or free
+        // `src` as soon as this call returns (the relayout below stays asynchronous)
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
         dsrc = h->d_stage;
     } else if (mem != CLB_DEVICE) {
         return fail(CLB_ERR_INVALID, "clb_set_field: mem must be CLB_HOST or CLB_DEVICE");
@@ -1075,7 +1093,6 @@ int clb_set_field(clb_handle h, int32_t field, const double *src, int64_t stride
     CUDA_TRY(cudaGetLastError());
     h->field_set[field] = true;
     if (is_closure_param(field)) h->prep_dirty = true;
-    if (is_invariant_param(field)) h->param_write_pending = true;
     if (is_invariant_param(field)) h->param_write_pending = true;
     return CLB_OK;
 }
@@ -1492,9 +1509,8 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters, cons
         return fail(CLB_ERR_INVALID, "clb_implicit_step_host: null field list");
     {
         DeviceGuard guard(h->cfg.device);
-        static const bool no_pipeline = getenv("CLB_HOST_NO_PIPELINE") != nullptr;
-        const int rc = no_pipeline ? 0 : step_host_pipelined(h, dtgamma, max_iters, in_fields, in_ptrs, n_in, out_fields,
-                                                             out_ptrs, n_out);
+        const int rc = (h->host_route == 2) ? 0 : step_host_pipelined(h, dtgamma, max_iters, in_fields, in_ptrs, n_in, out_fields,
+                                                                      out_ptrs, n_out);
         if (rc != 0) return rc < 0 ? rc : CLB_OK;
     }
     const int N = h->cfg.n_levels;

@@ -73,6 +73,21 @@ class SoilColumnSolver:
             idx = np.ascontiguousarray(active_columns, dtype=np.int64)
             check(self.L.clb_set_active_columns(self.h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
 
+    @classmethod
+    def from_workload(cls, w, closure=VAN_GENUCHTEN, top_bc=TOP_FLUX, bottom_bc=BOT_FLUX, **kw):
+        """A solver with every field of a `workloads.make_workload` dict uploaded (bench, smoke, tests)."""
+        model = RICHARDS if w["model"] == "richards" else ENERGY_HYDROLOGY
+        s = cls(model=model, n_columns=w["ncol"], z_f=w["z_f"], z_c=w["z_c"], closure=closure, top_bc=top_bc,
+                bottom_bc=bottom_bc, has_topmodel_source=w.get("topmodel", False), **kw)
+        for k, v in w.items():
+            if k.lower() in FIELDS:
+                s.set(k, v)
+        return s
+
+    def set_option(self, name, value):
+        """clb_set_option by name: "host_route", "host_chunks", "tile_boxes", "out_of_place", ..."""
+        check(self.L.clb_set_option(self.h, K["CLB_OPT_" + name.upper()], int(value)))
+
     # ---- lifetime ----------------------------------------------------------
     def close(self):
         if getattr(self, "h", None) is not None and self.h:

@@ -95,7 +95,13 @@ enum { CLB_LAYOUT_AUTO = 0,
 /* clb_set_option */
 enum { CLB_OPT_OUT_OF_PLACE = 1,        /* fused stage reads Y (= temp) and writes the U fields */
        CLB_OPT_CO2_TOP_STATE = 2,       /* SoilCO2Model: the top BC of CO2 is AtmosCO2StateBC (value CLB_F_CO2_C_ATM) */
-       CLB_OPT_O2_TOP_STATE = 3 };      /* ... of O2 is AtmosO2StateBC (value CLB_F_O2_C_ATM); 0 = flux values */
+       CLB_OPT_O2_TOP_STATE = 3,        /* ... of O2 is AtmosO2StateBC (value CLB_F_O2_C_ATM); 0 = flux values */
+       CLB_OPT_HOST_ROUTE = 4,          /* clb_implicit_step_host: 0 = the library's choice (zero-copy for pinned caller
+                                           arrays, staged copies for pageable ones), 1 = staged copies always,
+                                           2 = field by field (clb_set_field / clb_implicit_step / clb_get_field) */
+       CLB_OPT_HOST_CHUNKS = 5,         /* column chunks of the pipelined host route (0 = default, 4) */
+       CLB_OPT_TILE_BOXES = 6 };        /* lane kernels: 0 = two TMA boxes of the arena per tile where the mirrors are
+                                           equally spaced, 1 = one box per field always (same results, bit for bit) */
 
 /* Field ids.  "cell" fields are N x ncol, "col" fields are ncol. */
 typedef enum {
@@ -214,7 +220,9 @@ int clb_set_active_columns(clb_handle h, const int64_t *idx, int64_t n);
 /* Copy a caller array into / out of the library mirror.  Element (i, c) of the
  * caller array is at  ptr[i*stride_level + idx[c]*stride_column]  (strides in
  * elements, >= 0; stride_level is ignored for per-column fields).  `mem` says
- * whether ptr is a host or a device pointer. */
+ * whether ptr is a host or a device pointer.  A host source has been read completely
+ * when clb_set_field returns (it may be reused or freed); a device source is read
+ * asynchronously on the handle's stream.  clb_get_field to a host pointer synchronises. */
 int clb_set_field(clb_handle h, int32_t field, const double *src, int64_t stride_level,
                   int64_t stride_column, int32_t mem);
 int clb_get_field(clb_handle h, int32_t field, double *dst, int64_t stride_level,
@@ -315,7 +323,9 @@ int clb_ldiv_diagonal(clb_handle h, int32_t w_field, int32_t b_field, int32_t x_
  * convergence checker, Simulations.jl:127-135).  With tol >= 0 the iterations
  * are separate launches that stop -- without a host round trip -- once
  * ||dx||_2 <= tol over all columns of all ranks.  stats may be NULL; when it is
- * not, the call synchronises the stream to fill it. */
+ * not, the call synchronises the stream to fill it.  With a communicator (clb_comm_init)
+ * a non-NULL stats and the tol >= 0 path issue an all-reduce: every rank must then make
+ * the same choice (stats NULL or not, same tol) in the same call. */
 int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double tol, clb_stats *stats);
 
 /* CLB_VARIANT_* the last clb_implicit_step launched (what CLB_VARIANT_AUTO resolved to; 0 before the first step). */

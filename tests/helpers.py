@@ -39,13 +39,7 @@ def oracle_problem(w, closure=0, top_bc=0, bottom_bc=0, nthreads=1):
 
 def cuda_solver(w, closure=0, top_bc=0, bottom_bc=0, **kw):
     import climaland_b200 as cl
-    model = cl.RICHARDS if w["model"] == "richards" else cl.ENERGY_HYDROLOGY
-    s = cl.SoilColumnSolver(model=model, n_columns=w["ncol"], z_f=w["z_f"], z_c=w["z_c"], closure=closure,
-                            top_bc=top_bc, bottom_bc=bottom_bc, has_topmodel_source=w.get("topmodel", False), **kw)
-    for k, v in w.items():
-        if k.lower() in cl.FIELDS:
-            s.set(k, v)
-    return s
+    return cl.SoilColumnSolver.from_workload(w, closure=closure, top_bc=top_bc, bottom_bc=bottom_bc, **kw)
 
 
 def rel_err(a, b):

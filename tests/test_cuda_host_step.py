@@ -2,8 +2,6 @@
 out): the pipelined route (column chunks, H2D / kernels / D2H overlapped on three streams) and the
 field-by-field route must both give the oracle's stage, and each other's bits."""
 import os
-import subprocess
-import sys
 
 import numpy as np
 import pytest
@@ -29,7 +27,7 @@ def _pin(a):
 _pin.keep = []
 
 
-def _run(model, ncol, out_of_place, seed=3, steps=1, pinned=False):
+def _run(model, ncol, out_of_place, seed=3, steps=1, pinned=False, options=None):
     import climaland_b200  # noqa: F401
     from climaland_b200 import workloads
     eh = model == "energy_hydrology"
@@ -37,6 +35,8 @@ def _run(model, ncol, out_of_place, seed=3, steps=1, pinned=False):
     w = workloads.make_workload(model, ncol, N=15, seed=seed, topmodel=True)
     P, U, p = oracle_problem(w, nthreads=os.cpu_count() or 1)
     s = cuda_solver(w, out_of_place=out_of_place)
+    for k, v in (options or {}).items():
+        s.set_option(k, v)
     names = IN_EH if eh else IN_RI
     pre = "u" if out_of_place else "y"
     outs = {f"{pre}_theta_l": np.zeros((ncol, 15)), f"{pre}_intf_w": np.zeros(ncol)}
@@ -85,19 +85,12 @@ def test_host_step_repeated_calls(pinned):
 
 
 def test_pipelined_and_plain_routes_agree_bitwise():
-    """CLB_HOST_NO_PIPELINE=1 forces the field-by-field route, CLB_HOST_NO_ZEROCOPY=1 the staged route for pinned
-    arrays, CLB_NO_ARENA_BOX=1 the lane kernel's one-box-per-field tile requests (all read once per process): run each
-    in a child."""
-    code = ("import sys, numpy as np; sys.path[:0] = ['.', 'oracle', 'tests'];"
-            "from test_cuda_host_step import _run; U, outs, pre, v = _run('energy_hydrology', 20000, True, pinned=True);"
-            "np.save(sys.argv[1], outs['u_theta_l'])")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    """CLB_OPT_HOST_ROUTE = 2 forces the field-by-field route, 1 the staged route for pinned arrays, CLB_OPT_TILE_BOXES
+    = 1 the lane kernel's one-box-per-field tile requests, CLB_OPT_HOST_CHUNKS another chunking: same bits."""
     res = {}
-    for tag, env in (("zerocopy", {}), ("staged", {"CLB_HOST_NO_ZEROCOPY": "1"}), ("plain", {"CLB_HOST_NO_PIPELINE": "1"}),
-                     ("boxes_per_field", {"CLB_NO_ARENA_BOX": "1"})):
-        path = f"/tmp/clb_host_{tag}.npy"
-        subprocess.run([sys.executable, "-c", code, path], cwd=root, env={**os.environ, **env}, check=True, timeout=600)
-        res[tag] = np.load(path)
-    assert np.array_equal(res["zerocopy"], res["plain"]) and np.array_equal(res["staged"], res["plain"])
-    # CLB_NO_ARENA_BOX=1: one TMA box per field instead of the two boxes of the arena's 3-D tensor
-    assert np.array_equal(res["boxes_per_field"], res["zerocopy"])
+    for tag, opt in (("zerocopy", {}), ("staged", {"host_route": 1}), ("plain", {"host_route": 2}),
+                     ("boxes_per_field", {"tile_boxes": 1}), ("chunks7", {"host_chunks": 7})):
+        _, outs, _, _ = _run("energy_hydrology", 20000, True, pinned=True, options=opt)
+        res[tag] = outs["u_theta_l"].copy()
+    for tag in ("staged", "zerocopy", "boxes_per_field", "chunks7"):
+        assert np.array_equal(res[tag], res["plain"]), tag
