@@ -608,7 +608,10 @@ int launch_lanes(clb_handle h, const clb::DevView &P, double dtg, int max_iters,
 template <int CLOSURE, int MODEL, int N, bool PIPELINED>
 int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0)
 {
-    constexpr int NS = (MODEL == 1) ? (PIPELINED ? 14 : CLB_QUAD_NS) : 11;
+#ifndef CLB_QUAD_NBUF
+#define CLB_QUAD_NBUF 2
+#endif
+    constexpr int NS = (MODEL == 1) ? ((PIPELINED && CLB_QUAD_NBUF == 2) ? 14 : CLB_QUAD_NS) : 11;
     if constexpr (PIPELINED)
 #ifndef CLB_QUAD_BLOCK_R
 #define CLB_QUAD_BLOCK_R 256
@@ -616,7 +619,7 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, 
 #ifndef CLB_QUAD_BLOCK
 #define CLB_QUAD_BLOCK 256  // 8 warps per SM; 128 = one warp per sub-partition (latency experiment)
 #endif
-        return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 2, (MODEL == 0) ? CLB_QUAD_BLOCK_R : CLB_QUAD_BLOCK, 1, true>(h, P, dtg, max_iters,
+        return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, CLB_QUAD_NBUF, (MODEL == 0) ? CLB_QUAD_BLOCK_R : CLB_QUAD_BLOCK, 1, true>(h, P, dtg, max_iters,
                                                                                                                 col0);
     else
         return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 1, 128, CLB_QUAD_MINB, false>(h, P, dtg, max_iters, col0);
@@ -1426,6 +1429,13 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
     nvtxRangePushA("implicit_step!");
     int iters_done = max_iters;
     if (fixed) {
+#ifdef CLB_DEV_FAST  // tuning builds (tools/build_variant.sh NAME -DCLB_DEV_FAST): only the pipelined N = 15 quad is compiled
+        if (variant == CLB_VARIANT_LANE_QUAD_PIPELINED && N == 15) {
+            TRY((launch_quad_n<15, true>(h, P, dtgamma, max_iters)));
+        } else if (variant == CLB_VARIANT_LANE_QUAD || variant == CLB_VARIANT_LANE_QUAD_PIPELINED ||
+                   variant == CLB_VARIANT_LANE_OCTET) {
+            return fail(CLB_ERR_INVALID, "CLB_DEV_FAST build: only the pipelined N = 15 quad is compiled");
+#else
         if (variant == CLB_VARIANT_LANE_QUAD) {
             if (N == 15) TRY((launch_quad_n<15, false>(h, P, dtgamma, max_iters)));
             else TRY((launch_quad_n<16, false>(h, P, dtgamma, max_iters)));
@@ -1440,6 +1450,7 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
             else if (N <= 32) TRY((launch_octet_rt_q<4>(h, P, dtgamma, max_iters)));
             else if (N <= 40) TRY((launch_octet_rt_q<5>(h, P, dtgamma, max_iters)));
             else TRY((launch_octet_rt_q<6>(h, P, dtgamma, max_iters)));
+#endif
         } else if (variant == CLB_VARIANT_LANE_PER_CELL) {
             const int cpw = (N <= 15) ? 2 : 1;  // columns per warp (one lane of each segment is a ghost)
             const int64_t warps = (P.ncol + cpw - 1) / cpw;
@@ -1528,11 +1539,11 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters, cons
 
 #ifdef CLB_PHASE_CLOCKS
 // tuning builds only: the lane kernels' phase clocks summed over warps since the last call (then reset)
-__attribute__((visibility("default"))) int clb_debug_phase_clocks(unsigned long long *out12)
+__attribute__((visibility("default"))) int clb_debug_phase_clocks(unsigned long long *out16)
 {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out12, clb::g_phase_clk, sizeof(unsigned long long) * 12);
-    unsigned long long zero[12] = {};
+    cudaMemcpyFromSymbol(out16, clb::g_phase_clk, sizeof(unsigned long long) * 16);
+    unsigned long long zero[16] = {};
     cudaMemcpyToSymbol(clb::g_phase_clk, zero, sizeof(zero));
     return CLB_OK;
 }

@@ -158,7 +158,7 @@ __device__ __forceinline__ void log_tab(const MathTab &T, const double (&x)[W], 
         const int hx = __double2hiint(x[j]);
         const int tmp = hx - mtab::kLogOffHi;
         const int k = tmp >> 20;
-        e[j] = T.logt[(tmp >> 13) & (mtab::kLogN - 1)];
+                e[j] = T.logt[(tmp >> 13) & (mtab::kLogN - 1)];
         z[j] = __hiloint2double(hx - (tmp & 0xfff00000), __double2loint(x[j]));
         dk[j] = __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;
     }
@@ -184,7 +184,7 @@ __device__ __forceinline__ void exp_tab(const MathTab &T, const double (&x)[W], 
     CLB_V {
         k[j] = __double2loint(t[j]);
         t[j] = t[j] - MAGIC;
-        tb[j] = T.expt[k[j] & (mtab::kExpN - 1)];
+                tb[j] = T.expt[k[j] & (mtab::kExpN - 1)];
     }
     CLB_V r[j] = fma(t[j], -mtab::kLn2NHi, x[j]);
     CLB_V r[j] = fma(t[j], -mtab::kLn2NLo, r[j]);

@@ -326,14 +326,19 @@ __device__ __forceinline__ ColScalars load_col_scalars(const DevView &P, int64_t
 // Phase clocks (tuning builds only, -DCLB_PHASE_CLOCKS; tools/phase_clocks.py): lane 0 of every warp adds the SM
 // clock ticks it spent in each phase of a tile; read back through clb_debug_phase_clocks.
 #ifdef CLB_PHASE_CLOCKS
-__device__ unsigned long long g_phase_clk[12];
-#define CLB_PC_DECL unsigned pc_[12] = {}; unsigned pc_t_ = (unsigned)clock();
+__device__ unsigned long long g_phase_clk[16];
+#define CLB_PC_DECL unsigned pc_[16] = {}; unsigned pc_t_ = (unsigned)clock();
 #define CLB_PC(k) { const unsigned now_ = (unsigned)clock(); pc_[k] += now_ - pc_t_; pc_t_ = now_; }
-#define CLB_PC_FLUSH if (lane == 0) { _Pragma("unroll") for (int k_ = 0; k_ < 12; ++k_) atomicAdd(&g_phase_clk[k_], (unsigned long long)pc_[k_]); }
+#define CLB_PC_FLUSH if (lane == 0) { _Pragma("unroll") for (int k_ = 0; k_ < 16; ++k_) atomicAdd(&g_phase_clk[k_], (unsigned long long)pc_[k_]); }
 #else
 #define CLB_PC_DECL
 #define CLB_PC(k)
 #define CLB_PC_FLUSH
+#endif
+#if defined(CLB_PHASE_CLOCKS) && defined(CLB_PC_SETUP)
+#define CLB_PCS(k) CLB_PC(k)  // sub-phases of the set-up (slots 12 .. 15; the rest of it stays in slot 2)
+#else
+#define CLB_PCS(k)
 #endif
 template <int CLOSURE, int MODEL, int NT, int PARTS, int NS, int NBUF, int BLOCK, int MINB, int QC = kPairQ / PARTS,
           bool LF = false>
@@ -497,15 +502,19 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     // its dependent chain interleaves with the set-up below
     double dx2_int = 0.0;
     {
+        // The recurrence U <- U - (-(t + dtg T - U)) started at U = t, written out: U_1 = t + ((t + dtg T) - t), and
+        // from the second iteration on U = a := t + dtg T exactly (a - U_1 is exactly representable and U_1 + (a - U_1)
+        // = a), with dx = -(a - U_1) in the second iteration and -0 afterwards.  Straight-line code: as a loop with a
+        // run-time trip count it was a serial chain of ~4 dependent DADDs per iteration in basic blocks of its own.
         const double tiw = cur.intF_w, tie = cur.intF_e;
         const double Tiw = -(top_w - bot_w) - ld_Rss, Tie = -(top_h - bot_h) - ld_Ress;
-        double Uw = tiw, dxw = 0.0, Ue = tie, dxe = 0.0;
-        for (int it = 0; it < max_iters; ++it) {
-            dxw = -(tiw + dtg * Tiw - Uw);
-            Uw -= dxw;
-            dxe = -(tie + dtg * Tie - Ue);
-            Ue -= dxe;
-        }
+        const double aw = tiw + dtg * Tiw, ae = tie + dtg * Tie;
+        const double dw1 = -(aw - tiw), de1 = -(ae - tie);
+        const double Uw1 = tiw - dw1, Ue1 = tie - de1;
+        const double dw2 = -(aw - Uw1), de2 = -(ae - Ue1);
+        const double Uw = (max_iters >= 2) ? Uw1 - dw2 : Uw1, Ue = (max_iters >= 2) ? Ue1 - de2 : Ue1;
+        const double dxw = (max_iters == 1) ? dw1 : ((max_iters == 2) ? dw2 : 0.0);
+        const double dxe = (max_iters == 1) ? de1 : ((max_iters == 2) ? de2 : 0.0);
         if (idx == 0 && col_ok) {
             dx2_int = dxw * dxw + dxe * dxe;
             P.out_intF_w[c] = Uw;
@@ -566,12 +575,14 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             rc[q] = fm::rcp(volumetric_heat_capacity(real ? S.template get<12>(q) : 0.0, real ? S.template get<8>(q) : 0.0,
                                                      real ? S.template get<9>(q) : 1e6, E));
         }
+        CLB_PCS(12)  // lagged loads, 1/rho_c
         double K_out, K_in, kap_out, kap_in, rc_out, rc_in;
         nb_exchange<Gm>(Kl[0], Kl[Q - 1], innermost, K_out, K_in);
         nb_exchange<Gm>(kap[0], kap[Q - 1], innermost, kap_out, kap_in);
         nb_exchange<Gm>(rc[0], rc[Q - 1], innermost, rc_out, rc_in);
         aK8 = (Kl[Q - 1] + K_in) * G.hidzf[half][r0 + Q];
         aC8 = (kap[Q - 1] + kap_in) * G.hidzf[half][r0 + Q];
+        CLB_PCS(13)  // exchange of the lagged fields
         double aCo[Q], o22[Q], d22[Q], i22[Q];
         // CH cells at a time: all Q of them up to 4 cells per lane; one by one beyond (11 raw values per cell: with
         // Q = 7 the N = 50 kernel, already at 254 registers, spills -- measured 498 against 456 us)
@@ -624,6 +635,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 S.template put<E_IRANGE>(q, cc[j].inv_range);
             }
         }
+        CLB_PCS(14)  // constants
         // rows of W22 = dtgamma d(T_rho_e)/d(rho_e) - I and their elimination, boundary -> seam
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -668,6 +680,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             }
         }
         r22 = fm::rcp(fma(-c22_last, xchg<Gm::SEAM>(c22_last), 1.0));
+        CLB_PCS(15)  // W22 rows, factorisation
     }
 
     // The next tile's per-column scalars are fetched only now, after everything that consumes this tile's has
@@ -682,6 +695,43 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     CLB_PC(2)  // set-up
     // ---- Newton iterations -----------------------------------------------------------------
     double dx2 = 0.0;
+    // right-hand side of the pending (rho_e, rho_e) solve, already scaled by the pivots' reciprocals (b2 den22)
+    double b2p[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) b2p[q] = 0.0;
+    // forward / backward substitution with the factors of the set-up, then the update of rho_e
+    auto w22_solve = [&](const bool is_last) {
+        if constexpr (MODEL == 1) {
+        double g2[Q], gin = 0.0;
+#pragma unroll
+        for (int pass = 0; pass < PARTS; ++pass) {
+            double gp = gin;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                gp = fma(-S.template get<E_OD22>(q), gp, b2p[q]);
+                g2[q] = gp;
+            }
+            if (pass + 1 < PARTS) {
+                const double rg_ = from_prev_part<Gm::PARTD>(gp);
+                gin = outermost ? 0.0 : rg_;
+            }
+        }
+        const double xs = fma(-c22_last, xchg<Gm::SEAM>(g2[Q - 1]), g2[Q - 1]) * r22;
+        double xn = xs, x2[Q];
+#pragma unroll
+        for (int pass = 0; pass < PARTS; ++pass) {
+            x2[Q - 1] = (pass == 0) ? xs : (innermost ? xs : fma(-c22_last, xn, g2[Q - 1]));
+#pragma unroll
+            for (int q = Q - 2; q >= 0; --q) x2[q] = fma(-S.template get<E_C22>(q), x2[q + 1], g2[q]);
+            if (pass + 1 < PARTS) xn = from_next_part<Gm::PARTD>(x2[0]);
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            U2[q] -= x2[q];
+            if (is_last) dx2 = fma(x2[q], x2[q], dx2);
+        }
+        }
+    };
 #ifndef CLB_NEWTON_UNROLL
 #define CLB_NEWTON_UNROLL 1
 #endif
@@ -689,7 +739,12 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 #pragma unroll kNewtonUnroll
     for (int it = 0; it < max_iters; ++it) {
         // cache_imp!: closures (and temperature) at the iterate, W cells at a time
-        double h[Q], dps[Q], Kc[Q], Td[Q], eK[Q];
+        double h[Q], dps[Q], Kc[Q], Td[Q], eK[Q], rcsv[Q];
+        // The (rho_e, rho_e) solve of the PREVIOUS iteration runs here, in the same basic block as the closures of
+        // this one: the closures only need theta (K, kappa are lagged, so the water equation never reads rho_e), and
+        // the substitution sweeps of W22 are a pure latency chain (4-deep fma chains, three lane crossings) that
+        // fills the closures' issue slots instead of standing alone.  First iteration: b2 = 0, so x2 = 0 exactly.
+        if (MODEL == 1) w22_solve(false);
         // one group of WW cells (WW independent dependency chains); Q = WG full groups of W and a tail
         auto closure_group = [&](auto wtag, const int g) {
             constexpr int W = decltype(wtag)::value;
@@ -704,21 +759,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 Ksat[j] = 0.0;
             }
             if (MODEL == 1) {
-                // update_implicit_aux (energy_hydrology.jl:427-445): T from (theta_l clipped to the pore
-                // space left by ice, rho_e_int, theta_i)
-                double num[W], rcs[W], Tq[W];
+                // volumetric heat capacity at the iterate (theta_l clipped to the pore space left by ice); the
+                // temperature itself follows the closures, below
 #pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    num[j] = U2[g + j] + S.template get<E_ICE>(g + j);
-                    rcs[j] = fma(fmv::min_nn(nue[j], th[j]), C1, S.template get<E_RCBASE>(g + j));
-                }
-                fmv::div<W>(num, rcs, Tq);
-#pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    const double T = T_ref + Tq[j];
-                    Td[g + j] = T;
-                    eK[g + j] = (T - T_ref) * S.template get<E_KC>(g + j);
-                }
+                for (int j = 0; j < W; ++j) rcsv[g + j] = fma(fmv::min_nn(nue[j], th[j]), C1, S.template get<E_RCBASE>(g + j));
 #pragma unroll
                 for (int j = 0; j < W; ++j) {
                     ca[j] = S.template get<E_CA>(g + j);
@@ -752,6 +796,20 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 #pragma unroll
         for (int g = 0; g + WFULL <= Q; g += WFULL) closure_group(std::integral_constant<int, WFULL>{}, g);
         if constexpr (Q % WFULL != 0) closure_group(std::integral_constant<int, Q % WFULL>{}, Q - Q % WFULL);
+        if (MODEL == 1) {
+            // update_implicit_aux (energy_hydrology.jl:427-445): T from (theta_l, rho_e_int, theta_i); after the
+            // closures because it reads the rho_e the lagged solve above has just updated
+            double num[Q], Tq[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) num[q] = U2[q] + S.template get<E_ICE>(q);
+            fmv::div<Q>(num, rcsv, Tq);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double T = T_ref + Tq[q];
+                Td[q] = T;
+                eK[q] = (T - T_ref) * S.template get<E_KC>(q);
+            }
+        }
         CLB_PC(3)  // closures + T
         double h_out, h_in, dps_out, dps_in, K_out = 0.0, K_in = 0.0, T_out = 0.0, T_in = 0.0, eK_out = 0.0, eK_in = 0.0;
         nb_exchange<Gm>(h[0], h[Q - 1], innermost, h_out, h_in);
@@ -880,46 +938,18 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             // then the pre-factored W22
             double y_out, y_in;
             nb_exchange<Gm>(y[0], y[Q - 1], innermost, y_out, y_in);
-            double b2[Q], g2[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const double yn = (q < Q - 1) ? y[q + 1] : y_in;
                 const double yo = (q == 0) ? y_out : y[q - 1];
                 const double acc = fma(aE[q], yo - y[q], aE[q + 1] * (yn - y[q]));
                 const double s = fma(G.dti[half][r0 + q], acc, -x1[q]);
-                b2[q] = (f2[q] - s) * S.template get<E_DEN22>(q);
-            }
-            double gin = 0.0;
-#pragma unroll
-            for (int pass = 0; pass < PARTS; ++pass) {
-                double gp = gin;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    gp = fma(-S.template get<E_OD22>(q), gp, b2[q]);
-                    g2[q] = gp;
-                }
-                if (pass + 1 < PARTS) {
-                    const double rg_ = from_prev_part<Gm::PARTD>(gp);
-                    gin = outermost ? 0.0 : rg_;
-                }
-            }
-            const double xs = fma(-c22_last, xchg<Gm::SEAM>(g2[Q - 1]), g2[Q - 1]) * r22;
-            double xn = xs, x2[Q];
-#pragma unroll
-            for (int pass = 0; pass < PARTS; ++pass) {
-                x2[Q - 1] = (pass == 0) ? xs : (innermost ? xs : fma(-c22_last, xn, g2[Q - 1]));
-#pragma unroll
-                for (int q = Q - 2; q >= 0; --q) x2[q] = fma(-S.template get<E_C22>(q), x2[q + 1], g2[q]);
-                if (pass + 1 < PARTS) xn = from_next_part<Gm::PARTD>(x2[0]);
-            }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                U2[q] -= x2[q];
-                if (last) dx2 = fma(x2[q], x2[q], dx2);
+                b2p[q] = (f2[q] - s) * S.template get<E_DEN22>(q);  // solved at the top of the next iteration / after the loop
             }
         }
         CLB_PC(8)  // W21 x1, W22 solve, update of rho_e
     }
+    if (MODEL == 1) w22_solve(true);  // the last iteration's
 
     // ---- this tile's constants are dead: hand its buffer to the TMA ------------------------------------
     // BEFORE the global stores below: fence.proxy.async carries a MEMBAR.ALL.CTA, which would otherwise wait

@@ -1,6 +1,7 @@
 """Dump the SASS of one kernel: python tools/sass_fn.py <substring of mangled name> > out.sass"""
 import re, subprocess, sys
-so = "climaland.jl_b200/libclimaland_b200.so"
+import os
+so = os.environ.get("SASS_SO", "climaland.jl_b200/libclimaland_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 for b in re.split(r"\n\s*Function : ", out)[1:]:
     if sys.argv[1] in b.split("\n", 1)[0]:

@@ -1,6 +1,7 @@
 """Static SASS instruction mix of one kernel: python tools/sass_mix.py <substring of mangled name> [--loop]"""
 import re, subprocess, sys, collections
-so = "climaland.jl_b200/libclimaland_b200.so"
+import os
+so = os.environ.get("SASS_SO", "climaland.jl_b200/libclimaland_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 blocks = re.split(r"\n\s*Function : ", out)
 for b in blocks[1:]:
