@@ -131,7 +131,7 @@ class Column:
     def _closure(self, theta, nu_eff):
         if self.closure == 0:
             return vg_psi_dpsi_K(theta, nu_eff, self.theta_r, self.a, self.b, self.m, self.S_s, self.K_sat)
-        return bc_psi_dpsi_K(theta, nu_eff, self.theta_r, self.a, self.b, self.S_s, self.K_sat)
+        return bc_psi_dpsi_K(theta, nu_eff, self.theta_r, self.b, self.a, self.S_s, self.K_sat)  # fields: a = c, b = psi_b
 
     def _flux_div(self, q_int, top, bot):
         """-(D q) with the boundary faces of q set to the boundary fluxes (DivergenceF2C with SetValue)."""

@@ -76,11 +76,17 @@ def test_energy_hydrology_one_day(topmodel):
     # water and energy balance of the CUDA path against its own flux integrals
     water = (s.get("y_theta_l") - w["y_theta_l"]) @ dz
     energy = (s.get("y_rho_e_int") - w["y_rho_e_int"]) @ dz
+    # The implicit TOPMODEL source removes R_ss / max(h_grad, eps) per unit depth from the saturated cells
+    # (Runoff.jl:321-359) while the flux integral is charged R_ss (energy_hydrology.jl:363-376 + the source): the
+    # column balance differs from the flux integral by dt R_ss (1 - sum(dz sat) / max(h_grad, eps)) per step; the lagged
+    # is_saturated / R_ss / h_grad are constant over this test's day.
     src_w = src_e = 0.0
-    assert np.max(np.abs(water - (s.get("y_intf_w") - w["y_intf_w"]) - src_w)) <= 1e-11 * np.max(np.abs(w["y_theta_l"] @ dz)) \
-        or topmodel
-    assert np.max(np.abs(energy - (s.get("y_intf_e") - w["y_intf_e"]) - src_e)) <= 1e-10 * np.max(np.abs(w["y_rho_e_int"] @ dz)) \
-        or topmodel
+    if topmodel:
+        frac = (w["is_saturated"] @ dz) / np.maximum(w["h_grad"], np.finfo(np.float64).eps)
+        src_w = nsteps * dt * w["r_ss"] * (1.0 - frac)
+        src_e = nsteps * dt * w["r_ess"] * (1.0 - frac)
+    assert np.max(np.abs(water - (s.get("y_intf_w") - w["y_intf_w"]) - src_w)) <= 1e-11 * np.max(np.abs(w["y_theta_l"] @ dz))
+    assert np.max(np.abs(energy - (s.get("y_intf_e") - w["y_intf_e"]) - src_e)) <= 1e-10 * np.max(np.abs(w["y_rho_e_int"] @ dz))
     s.close()
 
 
@@ -165,8 +171,10 @@ def test_energy_hydrology_one_day_with_the_explicit_stage_on_the_device(math_mod
     print("one-day errors:", {k: rel_err(s.get(k), v) for k, v in (("y_theta_l", U.theta_l), ("y_theta_i", U.theta_i),
                                                                    ("y_rho_e_int", U.rho_e_int), ("y_intf_w", U.intF_w))})
     assert_close(s.get("y_theta_l"), U.theta_l, 1e-9, "theta_l after one day")
+    # theta_i, and rho_e_int element by element (its small entries follow theta_i through the latent heat), carry the
+    # freeze-thaw amplification described above: 1e-8 / 2e-8, per variable; everything else 1e-9
     assert_close(s.get("y_theta_i"), U.theta_i, 1e-8, "theta_i after one day")
-    assert_close(s.get("y_rho_e_int"), U.rho_e_int, 1e-9, "rho_e_int after one day")
+    assert_close(s.get("y_rho_e_int"), U.rho_e_int, 1e-9, "rho_e_int after one day", elem_tol=2e-8)
     assert_close(s.get("y_intf_w"), U.intF_w, 1e-9, "intF_w after one day")
     assert np.max(np.abs(s.get("y_theta_i") - w["y_theta_i"])) > 1e-6
     s.close()
