@@ -264,6 +264,82 @@ def main():
     st = solvers[0].implicit_step(DT, MAX_ITERS, want_stats=True)
     assert st["nan_count"] == 0, "non-finite state after the timed steps"
 
+    # ---- ONE ~1 degree domain sharded over the ranks (north_star: "global domains shard by horizontal element") ----
+    # rank g holds the contiguous block [g n / G, (g + 1) n / G) of the domain's columns (parallel.shard_range; the
+    # reference's partition: Domains.jl:650-652); no collective in the timed region.  Enough independent copies of the
+    # shard that successive steps do not find their inputs in L2.
+    from climaland_b200 import parallel
+    lo, hi = parallel.shard_range(NCOL, world, rank)
+    shard_bytes = (hi - lo) * workloads.algorithmic_bytes(MODEL, NLEV, topmodel=True)
+    n_rep = REPLICAS if world == 1 else max(REPLICAS, int(np.ceil(1.2 * 126e6 / shard_bytes)) + 1)
+    if world == 1:
+        shard_solvers = solvers  # the whole domain on one GPU: the loop above
+        ms_shard = ms_step
+    else:
+        w_full = make_inputs(seed=7)
+        w_shard = parallel.shard_workload(w_full, world, rank)
+        shard_solvers = [cl.SoilColumnSolver.from_workload(w_shard, device=local_rank, stream=stream.cuda_stream,
+                                                           out_of_place=True, kernel_variant=args.variant, layout=args.layout)
+                         for _ in range(n_rep)]
+        with torch.cuda.stream(stream):
+            for k in range(max(warmup, n_rep)):
+                shard_solvers[k % n_rep].implicit_step(DT, MAX_ITERS)
+            barrier()
+            es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            es0.record(stream)
+            for k in range(args.steps):
+                shard_solvers[k % n_rep].implicit_step(DT, MAX_ITERS)
+            es1.record(stream)
+            barrier()
+        t = torch.tensor([es0.elapsed_time(es1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_shard = float(t.item()) / args.steps
+        for s_ in shard_solvers:
+            s_.close()
+
+    # ---- a WHOLE resident soil step (rank 0's domain; SURVEY 8f rows on the device): update_aux! + PhaseChange,
+    # TOPMODEL runoff, the integrator's explicit update (axpys) and the fused implicit stage, no host transfer
+    rng = np.random.default_rng(5 + rank)
+    for r, (s_, w_) in enumerate(zip(solvers, inputs)):
+        for k_, v_ in workloads.make_explicit_params(w_, r).items():
+            s_.set(k_, v_)
+        s_.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+        s_.set("f_max", rng.uniform(0.2, 0.6, NCOL))
+        s_.set("precip", -rng.uniform(0, 4e-7, NCOL))
+        s_.set_runoff_params(f_over=3.28, R_sb=1.484e-7, depth=50.0)
+        s_.set_option("out_of_place", 0)
+
+    def whole_step(s_):
+        s_.set("dye_theta_l", 0.0)
+        s_.set("dye_theta_i", 0.0)
+        s_.update_aux_and_phase_change()
+        s_.update_runoff()
+        s_.copy("top_bc_w", "infiltration")
+        s_.axpy("y_theta_l", DT, "dye_theta_l")
+        s_.axpy("y_theta_i", DT, "dye_theta_i")
+        s_.implicit_step(DT, MAX_ITERS)
+    n_whole = 200
+    with torch.cuda.stream(stream):
+        for k in range(REPLICAS):
+            whole_step(solvers[k])
+        barrier()
+        ew0, ew1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ew0.record(stream)
+        for k in range(n_whole):
+            whole_step(solvers[k % REPLICAS])
+        ew1.record(stream)
+        barrier()
+    t = torch.tensor([ew0.elapsed_time(ew1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_whole = float(t.item()) / n_whole
+    st = solvers[0].implicit_step(DT, MAX_ITERS, want_stats=True)
+    assert st["nan_count"] == 0, "non-finite state after the resident whole-step loop"
+    for s_, w_ in zip(solvers, inputs):  # back to the bench's own state for the host-buffer leg
+        s_.set_option("out_of_place", 1)
+        for k_ in ("y_theta_l", "y_rho_e_int", "y_theta_i", "top_bc_w"):
+            s_.set(k_, w_[k_])
+
     # ---- end to end through the host-buffer call ------------------------------------------
     def pinned(a):
         tns = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
@@ -320,7 +396,18 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config({"sypd_1deg_per_gpu": DT / (ms_step * 1e-3) / 365.0,
+            "config": workload_config({"sypd_1deg_per_gpu_implicit_stage_only": DT / (ms_step * 1e-3) / 365.0,
+                                       "sypd_whole_soil_step_per_gpu": DT / (ms_whole * 1e-3) / 365.0,
+                                       "ms_per_whole_soil_step": ms_whole,
+                                       "whole_soil_step": "update_aux! + PhaseChange, TOPMODEL runoff, explicit update, fused "
+                                                          "implicit stage on resident mirrors (8 launches, no host transfer)",
+                                       "sharded_1deg": {"columns_per_gpu": hi - lo, "ms_per_step": ms_shard,
+                                                        "column_steps_per_s": NCOL / (ms_shard * 1e-3),
+                                                        "sypd_1deg_sharded_implicit_stage_only": DT / (ms_shard * 1e-3) / 365.0,
+                                                        "speedup_vs_this_run_1gpu_whole_domain": ms_step / ms_shard,
+                                                        "field_sets": n_rep, "scaling": "strong",
+                                                        "note": "ONE 61 206-column domain cut into contiguous column blocks, "
+                                                                "one per rank; no collective in the timed region"},
                                        "kernel": KERNEL_NAMES.get(solvers[0].last_variant(), "?") + " (one launch per step)",
                                        "state": "out of place: Y (= temp) -> U, so every step does identical work"}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
