@@ -106,6 +106,8 @@ def lib():
         "clb_implicit_step": [h, d, i32, d, C.POINTER(Stats)],
         "clb_implicit_step_host": [h, d, i32, C.POINTER(i32), C.POINTER(C.c_void_p), i32,
                                    C.POINTER(i32), C.POINTER(C.c_void_p), i32],
+        "clb_soil_step_host": [h, d, i32, C.POINTER(i32), C.POINTER(C.c_void_p), i32,
+                               C.POINTER(i32), C.POINTER(C.c_void_p), i32],
         "clb_column_integral": [h, i32, i32],
         "clb_global_balance": [h, _dp],
         "clb_test_math": [i32, _dp, _dp, _dp, i64],

@@ -1537,6 +1537,43 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters, cons
     return clb_sync(h);
 }
 
+// A whole soil step of EnergyHydrology from and to HOST arrays holding the state at t_n (the reference's step_u! of
+// ARS111 for the soil, Simulations.jl:127-135 with the tendencies of energy_hydrology.jl:285-425, 722-906 and
+// Runoff.jl:234-283): per column chunk, upload the given fields, update_aux! + PhaseChange, TOPMODEL runoff (whose
+// infiltration becomes the top water flux), u + dt T_exp(u), the fused implicit stage, and the write-back of the
+// chunk before -- so PCIe carries only the state and the per-column forcing, never the lagged cache.
+int clb_soil_step_host(clb_handle h, double dt, int32_t max_iters, const int32_t *in_fields, const double *const *in_ptrs,
+                       int32_t n_in, const int32_t *out_fields, double *const *out_ptrs, int32_t n_out)
+{
+    TRY(check_handle(h));
+    if (max_iters < 1 || !(dt > 0.0)) return fail(CLB_ERR_INVALID, "clb_soil_step_host: dt > 0 and max_iters >= 1 expected");
+    if ((n_in > 0 && (!in_fields || !in_ptrs)) || (n_out > 0 && (!out_fields || !out_ptrs)))
+        return fail(CLB_ERR_INVALID, "clb_soil_step_host: null field list");
+    if (h->cfg.model != CLB_ENERGY_HYDROLOGY) return fail(CLB_ERR_INVALID, "clb_soil_step_host: EnergyHydrology only");
+    const int N = h->cfg.n_levels;
+    {
+        DeviceGuard guard(h->cfg.device);
+        const int rc = (h->host_route == 2) ? 0 : step_host_pipelined(h, dt, max_iters, in_fields, in_ptrs, n_in, out_fields,
+                                                                      out_ptrs, n_out, dt);
+        if (rc != 0) return rc < 0 ? rc : CLB_OK;
+    }
+    for (int j = 0; j < n_in; ++j) {
+        if (!is_cell_field(in_fields[j]) && !is_col_field(in_fields[j])) return fail(CLB_ERR_INVALID, "unknown field id %d", in_fields[j]);
+        TRY(clb_set_field(h, in_fields[j], in_ptrs[j], 1, is_cell_field(in_fields[j]) ? N : 1, CLB_HOST));
+    }
+    {
+        DeviceGuard guard(h->cfg.device);
+        TRY(whole_step_ready(h));
+        TRY(launch_explicit_chunk(h, make_view(h), 0, h->cfg.n_columns, dt));
+    }
+    TRY(clb_implicit_step(h, dt, max_iters, -1.0, nullptr));
+    for (int j = 0; j < n_out; ++j) {
+        if (!is_cell_field(out_fields[j]) && !is_col_field(out_fields[j])) return fail(CLB_ERR_INVALID, "unknown field id %d", out_fields[j]);
+        TRY(clb_get_field(h, out_fields[j], out_ptrs[j], 1, is_cell_field(out_fields[j]) ? N : 1, CLB_HOST));
+    }
+    return clb_sync(h);
+}
+
 #ifdef CLB_PHASE_CLOCKS
 // tuning builds only: the lane kernels' phase clocks summed over warps since the last call (then reset)
 __attribute__((visibility("default"))) int clb_debug_phase_clocks(unsigned long long *out16)

@@ -39,6 +39,7 @@ struct ExplicitView {
     double *total_water, *total_energy;                     // per column
     double *dYe_theta_l, *dYe_theta_i;                      // explicit tendency the PhaseChange source adds into
     ExplicitConst k;
+    int assign_source = 0;                                  // 1: the source is stored, not added (clb_soil_step_host)
 };
 
 // Table-driven log / exp of soil_mathv.cuh (11 / 10 FP64 instructions against 26 / 17 of the series-only
@@ -280,8 +281,13 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
         const double theta_star =
             inverse_matric_potential<CLOSURE, MATH>(cell, psi_w0 + psi_T) * (cell.nu - cell.theta_r) + cell.theta_r;
         const double s = dv<MATH>(theta_l - theta_star, tau);
-        X.dYe_theta_l[q] += -s;
-        X.dYe_theta_i[q] += (E.rho_l / E.rho_i) * s;
+        if (X.assign_source) {
+            X.dYe_theta_l[q] = -s;
+            X.dYe_theta_i[q] = (E.rho_l / E.rho_i) * s;
+        } else {
+            X.dYe_theta_l[q] += -s;
+            X.dYe_theta_i[q] += (E.rho_l / E.rho_i) * s;
+        }
     }
 }
 
@@ -313,6 +319,12 @@ struct RunoffView {
     double *is_sat, *h_grad, *infiltration, *R_s, *R_ss, *R_ess;
     const double *p_theta_l, *p_T;              // EnergyHydrology: p.soil.theta_l, p.soil.T
     double f_over, R_sb, depth, Omega, gamma, gammaT_ref;
+    // clb_soil_step_host: after the runoff of the column (which reads the state at t_n) the integrator's explicit update
+    // of the column, u + dt T_exp(u), in place: theta_l, theta_i += dt (PhaseChange source); the infiltration becomes
+    // the top water flux of the implicit stage.  apply_dt = 0: none of it.
+    double apply_dt = 0.0;
+    double *Y_theta_l = nullptr, *Y_theta_i = nullptr, *top_bc_w = nullptr;
+    const double *dYe_theta_l = nullptr, *dYe_theta_i = nullptr;
 };
 
 template <int MATH>
@@ -352,6 +364,14 @@ __global__ void __launch_bounds__(128) k_update_runoff(const DevView P, const Ru
     R.h_grad[c] = h_liq;
     R.R_ss[c] = R_ss;
     if (eh) R.R_ess[c] = e_liq * (R_ss / fmax(h_liq, kEps));
+    if (R.apply_dt != 0.0) {
+        R.top_bc_w[c] = inf;
+        for (int i = 0; i < P.N; ++i) {  // product and sum rounded separately, as `@. u + dt * du` is
+            const int64_t q = P.at(i, c);
+            R.Y_theta_l[q] = __dadd_rn(R.Y_theta_l[q], __dmul_rn(R.apply_dt, R.dYe_theta_l[q]));
+            R.Y_theta_i[q] = __dadd_rn(R.Y_theta_i[q], __dmul_rn(R.apply_dt, R.dYe_theta_i[q]));
+        }
+    }
 }
 
 }  // namespace clb

@@ -240,6 +240,17 @@ class SoilColumnSolver:
         po = (C.c_void_p * n_out)(*[v.ctypes.data for v in outputs.values()])
         check(self.L.clb_implicit_step_host(self.h, float(dtgamma), int(max_iters), fi, pi, n_in, fo, po, n_out))
 
+    def soil_step_host(self, dt, max_iters, inputs, outputs):
+        """A whole EnergyHydrology soil step from / to host arrays holding the state at t_n (clb_soil_step_host):
+        update_aux! + PhaseChange, TOPMODEL runoff, u + dt T_exp(u) and the implicit stage on the device; only the
+        fields in `inputs` / `outputs` cross PCIe (dict name -> contiguous float64 numpy array, ideally pinned)."""
+        n_in, n_out = len(inputs), len(outputs)
+        fi = (C.c_int32 * n_in)(*[field_id(k) for k in inputs])
+        pi = (C.c_void_p * n_in)(*[v.ctypes.data for v in inputs.values()])
+        fo = (C.c_int32 * n_out)(*[field_id(k) for k in outputs])
+        po = (C.c_void_p * n_out)(*[v.ctypes.data for v in outputs.values()])
+        check(self.L.clb_soil_step_host(self.h, float(dt), int(max_iters), fi, pi, n_in, fo, po, n_out))
+
     def column_integral(self, cell_field, col_field_out):
         check(self.L.clb_column_integral(self.h, field_id(cell_field), field_id(col_field_out)))
 

@@ -338,6 +338,25 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters,
                            const int32_t *in_fields, const double *const *in_ptrs, int32_t n_in,
                            const int32_t *out_fields, double *const *out_ptrs, int32_t n_out);
 
+/* A WHOLE soil step of EnergyHydrology from and to host arrays holding the state at t_n -- what
+ * ClimaTimeSteppers' step_u! does for the soil with IMEXAlgorithm(ARS111, NewtonsMethod(max_iters))
+ * (src/simulations/Simulations.jl:127-135), with every tendency on the device:
+ *   update_aux!(p, Y) + source!(dY, ::PhaseChange)   energy_hydrology.jl:722-814, 838-906
+ *   update_infiltration_water_flux!(::TOPMODELRunoff)  Runoff/Runoff.jl:234-283 (its infiltration is the top
+ *                                                      water flux of the stage; other top fluxes: CLB_F_TOP_BC_*)
+ *   U0 = u + dt T_exp(u)                               theta_l, theta_i += dt (PhaseChange source)
+ *   the implicit ARS111 stage                          clb_implicit_step(h, dt, max_iters)
+ * in_fields: whatever changed on the host since the last call -- normally Y (CLB_F_Y_THETA_L, _Y_RHO_E_INT,
+ * _Y_THETA_I, _Y_INTF_W, _Y_INTF_E), CLB_F_PRECIP and the heat / bottom boundary fluxes; the lagged cache (K, kappa,
+ * theta_l, is_saturated, R_ss, R_ess, h_grad) is computed on the device and never crosses PCIe.  out_fields: the new
+ * state (the Y fields, or the U fields with CLB_OPT_OUT_OF_PLACE).  Pinned host arrays are read and written in place
+ * column chunk by column chunk, chunk k's transfers overlapping chunk k-1's kernels; pageable arrays take the
+ * field-by-field route (same results).  Needs clb_set_explicit_params, clb_set_runoff_params, the explicit-stage
+ * parameter fields and CLB_F_F_MAX.  Synchronous. */
+int clb_soil_step_host(clb_handle h, double dt, int32_t max_iters,
+                       const int32_t *in_fields, const double *const *in_ptrs, int32_t n_in,
+                       const int32_t *out_fields, double *const *out_ptrs, int32_t n_out);
+
 /* ---- diagnostics / reductions -------------------------------------------- */
 /* out[c] = sum_i field[i,c] * dz_c[i]  (ClimaCore column_integral_definite!,
  * rre.jl:502-511).  out is a per-column field id. */
