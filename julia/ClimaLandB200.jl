@@ -17,8 +17,9 @@
 #                 return closures that `ccall` one entry point each; `jac_prototype` is a
 #                 B200SoilJacobian whose `ldiv!` is clb_ldiv.  ClimaTimeSteppers' own Newton loop
 #                 drives them (src/simulations/Simulations.jl:177-199).
-#   fused         FusedSoilNewton <: ClimaTimeSteppers.NewtonsMethod-like object whose
-#                 `solve_newton!` ignores the closures and calls clb_implicit_step once per stage.
+#   fused         FusedSoilNewton, a ClimaTimeSteppers.NewtonsMethod-like object whose `solve_newton!` takes dtγ, p, t
+#                 from the integrator's Jacobian closure and calls clb_implicit_step once per stage
+#                 (experimental until run under Julia; `fused = false` is the default).
 module ClimaLandB200
 
 using LinearAlgebra
@@ -425,47 +426,129 @@ end
 
 # ---- fused level: one call per implicit stage ---------------------------------------------------
 """
-    FusedSoilNewton(; max_iters = 3, tol = nothing)
+    FusedSoilNewton(b; max_iters = 3, tol = nothing)
 
-Passed as `IMEXAlgorithm(ARS111(), FusedSoilNewton(...))`.  ClimaTimeSteppers calls
-`solve_newton!(alg, cache, x, f!, j!, pre_iteration!, post_implicit!)` once per implicit stage with
-x = U (initialised to temp); this method ignores the closures and runs the whole loop
-(cache_imp!, max_iters x (Wfact, T_imp!, residual, ldiv!, update)) as ONE kernel.
-`dtγ` reaches us through `set_dtγ!`, called from the Wfact wrapper below.
+Passed as `IMEXAlgorithm(ARS111(), FusedSoilNewton(...))` where `NewtonsMethod` goes.  ClimaTimeSteppers
+(0.10, `src/solvers/imex_ark.jl` / `newtons_method.jl`) touches a Newton object in three places, all provided here:
+
+  * `step_u!` reads `newtons_method.update_j` and `newtons_method_cache.j` (to refresh the Jacobian at a new time step
+    when `update_j` asks for it): the `update_j` field below is the reference's choice
+    `UpdateEvery(NewNewtonIteration)` (Simulations.jl:127-135), for which that refresh is a no-op, and the cache
+    carries `j = B200SoilJacobian(b)`;
+  * `allocate_cache(alg, x_prototype, j_prototype)`;
+  * `solve_newton!(alg, cache, x, f!, j!, pre_iteration!, post_implicit!)`, once per implicit stage with x = U
+    (initialised to temp, `cache_imp!(U)` already called).  This method calls `j!(cache.j, x)` ONCE -- the integrator's
+    closure around `T_imp!.Wfact(j, U, p, dt a_ii, t)`, which is the only place dtγ, p and t are visible -- with
+    `Wfact = record_stage!` (below), which stores them in the Newton object instead of building a matrix; then the
+    whole loop (max_iters x (Wfact, T_imp!, residual, ldiv!, update, cache_imp!)) runs as ONE kernel and
+    `post_implicit!(x)` is called as the reference's loop does after its last iteration.
+
+STATUS: experimental until it has run under Julia (`LandSimulationB200(...; fused = false)` is the default).
 """
-mutable struct FusedSoilNewton{B}
+mutable struct FusedSoilNewton{B, U}
     b::B
     max_iters::Int
     tol::Float64       # < 0: fixed iteration count (the reference default, Simulations.jl:127-135)
+    update_j::U        # read by ClimaTimeSteppers' step_u!
     dtγ::Float64
     t::Any
     p::Any
 end
 FusedSoilNewton(b; max_iters = 3, tol = nothing) =
-    FusedSoilNewton(b, max_iters, isnothing(tol) ? -1.0 : Float64(tol), NaN, nothing, nothing)
-ClimaTimeSteppers.allocate_cache(::FusedSoilNewton, x_prototype, j_prototype) = (;)
+    FusedSoilNewton(b, max_iters, isnothing(tol) ? -1.0 : Float64(tol),
+                    ClimaTimeSteppers.UpdateEvery(ClimaTimeSteppers.NewNewtonIteration), NaN, nothing, nothing)
+ClimaTimeSteppers.allocate_cache(alg::FusedSoilNewton, x_prototype, j_prototype = nothing) = (; j = B200SoilJacobian(alg.b))
 
-function ClimaTimeSteppers.solve_newton!(alg::FusedSoilNewton, cache, x, f!, j!, pre_iteration!, post_implicit!)
+"Wfact of the fused level: remembers the stage's dtγ, p, t for solve_newton! (no matrix is built on the host)"
+record_stage!(alg::FusedSoilNewton) = (W, Y, p, dtγ, t) -> (alg.dtγ = float(dtγ); alg.t = t; alg.p = p; nothing)
+
+function ClimaTimeSteppers.solve_newton!(alg::FusedSoilNewton, cache, x, f!, j! = nothing, pre_iteration! = nothing,
+                                         post_implicit! = nothing)
     b = alg.b
+    isnothing(j!) && error("FusedSoilNewton needs the integrator's Jacobian closure (it carries dtγ, p, t)")
+    j!(cache.j, x)                      # -> record_stage!: alg.dtγ, alg.p, alg.t of THIS stage
+    isfinite(alg.dtγ) && !isnothing(alg.p) || error("FusedSoilNewton: T_imp!.Wfact is not record_stage!(alg)")
     push_state!(b, x); push_lagged!(b, alg.p, alg.t)
     stats = Ref(ClbStats(0, 0, 0.0, 0))
-    check(ccall((:clb_implicit_step, libclb), Cint, (Ptr{Cvoid}, Float64, Int32, Float64, Ref{ClbStats}),
-        b.h.ptr, alg.dtγ, alg.max_iters, alg.tol, alg.tol < 0 ? C_NULL : stats))
+    check(ccall((:clb_implicit_step, libclb), Cint, (Ptr{Cvoid}, Float64, Int32, Float64, Ptr{ClbStats}),
+        b.h.ptr, alg.dtγ, alg.max_iters, alg.tol, alg.tol < 0 ? C_NULL : Base.unsafe_convert(Ptr{ClbStats}, stats)))
     get_field!(x.soil.ϑ_l, b.h, F_Y_THETA_L); get_field!(x.soil.∫F_vol_liq_water_dt, b.h, F_Y_INTF_W)
     if b.energy
         get_field!(x.soil.ρe_int, b.h, F_Y_RHO_E_INT); get_field!(x.soil.∫F_e_dt, b.h, F_Y_INTF_E)
+    end
+    # The reference leaves p at the iterate BEFORE the last update (cache_imp! is the loop's pre_iteration!, not
+    # called after the last iteration); nothing downstream reads that state of p (the next explicit stage recomputes
+    # the cache from Y), so p is left as the integrator's cache_imp!(U) call before the solve wrote it.
+    isnothing(post_implicit!) || post_implicit!(x)
+    return nothing
+end
+
+# ---- resident state (SURVEY 8f rank 4): the integrator's vector operations and the surface blocks on the device ----
+"y .+= a .* x on library mirrors (the integrator's `@. U = u + dt * T_exp`): clb_field_axpy"
+field_axpy!(b::B200Soil, y::ClbField, a::Real, x::ClbField) =
+    check(ccall((:clb_field_axpy, libclb), Cint, (Ptr{Cvoid}, Int32, Float64, Int32), b.h.ptr, Int32(y), Float64(a), Int32(x)))
+"dst .= src on library mirrors: clb_field_copy"
+field_copy!(b::B200Soil, dst::ClbField, src::ClbField) =
+    check(ccall((:clb_field_copy, libclb), Cint, (Ptr{Cvoid}, Int32, Int32), b.h.ptr, Int32(dst), Int32(src)))
+
+"""
+    ldiv_diagonal!(x, w, rhs, b)
+
+`ldiv!` of a DiagonalMatrixRow block of a surface variable -- `canopy.energy.T` with ∂Tres∂T from
+src/standalone/Vegetation/canopy_energy.jl:222-250, solved by the reference inside `field_matrix_solve!`
+(implicit_timestepping.jl:111-152): x = rhs ./ w with the block's entries uploaded from the host model.
+"""
+function ldiv_diagonal!(x::Fields.Field, w::Fields.Field, rhs::Fields.Field, b::B200Soil)
+    set_field!(b.h, F_SFC_W_DI, w); set_field!(b.h, F_SFC_B, rhs)
+    check(ccall((:clb_ldiv_diagonal, libclb), Cint, (Ptr{Cvoid}, Int32, Int32, Int32), b.h.ptr,
+        Int32(F_SFC_W_DI), Int32(F_SFC_B), Int32(F_SFC_X)))
+    get_field!(x, b.h, F_SFC_X)
+    return x
+end
+
+"∫ field dz per column into a surface field (ClimaCore column_integral_definite!, rre.jl:502-511): clb_column_integral"
+function column_integral!(out::Fields.Field, b::B200Soil, cell::ClbField, col::ClbField)
+    check(ccall((:clb_column_integral, libclb), Cint, (Ptr{Cvoid}, Int32, Int32), b.h.ptr, Int32(cell), Int32(col)))
+    get_field!(out, b.h, col)
+end
+
+"global sums (Σ area-weighted column water, ∫F_w, column energy, ∫F_e) over all ranks: clb_global_balance"
+function global_balance(b::B200Soil)
+    out = zeros(Float64, 4)
+    check(ccall((:clb_global_balance, libclb), Cint, (Ptr{Cvoid}, Ptr{Float64}), b.h.ptr, out))
+    return out
+end
+
+"""
+    soil_step_host!(b, dt, max_iters, ins, outs)
+
+A WHOLE EnergyHydrology soil step from / to host `Array{Float64}`s in ClimaCore's `parent` layout (level fastest),
+for callers without CUDA.jl: `ins` / `outs` are vectors of `ClbField => Array` pairs (normally the prognostic state,
+`F_PRECIP` and the heat / bottom boundary fluxes in; the new state out).  clb_soil_step_host; pinned arrays
+(`CUDA.pin`) are read and written in place over PCIe, column chunk by column chunk.
+"""
+function soil_step_host!(b::B200Soil, dt, max_iters, ins::Vector{<:Pair}, outs::Vector{<:Pair})
+    fi = Int32[Int32(first(q)) for q in ins]; fo = Int32[Int32(first(q)) for q in outs]
+    ai = [last(q) for q in ins]; ao = [last(q) for q in outs]
+    GC.@preserve ai ao begin
+        pin_ = Ptr{Float64}[pointer(a) for a in ai]; pout = Ptr{Float64}[pointer(a) for a in ao]
+        check(ccall((:clb_soil_step_host, libclb), Cint,
+            (Ptr{Cvoid}, Float64, Int32, Ptr{Int32}, Ptr{Ptr{Float64}}, Int32, Ptr{Int32}, Ptr{Ptr{Float64}}, Int32),
+            b.h.ptr, Float64(dt), Int32(max_iters), fi, pin_, Int32(length(fi)), fo, pout, Int32(length(fo))))
     end
     return nothing
 end
 
 """
-    LandSimulationB200(t0, tf, Δt, model; fused = true, kwargs...)
+    LandSimulationB200(t0, tf, Δt, model; fused = false, kwargs...)
 
 `ClimaLand.Simulations.LandSimulation` (src/simulations/Simulations.jl:115-245) with the implicit
 hooks of the soil model replaced; everything else (set_ic!, exp_tendency!, drivers, diagnostics,
-callbacks, ClimaTimeSteppers.init) is the reference's own code.
+callbacks, ClimaTimeSteppers.init) is the reference's own code.  `fused = false` (default): ClimaTimeSteppers' own
+Newton loop drives the four hooks, one `ccall` each; `fused = true`: FusedSoilNewton, one kernel per stage
+(experimental until it has run under Julia, see its docstring).
 """
-function LandSimulationB200(t0, tf, Δt, model; fused = true, max_iters = 3, kwargs...)
+function LandSimulationB200(t0, tf, Δt, model; fused = false, max_iters = 3, kwargs...)
     Y, p, _ = ClimaLand.initialize(model)
     b = B200Soil(model, Y, p)
     newton = fused ? FusedSoilNewton(b; max_iters) :
@@ -474,10 +557,13 @@ function LandSimulationB200(t0, tf, Δt, model; fused = true, max_iters = 3, kwa
     ts = ClimaTimeSteppers.IMEXAlgorithm(ClimaTimeSteppers.ARS111(), newton)
     sim = ClimaLand.Simulations.LandSimulation(t0, tf, Δt, model; timestepper = ts, kwargs...)
     # swap the implicit side of the ClimaODEFunction the reference built (Simulations.jl:177-199)
-    imp! = make_compute_imp_tendency(b)
-    jac! = make_compute_jacobian(b)
     cache! = make_update_implicit_cache(b)
-    Wfact = fused ? ((W, Y, p, dtγ, t) -> (newton.dtγ = float(dtγ); newton.t = t; newton.p = p; nothing)) : jac!
+    imp_hook! = make_compute_imp_tendency(b)
+    # Fine-grained level: cache_imp!(U) precedes every T_imp! call inside the Newton loop, so the mirrors hold U and p.
+    # Fused level: the lane kernel keeps psi / T / K in shared memory and never writes the p mirrors, so a T_imp! call
+    # from outside the solve (the integrator's stage tendency) refreshes them first.
+    imp! = fused ? ((dY, Y, p, t) -> (cache!(p, Y, t); imp_hook!(dY, Y, p, t))) : imp_hook!
+    Wfact = fused ? record_stage!(newton) : make_compute_jacobian(b)
     f = sim._integrator.sol.prob.f
     T_imp! = ClimaTimeSteppers.ODEFunction(imp!; jac_prototype = initialize_jacobian(b), Wfact)
     newf = ClimaTimeSteppers.ClimaODEFunction(; T_exp! = f.T_exp!, T_imp!, dss! = f.dss!,
