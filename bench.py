@@ -310,14 +310,7 @@ def main():
         s_.set_option("out_of_place", 0)
 
     def whole_step(s_):
-        s_.set("dye_theta_l", 0.0)
-        s_.set("dye_theta_i", 0.0)
-        s_.update_aux_and_phase_change()
-        s_.update_runoff()
-        s_.copy("top_bc_w", "infiltration")
-        s_.axpy("y_theta_l", DT, "dye_theta_l")
-        s_.axpy("y_theta_i", DT, "dye_theta_i")
-        s_.implicit_step(DT, MAX_ITERS)
+        s_.soil_step(DT, MAX_ITERS)  # clb_soil_step: explicit cells, per-column sweep, fused implicit stage
     n_whole = 200
     with torch.cuda.stream(stream):
         for k in range(REPLICAS):
@@ -446,8 +439,9 @@ def main():
             "config": workload_config({"sypd_1deg_per_gpu_implicit_stage_only": DT / (ms_step * 1e-3) / 365.0,
                                        "sypd_whole_soil_step_per_gpu": DT / (ms_whole * 1e-3) / 365.0,
                                        "ms_per_whole_soil_step": ms_whole,
-                                       "whole_soil_step": "update_aux! + PhaseChange, TOPMODEL runoff, explicit update, fused "
-                                                          "implicit stage on resident mirrors (8 launches, no host transfer)",
+                                       "whole_soil_step": "clb_soil_step: update_aux! + PhaseChange, TOPMODEL runoff + column "
+                                                          "integrals + explicit update, fused implicit stage on resident "
+                                                          "mirrors (3 launches, no host transfer)",
                                        "sharded_1deg": {"columns_per_gpu": hi - lo, "ms_per_step": ms_shard,
                                                         "column_steps_per_s": NCOL / (ms_shard * 1e-3),
                                                         "sypd_1deg_sharded_implicit_stage_only": DT / (ms_shard * 1e-3) / 365.0,

@@ -162,6 +162,7 @@ struct clb_handle_s {
     bool runoff_set = false;
     bool co2_top_state[2] = {false, false};  // SoilCO2Model: AtmosCO2StateBC / AtmosO2StateBC at the top
     int host_route = 0, host_chunks = 0, tile_boxes = 0;  // CLB_OPT_HOST_ROUTE / _HOST_CHUNKS / _TILE_BOXES
+    int explicit_kernel = 0;                              // CLB_OPT_EXPLICIT_KERNEL
     // multi-GPU
     NcclComm comm = nullptr;
     int32_t n_ranks = 1, rank = 0;
@@ -985,6 +986,9 @@ int clb_set_option(clb_handle h, int32_t option, int64_t value)
     case CLB_OPT_TILE_BOXES:
         h->tile_boxes = value != 0;
         return CLB_OK;
+    case CLB_OPT_EXPLICIT_KERNEL:
+        h->explicit_kernel = value != 0;
+        return CLB_OK;
     default:
         return fail(CLB_ERR_INVALID, "clb_set_option: unknown option %d", option);
     }
@@ -1572,6 +1576,20 @@ int clb_soil_step_host(clb_handle h, double dt, int32_t max_iters, const int32_t
         TRY(clb_get_field(h, out_fields[j], out_ptrs[j], 1, is_cell_field(out_fields[j]) ? N : 1, CLB_HOST));
     }
     return clb_sync(h);
+}
+
+// the whole soil step on resident state: see clb_soil_step_host for the sequence
+int clb_soil_step(clb_handle h, double dt, int32_t max_iters)
+{
+    TRY(check_handle(h));
+    if (max_iters < 1 || !(dt > 0.0)) return fail(CLB_ERR_INVALID, "clb_soil_step: dt > 0 and max_iters >= 1 expected");
+    if (h->cfg.model != CLB_ENERGY_HYDROLOGY) return fail(CLB_ERR_INVALID, "clb_soil_step: EnergyHydrology only");
+    {
+        DeviceGuard guard(h->cfg.device);
+        TRY(whole_step_ready(h));
+        TRY(launch_explicit_chunk(h, make_view(h), 0, h->cfg.n_columns, dt));
+    }
+    return clb_implicit_step(h, dt, max_iters, -1.0, nullptr);
 }
 
 #ifdef CLB_PHASE_CLOCKS

@@ -40,6 +40,10 @@ struct ExplicitView {
     double *dYe_theta_l, *dYe_theta_i;                      // explicit tendency the PhaseChange source adds into
     ExplicitConst k;
     int assign_source = 0;                                  // 1: the source is stored, not added (clb_soil_step_host)
+    // k_explicit_cells_uniform, clb_soil_step: != 0: the integrator's explicit update of the cell, u + dt T_exp(u), in
+    // place (Y_theta_l, Y_theta_i += dt * source, product and sum rounded separately as `@. u + dt * du` is) instead
+    // of a stored source -- the per-column sweep, which needs the state at t_n, has then already run
+    double apply_dt = 0.0;
 };
 
 // Table-driven log / exp of soil_mathv.cuh (11 / 10 FP64 instructions against 26 / 17 of the series-only
@@ -291,6 +295,353 @@ __global__ void __launch_bounds__(128) k_explicit_cells(const DevView P, const E
     }
 }
 
+// the per-column sweep of the explicit stage (k_update_runoff below; the SWEEP form of k_explicit_cells_uniform)
+struct RunoffView {
+    const double *f_max, *precip;               // per column
+    double *is_sat, *h_grad, *infiltration, *R_s, *R_ss, *R_ess;
+    const double *p_theta_l, *p_T;              // EnergyHydrology: p.soil.theta_l, p.soil.T
+    double f_over, R_sb, depth, Omega, gamma, gammaT_ref;
+    // clb_soil_step_host: after the runoff of the column (which reads the state at t_n) the integrator's explicit update
+    // of the column, u + dt T_exp(u), in place: theta_l, theta_i += dt (PhaseChange source); the infiltration becomes
+    // the top water flux of the implicit stage.  apply_dt = 0: none of it.
+    double apply_dt = 0.0;
+    double *Y_theta_l = nullptr, *Y_theta_i = nullptr, *top_bc_w = nullptr;
+    const double *dYe_theta_l = nullptr, *dYe_theta_i = nullptr;
+    // the column integrals of update_aux! (k_explicit_totals) taken in the same sweep over the levels; nullptr: not here
+    double *total_water = nullptr, *total_energy = nullptr;
+};
+
+// ---- FAST mode, warp-uniform control flow ------------------------------------------------------------------
+// The kernel above follows the reference's case distinctions cell by cell: frozen / unfrozen (Kersten number, kappa_sat,
+// the shared closure, the second depressed freezing point), saturated / unsaturated, T above / below T_f.  With the
+// cases mixed inside a warp its lanes idle on each other's paths (ncu, profiles/r1: 19 of 32 lanes active, 45.5 M
+// warp instructions per ~1 degree domain -- more than the implicit stage).  Here every decision that changes the
+// INSTRUCTION STREAM is taken per warp (__any_sync votes), and per lane only as a select between finished values:
+//   * no lane of the warp holds ice: the no-ice shortcuts for the whole warp (what a summer warp of a real domain,
+//     whose ice is spatially coherent, takes); otherwise the general formulas for every lane -- they reduce to the
+//     shortcut's VALUE where theta_i = 0 (same saturation, same theta_tot, 10^0 = 1) -- so a mixed warp costs the
+//     general path once instead of both paths one after the other;
+//   * saturated cells run the unsaturated formulas on finite garbage and select, as the lane kernels' closure does;
+//   * the logarithm of T / T_f (series log: it needs relative accuracy near 1) only where some lane is below T_f.
+// Every value is the one the kernel above produces (same formulas, same functions, same rounding sequence) except
+// kappa_sat of an ice-free cell in a warp with ice, exp(log k_u) instead of k_u (<= 2^-52 relative).
+constexpr int kExplicitStage = 17;  // per-cell inputs of k_explicit_cells_uniform staged in shared memory
+
+namespace xbf {
+
+// tlog / texp with the tables in SHARED memory (2.5 KB per block, filled by its 128 threads): a look-up through L1
+// from global memory stalls the warp on the long scoreboard (ncu: 3.8 stall cycles per issued instruction, the
+// largest item), from shared memory it is a ~25-cycle access
+struct Tab {
+    fmv::MathTab MT;
+    __device__ __forceinline__ double log(double x) const
+    {
+        const double xv[1] = {x};
+        double r[1];
+        fmv::log_tab<1>(MT, xv, r);
+        return r[0];
+    }
+    __device__ __forceinline__ double exp(double x) const
+    {
+        const double xv[1] = {x};
+        double r[1];
+        fmv::exp_tab<1>(MT, xv, r);
+        return r[0];
+    }
+};
+
+// van Genuchten / Brooks-Corey matric potential at saturation S in (0, 1] (soil_hydrology_parameterizations.jl:59-63,
+// 182-186), with the reciprocals of m, n (or of c) passed in
+template <int CLOSURE>
+__device__ __forceinline__ double matric_potential(const Tab &M, const HydroCell &p, double inv_m, double inv_n, double S)
+{
+    if (CLOSURE == kVanGenuchten) {
+        const double u = M.exp(-inv_m * M.log(S)) - 1.0;            // S^(-1/m) - 1 >= 0
+        const double v = M.exp(inv_n * M.log(u + 1e-300));          // u = 0: selected below
+        return -(((u == 0.0) ? 0.0 : v) * fm::rcp(p.a));         // the closure's own 1/alpha (one rcp per cell after CSE)
+    }
+    return p.b * M.exp(-inv_m * M.log(S));                           // inv_m carries 1/c
+}
+
+template <int CLOSURE>
+__device__ __forceinline__ double inverse_matric_potential(const Tab &M, const HydroCell &p, double psi)
+{
+    double r;
+    if (CLOSURE == kVanGenuchten) {
+        const double x = p.a * fabs(psi);
+        const double inner = M.exp(p.b * M.log(x + 1e-300));         // (alpha |psi|)^n; x = 0: 0
+        r = M.exp(-p.m * M.log(1.0 + ((x == 0.0) ? 0.0 : inner)));
+    } else {
+        const double x = fm::div(psi, p.b);                        // psi / psi_b >= 0
+        r = (x == 0.0) ? INFINITY : M.exp(-p.a * M.log(x + 1e-300));
+    }
+    return (psi > 0.0) ? NAN : r;
+}
+
+template <int CLOSURE>
+__device__ __forceinline__ double Tf_depressed(const Tab &M, const HydroCell &p, double inv_m, double inv_n, double theta_l, double theta_i,
+                                               double ratio, const ExplicitConst &k, double LH_f0, double &psi_w0)
+{
+    const double theta_tot = fmin(ratio * theta_i + theta_l, p.nu);
+    const double lo = p.theta_r + kSqrtEps;
+    const double S = fm::div(fmax(theta_tot, lo) - p.theta_r, fmax(p.nu, lo) - p.theta_r);
+    psi_w0 = matric_potential<CLOSURE>(M, p, inv_m, inv_n, S);
+    return fmax(k.T_freeze * M.exp((k.grav * psi_w0) * fm::rcp(LH_f0)), 1.0);  // |g psi / LH| ~ 1e-3: an ulp of it is nothing
+}
+
+}  // namespace xbf
+
+// SWEEP (column-fastest mirrors, N <= 32; a block is COLS columns x N levels, rounded up to whole warps): the per-column sweep of
+// the explicit stage -- TOPMODEL runoff (k_update_runoff) and the column integrals of update_aux! -- in the SAME
+// kernel: every cell leaves its five dz-weighted terms in shared memory, and the warp of the top level, which holds the
+// top cell's T and theta_l in registers, adds them up level by level (the order of the sweep kernel: same bits) and
+// finishes the column.  Each cell then applies its own explicit update in place (X.apply_dt), so a whole explicit stage
+// is ONE launch that reads every field once.
+template <int CLOSURE, bool AUX, bool PHASE, bool SWEEP = false, int COLS = 32>
+#ifndef CLB_XBF_MINB
+#define CLB_XBF_MINB 8  // 64 registers (a 52-byte spill) against 72 at 7 blocks per SM
+#endif
+__global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : CLB_XBF_MINB)  // 64 registers either way
+    k_explicit_cells_uniform(const DevView P, const ExplicitView X, const RunoffView R)
+{
+    constexpr unsigned kFull = 0xffffffffu;
+    static_assert(mtab::kLogN <= 128 && mtab::kExpN <= 128, "one table entry per thread of the block");
+    static_assert(!SWEEP || (AUX && PHASE), "the sweep belongs to the whole explicit stage");
+    __shared__ __align__(16) unsigned char tab_sm[fmv::kMathTabBytes];
+    // dynamic shared memory: [kExplicitStage fields][blockDim] staging of the cell's inputs, then (SWEEP) the column
+    // terms [5][N levels][COLS columns]
+    extern __shared__ double dyn_sm[];
+    double *const stage = dyn_sm + threadIdx.x;
+    const int nt = blockDim.x;
+    double *const sweep_sm = dyn_sm + (size_t)kExplicitStage * nt;
+    int64_t c;
+    int i;
+    bool pad = false;  // SWEEP: threads that round the block up to whole warps
+    if (SWEEP) {
+        c = (int64_t)blockIdx.x * COLS + (threadIdx.x % COLS);
+        i = threadIdx.x / COLS;
+        pad = i >= P.N;
+        i = pad ? P.N - 1 : i;
+    } else if (P.sl == 1) {
+        int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t last = P.ncol * P.N - 1;
+        k = (k > last) ? -1 : k;
+        c = (k < 0) ? P.ncol : k / P.N;
+        i = (k < 0) ? 0 : (int)(k - c * P.N);
+    } else {
+        c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        i = blockIdx.y;
+    }
+    // every lane stays alive for the warp votes: lanes past the last column work on a copy of it and store nothing
+    const bool live = c < P.ncol && !pad;
+    if (c >= P.ncol) c = P.ncol - 1;
+    const int64_t q = P.at(i, c);
+    const EarthConst &E = P.earth;
+    // Every per-cell input goes HBM -> shared memory by cp.async, all requests in flight before anything waits: read
+    // one by one where they are used (the registers do not hold 17 doubles ahead of time), the loads were ~5 dependent
+    // HBM round trips per cell (ncu: long_scoreboard 3.2 stall cycles per issued instruction, the largest item).  A
+    // thread only reads what it staged itself: no block barrier.
+    {
+        auto cpa = [&](int slot, const double *src) {
+            if (src) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + (size_t)slot * nt);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + q) : "memory");
+            }
+        };
+        // (Programmatic dependent launch of this kernel and an early release of the implicit stage behind it were
+        // measured: 130.8 against 127.3 us per whole step -- the stage's blocks, which need a whole SM's shared memory,
+        // get in the way of this grid's last wave -- and not kept.)
+        cpa(0, P.nu); cpa(1, P.theta_r); cpa(2, P.K_sat); cpa(3, P.S_s); cpa(4, P.hcm_a); cpa(5, P.hcm_b); cpa(6, P.hcm_m);
+        cpa(7, P.Y_theta_l); cpa(8, P.Y_theta_i); cpa(9, P.rho_c_ds); cpa(10, P.Y_rho_e);
+        if (AUX) {
+            cpa(11, X.nu_ss_om); cpa(12, X.nu_ss_quartz); cpa(13, X.nu_ss_gravel); cpa(14, X.kappa_sat_unfrozen);
+            cpa(15, X.kappa_sat_frozen); cpa(16, X.kappa_dry);
+        } else {
+            cpa(11, X.p_theta_l); cpa(12, X.p_kappa); cpa(13, X.p_T);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int t = threadIdx.x; t < mtab::kLogN; t += blockDim.x) fmv::math_tab_fill(tab_sm, t);
+    const xbf::Tab M{fmv::MathTab{reinterpret_cast<const double2 *>(tab_sm),
+                                  reinterpret_cast<const double *>(tab_sm + mtab::kLogN * 16)}};
+    __syncthreads();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    auto in = [&](int slot) { return stage[(size_t)slot * nt]; };
+    HydroCell cell;
+    cell.nu = in(0); cell.theta_r = in(1); cell.K_sat = in(2); cell.S_s = in(3); cell.a = in(4); cell.b = in(5);
+    cell.m = P.hcm_m ? in(6) : 0.0;
+    const double th = in(7), thi = in(8);
+    const double rcds = in(9);
+    const bool any_ice = __any_sync(kFull, thi != 0.0);
+    const double inv_m = (CLOSURE == kVanGenuchten) ? fm::rcp(cell.m) : fm::div(1.0, cell.a);
+    const double inv_n = (CLOSURE == kVanGenuchten) ? fm::rcp(cell.b) : 0.0;
+    const double lo = cell.theta_r + kSqrtEps;
+    double theta_l, kappa, T, Tf_aux = 0.0, psi_w0_aux = 0.0, rho_e = 0.0;
+    if (AUX) {
+        const double th_s = fmax(th, lo), num = th_s - cell.theta_r;
+        const double nu_psi = fmax(cell.nu - thi, lo), nu_K = fmax(cell.nu, lo);
+        theta_l = (th_s < nu_psi) ? th_s : nu_psi;
+        const double S_r = fm::div(theta_l + thi, cell.nu);
+        // ---- Kersten number (soil_heat_parameterizations.jl:301-323): both forms share log S_r
+        const double om = in(11);
+        const bool unfrozen = thi < kEps;
+        const double lSr = M.log(S_r);
+        double K_e = 0.0;
+        if (__any_sync(kFull, unfrozen)) {
+            const double e1 = 1.0 + M.exp(-X.k.beta * S_r), h = (1.0 - S_r) / 2.0;
+            const double base = fm::rcp(e1 * e1 * e1) - h * h * h;
+            const double v = M.exp(((1.0 + om - X.k.alpha * in(12) - in(13)) / 2.0) * lSr +
+                                  (1.0 - om) * M.log(fmax(base, 1e-300)));
+            K_e = (base > 0.0) ? v : ((base == 0.0) ? 0.0 : NAN);
+        }
+        if (__any_sync(kFull, !unfrozen)) {
+            const double v = M.exp((1.0 + om) * lSr);
+            K_e = unfrozen ? K_e : v;
+        }
+        // ---- kappa_sat (:243-254)
+        const double ku = in(14), kf = in(15);
+        double ks = ku;
+        if (any_ice) {
+            const double theta_w = theta_l + thi;
+            const double rw = fm::rcp(theta_w);
+            const double v = M.exp((theta_l * rw) * M.log(ku) + (thi * rw) * M.log(kf));
+            ks = (thi == 0.0) ? ku : v;
+            ks = (theta_w < kEps) ? (ku + kf) / 2.0 : ks;
+        }
+        kappa = K_e * ks + (1.0 - K_e) * in(16);
+        rho_e = in(10);
+        T = E.T_ref + fm::div(rho_e + thi * E.rho_i * E.LH_f0, volumetric_heat_capacity(theta_l, thi, rcds, E));
+        // ---- K at the saturation against nu, psi at the saturation against nu - theta_i (closure_K_psi_fast)
+        double Kh, psi;
+        {
+            const double range_K = nu_K - cell.theta_r, range_p = nu_psi - cell.theta_r;
+            const double S_K = fm::div(num, range_K);
+            const double L_K = M.log(S_K);
+            double L_p = L_K, E_K = 0.0, l1_K = 0.0;
+            if (CLOSURE == kVanGenuchten) {
+                E_K = L_K * inv_m;
+                const double omA = 1.0 - M.exp(E_K);
+                l1_K = M.log(fmax(omA, 0.0) + 1e-300);
+                const double t = 1.0 - M.exp(cell.m * l1_K);
+                Kh = (fm::sqrt(S_K) * (t * t)) * cell.K_sat;
+            } else {
+                Kh = M.exp((2.0 * inv_m + 3.0) * L_K) * cell.K_sat;
+            }
+            Kh = (num < range_K) ? Kh : cell.K_sat;
+            double E_p = E_K, l1_p = l1_K;
+            if (any_ice) {
+                L_p = M.log(fm::div(num, range_p));
+                if (CLOSURE == kVanGenuchten) {
+                    E_p = L_p * inv_m;
+                    l1_p = M.log(fmax(1.0 - M.exp(E_p), 0.0) + 1e-300);
+                }
+                // a lane without ice: range_p == range_K, the same operands, the same values
+            }
+            const double sat = (th_s - nu_psi) * fm::rcp(cell.S_s);
+            if (CLOSURE == kVanGenuchten) {
+                const double un = -(M.exp((l1_p - E_p) * inv_n) * fm::rcp(cell.a));
+                psi = (num < range_p) ? un : ((num == range_p) ? -0.0 : sat);
+            } else {
+                const double un = cell.b * M.exp(-L_p * inv_m);
+                psi = (num < range_p) ? un : ((num == range_p) ? cell.b : sat + cell.b);
+            }
+        }
+        const double f_i = fm::div(thi, theta_l + thi - cell.theta_r);
+        const double imp = any_ice ? M.exp((-X.k.Omega * f_i) * 2.302585092994045684) : 1.0;  // 10^0 = exp(0) = 1 exactly
+        const double visc = M.exp(X.k.gamma * (T - X.k.gammaT_ref));
+        Tf_aux = xbf::Tf_depressed<CLOSURE>(M, cell, inv_m, inv_n, theta_l, thi, E.rho_l / E.rho_i, X.k, E.LH_f0, psi_w0_aux);
+        if (live) {
+            X.p_theta_l[q] = theta_l;
+            X.p_kappa[q] = kappa;
+            X.p_T[q] = T;
+            X.p_K[q] = imp * visc * Kh;
+            X.p_psi[q] = psi;
+            X.p_Tf[q] = Tf_aux;
+        }
+    } else {
+        theta_l = in(11);
+        kappa = in(12);
+        T = in(13);
+    }
+    if (PHASE) {
+        const double dz = P.dz_c[i];
+        const double tau = fm::div(3.0 * volumetric_heat_capacity(theta_l, thi, rcds, E) * (dz * dz), kappa);
+        double psi_w0 = psi_w0_aux, Tf = Tf_aux;
+        if (!AUX || any_ice)  // without ice the density ratio does not enter theta_tot: the value of update_aux!
+            Tf = xbf::Tf_depressed<CLOSURE>(M, cell, inv_m, inv_n, theta_l, thi, E.rho_i / E.rho_l, X.k, E.LH_f0, psi_w0);
+        const bool below = (Tf - T) > kEps;  // heaviside(Tf - T)
+        double psi_T = 0.0;
+        if (__any_sync(kFull, below)) psi_T = below ? E.LH_f0 / X.k.grav * fm::log(fm::div(T, Tf)) : 0.0;
+        const double theta_star =
+            xbf::inverse_matric_potential<CLOSURE>(M, cell, psi_w0 + psi_T) * (cell.nu - cell.theta_r) + cell.theta_r;
+        const double s = fm::div(theta_l - theta_star, tau);
+        if (live) {
+            if (X.apply_dt != 0.0) {
+                P.Y_theta_l[q] = __dadd_rn(th, __dmul_rn(X.apply_dt, -s));
+                P.Y_theta_i[q] = __dadd_rn(thi, __dmul_rn(X.apply_dt, (E.rho_l / E.rho_i) * s));
+            } else if (X.assign_source) {
+                X.dYe_theta_l[q] = -s;
+                X.dYe_theta_i[q] = (E.rho_l / E.rho_i) * s;
+            } else {
+                X.dYe_theta_l[q] += -s;
+                X.dYe_theta_i[q] += (E.rho_l / E.rho_i) * s;
+            }
+        }
+    }
+    if (SWEEP) {
+        // update_infiltration_water_flux!(p, ::TOPMODELRunoff, ...) (Runoff/Runoff.jl:234-283) and the column integrals
+        // of update_aux! (energy_hydrology.jl:1282-1327); expressions and summation order of k_update_runoff
+        const int N = P.N;
+        const double dz = P.dz_c[i], range = cell.nu - cell.theta_r;
+        const double a_all = th + thi - cell.theta_r, a_liq = th - cell.theta_r;
+        const bool sat_all = (a_all - range) > kEps, sat_liq = (a_liq - range) > kEps;  // heaviside
+        double s_all = 0.0, s_liq = 0.0;
+        if (__any_sync(kFull, sat_all)) {  // the division only where some column of the warp is saturated at this level
+            s_all = sat_all ? a_all / range : 0.0;
+            s_liq = sat_liq ? a_liq / range : 0.0;
+        }
+        const int TS = N * COLS;
+        if (!pad) {
+            double *const term = sweep_sm + (size_t)i * COLS + (threadIdx.x % COLS);
+            term[0] = s_all * dz;
+            term[TS] = s_liq * dz;
+            term[2 * TS] = s_liq * volumetric_internal_energy_liq(T, E) * dz;
+            term[3 * TS] = (th + thi * E.rho_i / E.rho_l) * dz;
+            term[4 * TS] = rho_e * dz;
+        }
+        if (live) R.is_sat[q] = s_liq;
+        __syncthreads();
+        if (i == N - 1 && !pad) {  // the top level's threads: one per column
+            double h_all = 0.0, h_liq = 0.0, e_liq = 0.0, tw = 0.0, te = 0.0;
+            const double *col = sweep_sm + (threadIdx.x % COLS);
+            for (int l = 0; l < N; ++l) {
+                h_all += col[l * COLS];
+                h_liq += col[TS + l * COLS];
+                e_liq += col[2 * TS + l * COLS];
+                tw += col[3 * TS + l * COLS];
+                te += col[4 * TS + l * COLS];
+            }
+            const double f_i = thi / (theta_l + thi - cell.theta_r);
+            const double imp = texp((-R.Omega * f_i) * 2.302585092994045684);
+            const double ic = -cell.K_sat * imp * texp(R.gamma * (T - R.gammaT_ref));
+            const double precip = R.precip[c];
+            const double f_sat = fmin(R.f_max[c] * texp(-R.f_over / 2.0 * (R.depth - h_all)), 1.0);
+            const double inf = (1.0 - f_sat) * fmax(ic, precip);
+            const double R_ss = R.R_sb * texp(-R.f_over * (R.depth - h_liq));
+            if (live) {
+                R.infiltration[c] = inf;
+                R.R_s[c] = fabs(precip - inf);
+                R.h_grad[c] = h_liq;
+                R.R_ss[c] = R_ss;
+                R.R_ess[c] = e_liq * (R_ss / fmax(h_liq, kEps));
+                R.total_water[c] = tw;
+                R.total_energy[c] = te;
+                if (R.top_bc_w) R.top_bc_w[c] = inf;
+            }
+        }
+    }
+}
+
 // total_liq_water_vol_per_area! and total_energy_per_area! (ClimaCore column_integral_definite!)
 __global__ void __launch_bounds__(128) k_explicit_totals(const DevView P, const ExplicitView X)
 {
@@ -314,18 +665,6 @@ __global__ void __launch_bounds__(128) k_explicit_totals(const DevView P, const 
 // is_saturated :432-434, update_subsurface_energy_runoff! :266-279.  One thread per column; the three column
 // integrals (ice-inclusive and liquid-only saturated thickness, liquid energy of the saturated layers) share one
 // sweep over the levels.
-struct RunoffView {
-    const double *f_max, *precip;               // per column
-    double *is_sat, *h_grad, *infiltration, *R_s, *R_ss, *R_ess;
-    const double *p_theta_l, *p_T;              // EnergyHydrology: p.soil.theta_l, p.soil.T
-    double f_over, R_sb, depth, Omega, gamma, gammaT_ref;
-    // clb_soil_step_host: after the runoff of the column (which reads the state at t_n) the integrator's explicit update
-    // of the column, u + dt T_exp(u), in place: theta_l, theta_i += dt (PhaseChange source); the infiltration becomes
-    // the top water flux of the implicit stage.  apply_dt = 0: none of it.
-    double apply_dt = 0.0;
-    double *Y_theta_l = nullptr, *Y_theta_i = nullptr, *top_bc_w = nullptr;
-    const double *dYe_theta_l = nullptr, *dYe_theta_i = nullptr;
-};
 
 template <int MATH>
 __global__ void __launch_bounds__(128) k_update_runoff(const DevView P, const RunoffView R)
@@ -334,26 +673,64 @@ __global__ void __launch_bounds__(128) k_update_runoff(const DevView P, const Ru
     if (c >= P.ncol) return;
     const bool eh = P.model == 1;
     const EarthConst &E = P.earth;
-    double h_all = 0.0, h_liq = 0.0, e_liq = 0.0;
-    for (int i = 0; i < P.N; ++i) {
-        const int64_t q = P.at(i, c);
-        const double th = P.Y_theta_l[q], thi = eh ? P.Y_theta_i[q] : 0.0;
-        const double nu = __ldg(P.nu + q), theta_r = __ldg(P.theta_r + q);
-        const double range = nu - theta_r, dz = P.dz_c[i];
-        const double s_all = heaviside((th + thi - theta_r) - range) * (th + thi - theta_r) / range;
-        const double s_liq = heaviside((th - theta_r) - range) * (th - theta_r) / range;
-        R.is_sat[q] = s_liq;
-        h_all += s_all * dz;
-        h_liq += s_liq * dz;
-        if (eh) e_liq += s_liq * volumetric_internal_energy_liq(R.p_T[q], E) * dz;
+    double h_all = 0.0, h_liq = 0.0, e_liq = 0.0, tw = 0.0, te = 0.0;
+    const bool totals = R.total_water != nullptr;
+    // R.p_T == nullptr (the sweep runs BEFORE update_aux!, clb_soil_step): p.soil.T and p.soil.theta_l of the cell are
+    // evaluated here with update_aux!'s own expressions (energy_hydrology.jl:745-775), i.e. to the same bits
+    const bool own_T = eh && R.p_T == nullptr;
+    // CH levels at a time, every load of the chunk issued before the first use: a thread owns a whole column, so the
+    // memory-level parallelism of this HBM-bound sweep is what the chunk holds in flight
+    constexpr int CH = 5;
+    double T_top = 0.0, thl_top = 0.0;
+    for (int i0 = 0; i0 < P.N; i0 += CH) {
+        double th[CH], thi[CH], nu[CH], theta_r[CH], Tq[CH], rho_e[CH], rcds[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int i = min(i0 + j, P.N - 1);
+            const int64_t q = P.at(i, c);
+            th[j] = P.Y_theta_l[q];
+            thi[j] = eh ? P.Y_theta_i[q] : 0.0;
+            nu[j] = __ldg(P.nu + q);
+            theta_r[j] = __ldg(P.theta_r + q);
+            Tq[j] = (eh && !own_T) ? R.p_T[q] : 0.0;
+            rho_e[j] = (eh && (own_T || totals)) ? P.Y_rho_e[q] : 0.0;
+            rcds[j] = own_T ? __ldg(P.rho_c_ds + q) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int i = i0 + j;
+            if (i < P.N) {
+                const int64_t q = P.at(i, c);
+                const double range = nu[j] - theta_r[j], dz = P.dz_c[i];
+                if (totals) {  // total_liq_water_vol_per_area!, total_energy_per_area! (energy_hydrology.jl:1282-1327)
+                    tw += (th[j] + thi[j] * E.rho_i / E.rho_l) * dz;
+                    te += rho_e[j] * dz;
+                }
+                double T = Tq[j];
+                if (own_T) {
+                    const double lo = theta_r[j] + kSqrtEps;
+                    const double th_s = fmax(th[j], lo), nu_s = fmax(nu[j] - thi[j], lo);
+                    const double theta_l = (th_s < nu_s) ? th_s : nu_s;
+                    T = E.T_ref + dv<MATH>(rho_e[j] + thi[j] * E.rho_i * E.LH_f0, volumetric_heat_capacity(theta_l, thi[j], rcds[j], E));
+                    if (i == P.N - 1) { T_top = T; thl_top = theta_l; }
+                }
+                const double s_all = heaviside((th[j] + thi[j] - theta_r[j]) - range) * (th[j] + thi[j] - theta_r[j]) / range;
+                const double s_liq = heaviside((th[j] - theta_r[j]) - range) * (th[j] - theta_r[j]) / range;
+                R.is_sat[q] = s_liq;
+                h_all += s_all * dz;
+                h_liq += s_liq * dz;
+                if (eh) e_liq += s_liq * volumetric_internal_energy_liq(T, E) * dz;
+            }
+        }
     }
     const int64_t qt = P.at(P.N - 1, c);
     double ic = -1 * __ldg(P.K_sat + qt);
     if (eh) {
         const double thi = P.Y_theta_i[qt];
-        const double f_i = thi / (R.p_theta_l[qt] + thi - __ldg(P.theta_r + qt));
+        const double thl = own_T ? thl_top : R.p_theta_l[qt], Tt = own_T ? T_top : R.p_T[qt];
+        const double f_i = thi / (thl + thi - __ldg(P.theta_r + qt));
         const double imp = (MATH == kMathLibm) ? pow(10.0, -R.Omega * f_i) : texp((-R.Omega * f_i) * 2.302585092994045684);
-        ic = -__ldg(P.K_sat + qt) * imp * ex<MATH>(R.gamma * (R.p_T[qt] - R.gammaT_ref));
+        ic = -__ldg(P.K_sat + qt) * imp * ex<MATH>(R.gamma * (Tt - R.gammaT_ref));
     }
     const double precip = R.precip[c];
     const double f_sat = fmin(R.f_max[c] * ex<MATH>(-R.f_over / 2.0 * (R.depth - h_all)), 1.0);
@@ -364,12 +741,27 @@ __global__ void __launch_bounds__(128) k_update_runoff(const DevView P, const Ru
     R.h_grad[c] = h_liq;
     R.R_ss[c] = R_ss;
     if (eh) R.R_ess[c] = e_liq * (R_ss / fmax(h_liq, kEps));
+    if (totals) {
+        R.total_water[c] = tw;
+        R.total_energy[c] = te;
+    }
+    if (R.top_bc_w) R.top_bc_w[c] = inf;
     if (R.apply_dt != 0.0) {
-        R.top_bc_w[c] = inf;
-        for (int i = 0; i < P.N; ++i) {  // product and sum rounded separately, as `@. u + dt * du` is
-            const int64_t q = P.at(i, c);
-            R.Y_theta_l[q] = __dadd_rn(R.Y_theta_l[q], __dmul_rn(R.apply_dt, R.dYe_theta_l[q]));
-            R.Y_theta_i[q] = __dadd_rn(R.Y_theta_i[q], __dmul_rn(R.apply_dt, R.dYe_theta_i[q]));
+        for (int i0 = 0; i0 < P.N; i0 += CH) {  // product and sum rounded separately, as `@. u + dt * du` is
+            double yl[CH], yi[CH], dl[CH], di[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const int64_t q = P.at(min(i0 + j, P.N - 1), c);
+                yl[j] = R.Y_theta_l[q]; yi[j] = R.Y_theta_i[q]; dl[j] = R.dYe_theta_l[q]; di[j] = R.dYe_theta_i[q];
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                if (i0 + j < P.N) {
+                    const int64_t q = P.at(i0 + j, c);
+                    R.Y_theta_l[q] = __dadd_rn(yl[j], __dmul_rn(R.apply_dt, dl[j]));
+                    R.Y_theta_i[q] = __dadd_rn(yi[j], __dmul_rn(R.apply_dt, di[j]));
+                }
+            }
         }
     }
 }

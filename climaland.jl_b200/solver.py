@@ -251,6 +251,11 @@ class SoilColumnSolver:
         po = (C.c_void_p * n_out)(*[v.ctypes.data for v in outputs.values()])
         check(self.L.clb_soil_step_host(self.h, float(dt), int(max_iters), fi, pi, n_in, fo, po, n_out))
 
+    def soil_step(self, dt, max_iters=3):
+        """A whole EnergyHydrology soil step on resident state (clb_soil_step): explicit cells, the per-column sweep
+        (runoff, column integrals, explicit update), the fused implicit stage -- three launches, no host transfer."""
+        check(self.L.clb_soil_step(self.h, float(dt), int(max_iters)))
+
     def column_integral(self, cell_field, col_field_out):
         check(self.L.clb_column_integral(self.h, field_id(cell_field), field_id(col_field_out)))
 

@@ -100,8 +100,10 @@ enum { CLB_OPT_OUT_OF_PLACE = 1,        /* fused stage reads Y (= temp) and writ
                                            arrays, staged copies for pageable ones), 1 = staged copies always,
                                            2 = field by field (clb_set_field / clb_implicit_step / clb_get_field) */
        CLB_OPT_HOST_CHUNKS = 5,         /* column chunks of the pipelined host route (0 = default, 4) */
-       CLB_OPT_TILE_BOXES = 6 };        /* lane kernels: 0 = two TMA boxes of the arena per tile where the mirrors are
+       CLB_OPT_TILE_BOXES = 6,          /* lane kernels: 0 = two TMA boxes of the arena per tile where the mirrors are
                                            equally spaced, 1 = one box per field always (same results, bit for bit) */
+       CLB_OPT_EXPLICIT_KERNEL = 7 };   /* explicit stage, CLB_MATH_FAST: 0 = warp-uniform control flow (default),
+                                           1 = the reference's case distinctions cell by cell (comparison) */
 
 /* Field ids.  "cell" fields are N x ncol, "col" fields are ncol. */
 typedef enum {
@@ -356,6 +358,14 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters,
 int clb_soil_step_host(clb_handle h, double dt, int32_t max_iters,
                        const int32_t *in_fields, const double *const *in_ptrs, int32_t n_in,
                        const int32_t *out_fields, double *const *out_ptrs, int32_t n_out);
+
+/* The same whole soil step on RESIDENT state: the mirrors hold the state at t_n (CLB_F_Y_*), the
+ * forcing (CLB_F_PRECIP, CLB_F_TOP_BC_H, CLB_F_BOT_BC_*) and the parameters; on return they hold the state at
+ * t_n + dt (in the Y fields, or in the U fields with CLB_OPT_OUT_OF_PLACE -- theta_i always in CLB_F_Y_THETA_I) and the
+ * cache of the explicit stage (p.soil.{theta_l, kappa, K, T, psi, Tf_depressed, total_water, total_energy,
+ * is_saturated, h_grad, R_ss, R_ess, infiltration, R_s}).  Three launches: the explicit cells, the per-column sweep
+ * (runoff + column integrals + explicit update), the fused implicit stage.  Asynchronous on the handle's stream. */
+int clb_soil_step(clb_handle h, double dt, int32_t max_iters);
 
 /* ---- diagnostics / reductions -------------------------------------------- */
 /* out[c] = sum_i field[i,c] * dz_c[i]  (ClimaCore column_integral_definite!,

@@ -124,6 +124,12 @@ def lib():
         L.orc_phase_change.restype = None
         L.orc_update_runoff.argtypes = [pp, px, C.POINTER(_RunoffParams), ps, pa, _dp, C.POINTER(_Runoff)]
         L.orc_update_runoff.restype = None
+        L.orc_surface_runoff.argtypes = [pp, px, ps, pa, C.c_int, _dp, _dp, _dp, _dp]
+        L.orc_surface_runoff.restype = None
+        L.orc_atmos_driven_top_fluxes.argtypes = [pp] + [_dp] * 8
+        L.orc_atmos_driven_top_fluxes.restype = None
+        L.orc_energy_water_free_drainage.argtypes = [pp, pa, _dp, _dp]
+        L.orc_energy_water_free_drainage.restype = None
         pcs = C.POINTER(_CO2Species)
         L.orc_co2_boundary_flux.argtypes = [pp, pcs, _dp, _dp, _dp]
         L.orc_co2_imp_tendency.argtypes = [pp, pcs, _dp, _dp, _dp, _dp]
@@ -270,6 +276,34 @@ class Problem:
         lib().orc_update_runoff(C.byref(P), C.byref(x) if x is not None else None, C.byref(R), C.byref(y),
                                 C.byref(aa) if aa is not None else None, _ptr(pr), C.byref(o))
         return out
+
+    # ---- atmosphere-driven top boundary fluxes ------------------------------
+    def surface_runoff(self, Y, kind, liquid_influx, X=None, a=None):
+        """update_infiltration_water_flux! of NoRunoff (kind 0) / SurfaceRunoff (kind 1) -> (is_saturated, infiltration, R_s)"""
+        inp = np.ascontiguousarray(np.broadcast_to(np.asarray(liquid_influx, dtype=np.float64), (self.ncol,)))
+        sat, inf, R_s = np.zeros((self.ncol, self.N)), np.zeros(self.ncol), np.zeros(self.ncol)
+        P, y = self.c_struct(), Y.c_struct()
+        x = X.c_struct() if X is not None else None
+        aa = a.c_struct() if a is not None else None
+        lib().orc_surface_runoff(C.byref(P), C.byref(x) if x is not None else None, C.byref(y),
+                                 C.byref(aa) if aa is not None else None, int(kind), _ptr(inp), _ptr(sat), _ptr(inf), _ptr(R_s))
+        return sat, inf, R_s
+
+    def atmos_driven_top_fluxes(self, infiltration, vapor_flux_liq, lhf, shf, R_n, T_air):
+        """soil_boundary_fluxes!(::AtmosDrivenFluxBC, Val((:soil,)), ...) after the runoff -> (top_bc.water, top_bc.heat)"""
+        arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (self.ncol,)))
+                for v in (infiltration, vapor_flux_liq, lhf, shf, R_n, T_air)]
+        w, h = np.zeros(self.ncol), np.zeros(self.ncol)
+        P = self.c_struct()
+        lib().orc_atmos_driven_top_fluxes(C.byref(P), *[_ptr(v) for v in arrs], _ptr(w), _ptr(h))
+        return w, h
+
+    def energy_water_free_drainage(self, a):
+        """soil_boundary_fluxes!(::EnergyWaterFreeDrainage, ::BottomBoundary, ...) -> (bottom_bc.water, bottom_bc.heat)"""
+        w, h = np.zeros(self.ncol), np.zeros(self.ncol)
+        P, aa = self.c_struct(), a.c_struct()
+        lib().orc_energy_water_free_drainage(C.byref(P), C.byref(aa), _ptr(w), _ptr(h))
+        return w, h
 
     # ---- SoilCO2Model implicit diffusion (SURVEY 8f rank 3) -----------------------------------
     def co2_species(self, D, theta_eff, c_atm=None):

@@ -815,6 +815,77 @@ void orc_update_runoff(const orc_problem *P, const orc_explicit_params *X, const
 }
 
 /* ------------------------------------------------------------------ */
+/* Atmosphere-driven top boundary fluxes (second half) */
+/* ------------------------------------------------------------------ */
+
+/* soil_infiltration_capacity: Runoff.jl:385-410 (RichardsModel: -K_sat; EnergyHydrology: -K_sat x impedance x
+ * viscosity at the top cell centre, from p.soil.theta_l / T) */
+static double infiltration_capacity(const orc_problem *P, const orc_explicit_params *X, const orc_state *Y,
+                                    const orc_aux *a, int64_t kt)
+{
+    if (P->model != ORC_ENERGY_HYDROLOGY) return -1 * P->K_sat[kt];
+    return -P->K_sat[kt] *
+           orc_impedance_factor(Y->theta_i[kt] / (a->theta_l[kt] + Y->theta_i[kt] - P->theta_r[kt]), X->Omega) *
+           orc_viscosity_factor(a->T[kt], X->gamma, X->gammaT_ref);
+}
+
+/* update_infiltration_water_flux!(p, ::NoRunoff, input, ...): Runoff.jl:69-71 (infiltration = input) and
+ * update_infiltration_water_flux!(p, ::SurfaceRunoff, input, Y, t, model): Runoff.jl:129-148 with
+ * surface_infiltration :109-111 and is_saturated :432-434 (heaviside(theta_l + theta_i - nu) per cell).
+ * kind: 0 NoRunoff, 1 SurfaceRunoff.  is_saturated / R_s may be NULL for NoRunoff. */
+void orc_surface_runoff(const orc_problem *P, const orc_explicit_params *X, const orc_state *Y, const orc_aux *a,
+                        int kind, const double *input, double *is_saturated, double *infiltration, double *R_s)
+{
+    const int N = P->N;
+    const int eh = P->model == ORC_ENERGY_HYDROLOGY;
+    FOR_COLUMNS(P, c)
+    {
+        if (kind == 0) {
+            infiltration[c] = input[c];
+            continue;
+        }
+        for (int i = 0; i < N; ++i) {
+            const int64_t k = c * N + i;
+            is_saturated[k] = orc_heaviside((Y->theta_l[k] + (eh ? Y->theta_i[k] : 0.0)) - P->nu[k], 0.0);
+        }
+        const int64_t kt = c * N + N - 1;
+        const double ic = infiltration_capacity(P, X, Y, a, kt);
+        infiltration[c] = (1 - is_saturated[kt]) * dmax(ic, input[c]);
+        R_s[c] = fabs(input[c] - infiltration[c]);
+    }
+}
+
+/* soil_boundary_fluxes!(bc::AtmosDrivenFluxBC, Val((:soil,)), model, Y, p, t): boundary_conditions.jl:901-936 after the
+ * runoff has partitioned the liquid influx (compute_liquid_influx :955-961 = p.drivers.P_liq):
+ *   top_bc.water = infiltration + turbulent_fluxes.vapor_flux_liq
+ *   top_bc.heat  = R_n + lhf + shf + infiltration * volumetric_internal_energy_liq(p.drivers.T)   (:988-1002)
+ * The turbulent fluxes and the net radiation are the host model's (SurfaceFluxes.jl, radiation drivers). */
+void orc_atmos_driven_top_fluxes(const orc_problem *P, const double *infiltration, const double *vapor_flux_liq,
+                                 const double *lhf, const double *shf, const double *R_n, const double *T_air,
+                                 double *top_bc_w, double *top_bc_h)
+{
+    FOR_COLUMNS(P, c)
+    {
+        top_bc_w[c] = infiltration[c] + vapor_flux_liq[c];
+        const double inf_e = infiltration[c] * orc_volumetric_internal_energy_liq(T_air[c], P->rho_l, P->cp_l, P->T_ref);
+        top_bc_h[c] = R_n[c] + lhf[c] + shf[c] + inf_e;
+    }
+}
+
+/* soil_boundary_fluxes!(::EnergyWaterFreeDrainage, ::BottomBoundary, ...): boundary_conditions.jl:590-608:
+ *   bottom_bc.water = -K_1, bottom_bc.heat = -K_1 * volumetric_internal_energy_liq(T_1)  (level 1 = the bottom cell) */
+void orc_energy_water_free_drainage(const orc_problem *P, const orc_aux *a, double *bot_bc_w, double *bot_bc_h)
+{
+    const int N = P->N;
+    FOR_COLUMNS(P, c)
+    {
+        const int64_t k = c * N;
+        bot_bc_w[c] = -1 * a->K[k];
+        bot_bc_h[c] = -1 * a->K[k] * orc_volumetric_internal_energy_liq(a->T[k], P->rho_l, P->cp_l, P->T_ref);
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* SoilCO2Model: implicit CO2 / O2 diffusion        */
 /* ------------------------------------------------------------------ */
 

@@ -161,6 +161,15 @@ typedef struct {
 void orc_update_runoff(const orc_problem *P, const orc_explicit_params *X, const orc_runoff_params *R, const orc_state *Y,
                        const orc_aux *a, const double *precip, orc_runoff *out);
 
+/* ---- atmosphere-driven top boundary fluxes: boundary_conditions.jl:590-608, 901-1002,
+ *      Runoff/Runoff.jl:69-71, 109-148.  kind: 0 NoRunoff, 1 SurfaceRunoff (TOPMODELRunoff: orc_update_runoff). */
+void orc_surface_runoff(const orc_problem *P, const orc_explicit_params *X, const orc_state *Y, const orc_aux *a,
+                        int kind, const double *input, double *is_saturated, double *infiltration, double *R_s);
+void orc_atmos_driven_top_fluxes(const orc_problem *P, const double *infiltration, const double *vapor_flux_liq,
+                                 const double *lhf, const double *shf, const double *R_n, const double *T_air,
+                                 double *top_bc_w, double *top_bc_h);
+void orc_energy_water_free_drainage(const orc_problem *P, const orc_aux *a, double *bot_bc_w, double *bot_bc_h);
+
 /* ---- SoilCO2Model implicit diffusion: Biogeochemistry.jl:320-413, 1119-1195 ---------- */
 /* One diffusing species (CO2 with p.soilco2.{D, theta_eff}, or O2 with {D_o2, theta_eff_o2}); both have the same
  * G . Diag . D structure.  c_atm != NULL: the top BC is the atmosphere's state (AtmosCO2StateBC / AtmosO2StateBC,

@@ -10,10 +10,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-def _setup(ncol, N, seed, closure, math_mode, layout):
+def _setup(ncol, N, seed, closure, math_mode, layout, explicit_kernel=0, ice=True):
     import climaland_b200 as cl
     from climaland_b200 import workloads
-    w = workloads.make_workload("energy_hydrology", ncol, N=N, seed=seed, topmodel=False)
+    w = workloads.make_workload("energy_hydrology", ncol, N=N, seed=seed, topmodel=False, ice=ice)
     if closure == 1:
         from test_cuda_hooks_parity import _to_brooks_corey
         w = _to_brooks_corey(w)
@@ -23,6 +23,7 @@ def _setup(ncol, N, seed, closure, math_mode, layout):
     a = P.new_aux()
     P.update_aux(Xp, Y, a)
     s = cuda_solver(w, closure=closure, math_mode=math_mode, layout=layout)
+    s.set_option("explicit_kernel", explicit_kernel)
     for k, v in xp.items():
         s.set(k, v)
     s.set_explicit_params(**workloads.EXPLICIT_SCALARS)
@@ -68,6 +69,30 @@ def test_phase_change_source(closure, N, ncol, math_mode, fused):
     assert_close(s.get("dye_theta_l"), dl, TOL, "dY.theta_l", elem_tol=2e-12)
     assert_close(s.get("dye_theta_i"), di, TOL, "dY.theta_i", elem_tol=2e-12)
     s.close()
+
+
+@pytest.mark.parametrize("ice", [True, False], ids=["ice", "noice"])
+@pytest.mark.parametrize("layout", [1, 2], ids=["colfast", "levfast"])
+@pytest.mark.parametrize("closure,N,ncol", [(0, 15, 1003), (1, 15, 257), (0, 50, 131)])
+def test_percell_and_warp_uniform_kernels_agree(closure, N, ncol, layout, ice):
+    """CLB_OPT_EXPLICIT_KERNEL: the kernel that follows the reference's case distinctions cell by cell (1) and the one
+    with warp-uniform control flow (0, the default; what every FAST case above ran) evaluate the same formulas: equal
+    up to the last bits of one exp(log k_u), both within the per-call bar of the oracle; with ice in some cells of a
+    warp and with none anywhere (the shortcut of the whole warp); column counts that leave a partial last warp."""
+    out = {}
+    for kern in (0, 1):
+        cl, w, P, Xp, Y, a, s = _setup(ncol, N, 17, closure, 0, layout, explicit_kernel=kern, ice=ice)
+        dl, di = np.zeros_like(Y.theta_l), np.zeros_like(Y.theta_l)
+        P.phase_change(Xp, Y, a, dl, di)
+        s.update_aux_and_phase_change()
+        out[kern] = {dev: s.get(dev) for dev, _ in AUX_FIELDS}
+        out[kern].update(dye_theta_l=s.get("dye_theta_l"), dye_theta_i=s.get("dye_theta_i"))
+        for dev, orc_name in AUX_FIELDS:
+            assert_close(out[kern][dev], getattr(a, orc_name), TOL, orc_name)
+        assert_close(out[kern]["dye_theta_l"], dl, TOL, "source theta_l", elem_tol=2e-12)
+        s.close()
+    for k in out[0]:  # the source: a difference, 1 / alpha and g / LH as multiplications by reciprocals in kernel 0
+        assert_close(out[0][k], out[1][k], 1e-13, "source " + k if k.startswith("dye") else k, elem_tol=2e-12)
 
 
 def test_phase_change_alone_matches_source_scale():

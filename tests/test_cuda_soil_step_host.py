@@ -45,9 +45,9 @@ def _oracle_step(P, U, p, X, forcing, dt, iters):
     return float(np.abs(di).max()), float(R.R_ss.max())
 
 
-def _cuda(w, xp, forcing, out_of_place=False, options=None):
+def _cuda(w, xp, forcing, out_of_place=False, options=None, **kw):
     from climaland_b200 import workloads
-    s = cuda_solver(w, out_of_place=out_of_place)
+    s = cuda_solver(w, out_of_place=out_of_place, **kw)
     for k, v in (options or {}).items():
         s.set_option(k, v)
     for k, v in xp.items():
@@ -115,3 +115,41 @@ def test_soil_step_host_routes_agree_bitwise():
     for tag in ("chunked", "pageable", "chunks7"):
         for k in res["plain"]:
             assert np.array_equal(res[tag][k], res["plain"][k]), (tag, k)
+
+
+@pytest.mark.parametrize("form", ["one_launch", "level_fastest", "libm", "percell_kernel", "outofplace"])
+def test_resident_soil_step_matches_oracle(form):
+    """clb_soil_step: the same whole step on resident mirrors, two steps in a row.  one_launch: column-fastest mirrors,
+    FAST arithmetic -- the explicit stage is ONE kernel (cells + per-column sweep through shared memory + in-place
+    update); level_fastest: sweep kernel, then cells kernel with the in-place update; libm / percell_kernel: cells
+    kernel (source stored), then the sweep, which applies the update."""
+    dt, iters, ncol = 900.0, 3, 5003
+    out_of_place = form == "outofplace"
+    kw = {"level_fastest": dict(layout=2), "libm": dict(math_mode=1)}.get(form, {})
+    opts = {"explicit_kernel": 1} if form == "percell_kernel" else None
+    w, xp, forcing = _problem(ncol, 9)
+    P, U, p = oracle_problem(w, nthreads=os.cpu_count() or 1)
+    X = P.explicit_params(**xp)
+    s = _cuda(w, xp, forcing, out_of_place, opts, **kw)
+    s.set("precip", forcing["precip"])
+    for step in range(2):
+        a = P.new_aux()
+        P.update_aux(X, U, a)  # the cache of the explicit stage at t_n, for the comparison below
+        _oracle_step(P, U, p, X, forcing, dt, iters)
+        s.soil_step(dt, iters)
+        if out_of_place:  # the integrator's U -> u
+            for k in ("theta_l", "rho_e_int", "intf_w", "intf_e"):
+                s.copy("y_" + k, "u_" + k)
+        tol = 1e-12 if step == 0 else 1e-11
+        assert_close(s.get("y_theta_l"), U.theta_l, tol, "theta_l")
+        assert_close(s.get("y_theta_i"), U.theta_i, tol, "theta_i", floor_rel=1e-3)
+        assert_close(s.get("y_rho_e_int"), U.rho_e_int, tol, "rho_e_int")
+        assert_close(s.get("y_intf_w"), U.intF_w, tol, "intF_w")
+        # what the explicit stage leaves in the cache: update_aux!'s fields and column integrals, the runoff's outputs
+        for dev, name in (("p_t", "T"), ("kappa_lag", "kappa"), ("k_lag", "K"), ("total_water", "total_water"),
+                          ("total_energy", "total_energy")):
+            assert_close(s.get(dev), getattr(a, name), tol, name)
+        assert_close(s.get("r_ss"), P.f["R_ss"], tol, "R_ss")
+        assert_close(s.get("h_grad"), P.f["h_grad"], tol, "h_grad")
+        assert_close(s.get("is_saturated"), P.f["is_saturated"], tol, "is_saturated")
+    s.close()

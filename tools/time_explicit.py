@@ -18,10 +18,11 @@ xp = workloads.make_explicit_params(w, 0)
 # the totals kernel re-reads the 3 state fields; PhaseChange reads 3 state + 8 parameters + 3 cache, and
 # reads + writes the two tendencies; fused = update_aux! + the 4 tendency accesses
 BYTES = {"update_aux": 8 * (17 + 6 + 3), "phase_change_source": 8 * (14 + 4), "update_aux_and_phase_change": 8 * (17 + 6 + 3 + 4)}
-for mm, mname in ((0, "fast"), (1, "libm")):
+for mm, mname, kern in ((0, "fast (warp-uniform)", 0), (0, "fast (per-cell cases)", 1), (1, "libm", 0)):
     ss = []
     for r in range(4):
         s = cuda_solver(w, math_mode=mm)
+        s.set_option("explicit_kernel", kern)
         for k, v in xp.items():
             s.set(k, v)
         s.set_explicit_params(**workloads.EXPLICIT_SCALARS)

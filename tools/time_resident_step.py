@@ -37,18 +37,26 @@ def step(s):
     s.implicit_step(dt, 3)
 
 
+def time_it(fn, label, launches):
+    for s in ss:
+        fn(s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(200):
+        fn(ss[k % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / 200
+    st = ss[0].implicit_step(dt, 3, want_stats=True)
+    print(f"resident EnergyHydrology soil step, {label} ({NCOL} columns x {N} levels, {launches} launches): {us:.1f} us  "
+          f"{NCOL / (us * 1e-6):.3e} column-steps/s  SYPD(1 deg) = {dt / (us * 1e-6) / 365:.0f}  nan_count = {st['nan_count']}")
+
+
+time_it(step, "call by call", 8)
+time_it(lambda s: s.soil_step(dt, 3), "clb_soil_step", 3)
 for s in ss:
-    step(s)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for k in range(200):
-    step(ss[k % 4])
-e1.record()
-torch.cuda.synchronize()
-us = 1e3 * e0.elapsed_time(e1) / 200
-st = ss[0].implicit_step(dt, 3, want_stats=True)
-print(f"resident EnergyHydrology soil step ({NCOL} columns x {N} levels, 8 launches): {us:.1f} us  "
-      f"{NCOL / (us * 1e-6):.3e} column-steps/s  SYPD(1 deg) = {dt / (us * 1e-6) / 365:.0f}  nan_count = {st['nan_count']}")
+    s.set_option("explicit_kernel", 1)
+time_it(lambda s: s.soil_step(dt, 3), "clb_soil_step with the per-cell explicit kernel", 3)
 for s in ss:
     s.close()
