@@ -163,6 +163,8 @@ struct clb_handle_s {
     bool co2_top_state[2] = {false, false};  // SoilCO2Model: AtmosCO2StateBC / AtmosO2StateBC at the top
     int host_route = 0, host_chunks = 0, tile_boxes = 0;  // CLB_OPT_HOST_ROUTE / _HOST_CHUNKS / _TILE_BOXES
     int explicit_kernel = 0;                              // CLB_OPT_EXPLICIT_KERNEL
+    int runoff_model = CLB_RUNOFF_TOPMODEL;               // CLB_OPT_RUNOFF_MODEL
+    bool top_atmos = false, bottom_ewfd = false;          // CLB_OPT_TOP_ATMOS_DRIVEN, CLB_OPT_BOTTOM_EWFD
     // multi-GPU
     NcclComm comm = nullptr;
     int32_t n_ranks = 1, rank = 0;
@@ -797,6 +799,34 @@ __global__ void k_test_math(int kind, const double *x, const double *y, double *
 // =============================================================================
 #include "clb_api_explicit.inc"
 
+namespace {
+// the assembly kernels on columns [c0, c0 + n) (c0 = 0, n = ncol: all)
+int launch_atmos_assembly(clb_handle h, const clb::DevView &P, int64_t c0)
+{
+    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    double *const *F = h->field;
+    clb::AtmosView A = {};
+    A.infiltration = F[CLB_F_INFILTRATION] + c0;
+    A.top_bc_w = F[CLB_F_TOP_BC_W] + c0;
+    if (eh) {
+        A.vapor_flux_liq = F[CLB_F_VAPOR_FLUX_LIQ] + c0; A.lhf = F[CLB_F_LHF] + c0; A.shf = F[CLB_F_SHF] + c0;
+        A.R_n = F[CLB_F_R_N] + c0; A.T_air = F[CLB_F_T_AIR] + c0; A.top_bc_h = F[CLB_F_TOP_BC_H] + c0;
+    }
+    clb::k_atmos_driven_fluxes<<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, A);
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+int atmos_fields_ready(clb_handle h, const char *who)
+{
+    TRY(require(h, {CLB_F_PRECIP}, who));
+    if (h->cfg.model == CLB_ENERGY_HYDROLOGY)
+        TRY(require(h, {CLB_F_VAPOR_FLUX_LIQ, CLB_F_LHF, CLB_F_SHF, CLB_F_R_N, CLB_F_T_AIR}, who));
+    TRY(alloc_fields(h, {CLB_F_INFILTRATION, CLB_F_TOP_BC_W}));
+    if (h->cfg.model == CLB_ENERGY_HYDROLOGY) TRY(alloc_fields(h, {CLB_F_TOP_BC_H}));
+    return CLB_OK;
+}
+}  // namespace
+
 #include "clb_api_host_step.inc"
 
 #include "clb_api_soilco2.inc"
@@ -988,6 +1018,16 @@ int clb_set_option(clb_handle h, int32_t option, int64_t value)
         return CLB_OK;
     case CLB_OPT_EXPLICIT_KERNEL:
         h->explicit_kernel = value != 0;
+        return CLB_OK;
+    case CLB_OPT_RUNOFF_MODEL:
+        if (value < CLB_RUNOFF_NONE || value > CLB_RUNOFF_TOPMODEL) return fail(CLB_ERR_INVALID, "clb_set_option: CLB_OPT_RUNOFF_MODEL takes a CLB_RUNOFF_* value");
+        h->runoff_model = (int)value;
+        return CLB_OK;
+    case CLB_OPT_TOP_ATMOS_DRIVEN:
+        h->top_atmos = value != 0;
+        return CLB_OK;
+    case CLB_OPT_BOTTOM_EWFD:
+        h->bottom_ewfd = value != 0;
         return CLB_OK;
     default:
         return fail(CLB_ERR_INVALID, "clb_set_option: unknown option %d", option);
@@ -1288,6 +1328,55 @@ int clb_update_runoff(clb_handle h)
     if (h->cfg.math_mode == CLB_MATH_FAST) clb::k_update_runoff<0><<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, R);
     else clb::k_update_runoff<1><<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, R);
     nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
+int clb_update_atmos_driven_fluxes(clb_handle h, int32_t runoff_model)
+{
+    TRY(check_handle(h));
+    const bool eh = h->cfg.model == CLB_ENERGY_HYDROLOGY;
+    if (runoff_model < CLB_RUNOFF_NONE || runoff_model > CLB_RUNOFF_TOPMODEL)
+        return fail(CLB_ERR_INVALID, "clb_update_atmos_driven_fluxes: runoff_model must be a CLB_RUNOFF_* value");
+    if (!h->grid_set) return fail(CLB_ERR_UNSET, "clb_set_grid was never called");
+    TRY(atmos_fields_ready(h, "update_atmos_driven_fluxes"));
+    if (runoff_model == CLB_RUNOFF_TOPMODEL) {
+        TRY(clb_update_runoff(h));
+    } else {
+        DeviceGuard guard(h->cfg.device);
+        TRY(require(h, {CLB_F_NU, CLB_F_THETA_R, CLB_F_K_SAT, CLB_F_Y_THETA_L}, "update_atmos_driven_fluxes"));
+        if (eh && runoff_model == CLB_RUNOFF_SURFACE) {
+            if (!h->explicit_set) return fail(CLB_ERR_UNSET, "update_atmos_driven_fluxes: clb_set_explicit_params was never called");
+            TRY(require(h, {CLB_F_Y_THETA_I, CLB_F_THETA_L_LAG, CLB_F_P_T}, "update_atmos_driven_fluxes (call clb_update_aux first)"));
+        }
+        if (runoff_model == CLB_RUNOFF_SURFACE) TRY(alloc_fields(h, {CLB_F_IS_SATURATED, CLB_F_R_S}));
+        const clb::DevView P = make_view(h);
+        double *const *F = h->field;
+        clb::RunoffView R = {};
+        R.model = runoff_model;
+        R.precip = F[CLB_F_PRECIP];
+        R.is_sat = F[CLB_F_IS_SATURATED]; R.infiltration = F[CLB_F_INFILTRATION]; R.R_s = F[CLB_F_R_S];
+        R.p_theta_l = F[CLB_F_THETA_L_LAG]; R.p_T = F[CLB_F_P_T];
+        R.Omega = h->explicit_k.Omega; R.gamma = h->explicit_k.gamma; R.gammaT_ref = h->explicit_k.gammaT_ref;
+        if (eh && !R.p_T) R.p_T = F[CLB_F_Y_THETA_L];  // NoRunoff never reads it; keeps the sweep off its own-T path
+        if (h->cfg.math_mode == CLB_MATH_FAST) clb::k_update_runoff<0><<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, R);
+        else clb::k_update_runoff<1><<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, R);
+        CUDA_TRY(cudaGetLastError());
+    }
+    DeviceGuard guard(h->cfg.device);
+    return launch_atmos_assembly(h, make_view(h), 0);
+}
+
+int clb_update_energy_water_free_drainage(clb_handle h)
+{
+    TRY(check_handle(h));
+    if (h->cfg.model != CLB_ENERGY_HYDROLOGY) return fail(CLB_ERR_INVALID, "clb_update_energy_water_free_drainage: EnergyHydrology only");
+    TRY(require(h, {CLB_F_K_LAG, CLB_F_P_T}, "update_energy_water_free_drainage (call clb_update_aux first)"));
+    DeviceGuard guard(h->cfg.device);
+    TRY(alloc_fields(h, {CLB_F_BOT_BC_W, CLB_F_BOT_BC_H}));
+    const clb::DevView P = make_view(h);
+    clb::k_energy_water_free_drainage<<<grid_for(P.ncol), kBlock, 0, h->stream>>>(P, h->field[CLB_F_K_LAG], h->field[CLB_F_P_T],
+                                                                                    h->field[CLB_F_BOT_BC_W], h->field[CLB_F_BOT_BC_H]);
     CUDA_TRY(cudaGetLastError());
     return CLB_OK;
 }

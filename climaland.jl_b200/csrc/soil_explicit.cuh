@@ -309,6 +309,7 @@ struct RunoffView {
     const double *dYe_theta_l = nullptr, *dYe_theta_i = nullptr;
     // the column integrals of update_aux! (k_explicit_totals) taken in the same sweep over the levels; nullptr: not here
     double *total_water = nullptr, *total_energy = nullptr;
+    int model = 2;  // CLB_RUNOFF_*: 0 NoRunoff, 1 SurfaceRunoff, 2 TOPMODELRunoff (k_update_runoff only)
 };
 
 // ---- FAST mode, warp-uniform control flow ------------------------------------------------------------------
@@ -714,12 +715,18 @@ __global__ void __launch_bounds__(128) k_update_runoff(const DevView P, const Ru
                     T = E.T_ref + dv<MATH>(rho_e[j] + thi[j] * E.rho_i * E.LH_f0, volumetric_heat_capacity(theta_l, thi[j], rcds[j], E));
                     if (i == P.N - 1) { T_top = T; thl_top = theta_l; }
                 }
-                const double s_all = heaviside((th[j] + thi[j] - theta_r[j]) - range) * (th[j] + thi[j] - theta_r[j]) / range;
-                const double s_liq = heaviside((th[j] - theta_r[j]) - range) * (th[j] - theta_r[j]) / range;
-                R.is_sat[q] = s_liq;
-                h_all += s_all * dz;
-                h_liq += s_liq * dz;
-                if (eh) e_liq += s_liq * volumetric_internal_energy_liq(T, E) * dz;
+                if (R.model == 2) {
+                    const double s_all = heaviside((th[j] + thi[j] - theta_r[j]) - range) * (th[j] + thi[j] - theta_r[j]) / range;
+                    const double s_liq = heaviside((th[j] - theta_r[j]) - range) * (th[j] - theta_r[j]) / range;
+                    R.is_sat[q] = s_liq;
+                    h_all += s_all * dz;
+                    h_liq += s_liq * dz;
+                    if (eh) e_liq += s_liq * volumetric_internal_energy_liq(T, E) * dz;
+                } else if (R.model == 1) {  // SurfaceRunoff: is_saturated(theta_l + theta_i, nu), Runoff.jl:139, 432-434
+                    const double s = heaviside((th[j] + thi[j]) - nu[j]);
+                    R.is_sat[q] = s;
+                    if (i == P.N - 1) h_all = s;  // the top centre's value (top_center_to_surface)
+                }
             }
         }
     }
@@ -733,14 +740,21 @@ __global__ void __launch_bounds__(128) k_update_runoff(const DevView P, const Ru
         ic = -__ldg(P.K_sat + qt) * imp * ex<MATH>(R.gamma * (Tt - R.gammaT_ref));
     }
     const double precip = R.precip[c];
-    const double f_sat = fmin(R.f_max[c] * ex<MATH>(-R.f_over / 2.0 * (R.depth - h_all)), 1.0);
-    const double inf = (1.0 - f_sat) * fmax(ic, precip);
-    const double R_ss = R.R_sb * ex<MATH>(-R.f_over * (R.depth - h_liq));
+    double inf;
+    if (R.model == 2) {
+        const double f_sat = fmin(R.f_max[c] * ex<MATH>(-R.f_over / 2.0 * (R.depth - h_all)), 1.0);
+        inf = (1.0 - f_sat) * fmax(ic, precip);
+        const double R_ss = R.R_sb * ex<MATH>(-R.f_over * (R.depth - h_liq));
+        R.h_grad[c] = h_liq;
+        R.R_ss[c] = R_ss;
+        if (eh) R.R_ess[c] = e_liq * (R_ss / fmax(h_liq, kEps));
+    } else if (R.model == 1) {
+        inf = (1 - h_all) * fmax(ic, precip);  // surface_infiltration, Runoff.jl:109-111
+    } else {
+        inf = precip;                          // NoRunoff, Runoff.jl:69-71
+    }
     R.infiltration[c] = inf;
-    R.R_s[c] = fabs(precip - inf);
-    R.h_grad[c] = h_liq;
-    R.R_ss[c] = R_ss;
-    if (eh) R.R_ess[c] = e_liq * (R_ss / fmax(h_liq, kEps));
+    if (R.model != 0) R.R_s[c] = fabs(precip - inf);
     if (totals) {
         R.total_water[c] = tw;
         R.total_energy[c] = te;
@@ -764,6 +778,37 @@ __global__ void __launch_bounds__(128) k_update_runoff(const DevView P, const Ru
             }
         }
     }
+}
+
+// soil_boundary_fluxes!(bc::AtmosDrivenFluxBC, Val((:soil,)), ...) after the runoff: boundary_conditions.jl:922-935,
+// 988-1002.  heat == nullptr (RichardsModel): top_bc = infiltration (boundary_flux! :200-213).
+struct AtmosView {
+    const double *infiltration, *vapor_flux_liq, *lhf, *shf, *R_n, *T_air;
+    double *top_bc_w, *top_bc_h;
+};
+__global__ void __launch_bounds__(128) k_atmos_driven_fluxes(const DevView P, const AtmosView A)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.ncol) return;
+    const double inf = A.infiltration[c];
+    if (!A.top_bc_h) {
+        A.top_bc_w[c] = inf;
+        return;
+    }
+    A.top_bc_w[c] = inf + A.vapor_flux_liq[c];
+    A.top_bc_h[c] = A.R_n[c] + A.lhf[c] + A.shf[c] + inf * volumetric_internal_energy_liq(A.T_air[c], P.earth);
+}
+
+// soil_boundary_fluxes!(::EnergyWaterFreeDrainage, ::BottomBoundary, ...): boundary_conditions.jl:590-608
+__global__ void __launch_bounds__(128) k_energy_water_free_drainage(const DevView P, const double *p_K, const double *p_T,
+                                                                     double *bot_bc_w, double *bot_bc_h)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.ncol) return;
+    const int64_t q = P.at(0, c);
+    const double K = p_K[q];
+    bot_bc_w[c] = -1 * K;
+    bot_bc_h[c] = -1 * K * volumetric_internal_energy_liq(p_T[q], P.earth);
 }
 
 }  // namespace clb

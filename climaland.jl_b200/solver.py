@@ -251,6 +251,15 @@ class SoilColumnSolver:
         po = (C.c_void_p * n_out)(*[v.ctypes.data for v in outputs.values()])
         check(self.L.clb_soil_step_host(self.h, float(dt), int(max_iters), fi, pi, n_in, fo, po, n_out))
 
+    def update_atmos_driven_fluxes(self, runoff_model=2):
+        """soil_boundary_fluxes!(::AtmosDrivenFluxBC, ...) after the host's turbulent fluxes and net radiation:
+        runoff (0 NoRunoff, 1 SurfaceRunoff, 2 TOPMODELRunoff) + the assembly of top_bc (clb_update_atmos_driven_fluxes)"""
+        check(self.L.clb_update_atmos_driven_fluxes(self.h, int(runoff_model)))
+
+    def update_energy_water_free_drainage(self):
+        """soil_boundary_fluxes!(::EnergyWaterFreeDrainage, ::BottomBoundary, ...)"""
+        check(self.L.clb_update_energy_water_free_drainage(self.h))
+
     def soil_step(self, dt, max_iters=3):
         """A whole EnergyHydrology soil step on resident state (clb_soil_step): explicit cells, the per-column sweep
         (runoff, column integrals, explicit update), the fused implicit stage -- three launches, no host transfer."""

@@ -102,8 +102,20 @@ enum { CLB_OPT_OUT_OF_PLACE = 1,        /* fused stage reads Y (= temp) and writ
        CLB_OPT_HOST_CHUNKS = 5,         /* column chunks of the pipelined host route (0 = default, 4) */
        CLB_OPT_TILE_BOXES = 6,          /* lane kernels: 0 = two TMA boxes of the arena per tile where the mirrors are
                                            equally spaced, 1 = one box per field always (same results, bit for bit) */
-       CLB_OPT_EXPLICIT_KERNEL = 7 };   /* explicit stage, CLB_MATH_FAST: 0 = warp-uniform control flow (default),
+       CLB_OPT_EXPLICIT_KERNEL = 7,     /* explicit stage, CLB_MATH_FAST: 0 = warp-uniform control flow (default),
                                            1 = the reference's case distinctions cell by cell (comparison) */
+       /* clb_soil_step / clb_soil_step_host: what the explicit stage does about the boundary fluxes */
+       CLB_OPT_RUNOFF_MODEL = 8,        /* CLB_RUNOFF_*: how the liquid influx CLB_F_PRECIP becomes the infiltration
+                                           (default CLB_RUNOFF_TOPMODEL) */
+       CLB_OPT_TOP_ATMOS_DRIVEN = 9,    /* 1: AtmosDrivenFluxBC -- top_bc = (infiltration + vapor_flux_liq, R_n + lhf +
+                                           shf + infiltration * e_liq(T_air)); 0 (default): top_bc.water =
+                                           infiltration, top_bc.heat as the caller set it */
+       CLB_OPT_BOTTOM_EWFD = 10 };      /* 1: EnergyWaterFreeDrainage bottom -- bottom_bc = (-K_1, -K_1 e_liq(T_1));
+                                           0 (default): the bottom fluxes as the caller set them */
+/* the runoff models of Runoff/Runoff.jl */
+enum { CLB_RUNOFF_NONE = 0,             /* NoRunoff :51-75: infiltration = influx */
+       CLB_RUNOFF_SURFACE = 1,          /* SurfaceRunoff :78-154: saturation excess at the top cell */
+       CLB_RUNOFF_TOPMODEL = 2 };       /* TOPMODELRunoff :157-283 */
 
 /* Field ids.  "cell" fields are N x ncol, "col" fields are ncol. */
 typedef enum {
@@ -164,6 +176,9 @@ typedef enum {
     CLB_F_CO2_DFLUXBCDY, CLB_F_O2_DFLUXBCDY,  /* p.soilco2.dfluxBCdY(_o2) */
     CLB_F_SFC_W_DI, CLB_F_SFC_B, CLB_F_SFC_X, /* one surface (PointSpace) variable of an integrated model: its
                                                  DiagonalMatrixRow Jacobian block, right-hand side, solution */
+    /* the host model's surface fluxes for the atmosphere-driven top boundary (AtmosDrivenFluxBC,
+     * boundary_conditions.jl:901-936): p.soil.turbulent_fluxes.{vapor_flux_liq, lhf, shf}, p.soil.R_n, p.drivers.T */
+    CLB_F_VAPOR_FLUX_LIQ, CLB_F_LHF, CLB_F_SHF, CLB_F_R_N, CLB_F_T_AIR,
     CLB_F_NUM
 } clb_field;
 
@@ -293,6 +308,24 @@ typedef struct {
 } clb_runoff_params;
 int clb_set_runoff_params(clb_handle h, const clb_runoff_params *p);
 int clb_update_runoff(clb_handle h);
+
+/* The atmosphere-driven top boundary of the explicit stage (second half):
+ * soil_boundary_fluxes!(bc::AtmosDrivenFluxBC, Val((:soil,)), model, Y, p, t), boundary_conditions.jl:901-936, after the
+ * host model has evaluated turbulent_fluxes! and net_radiation! (SurfaceFluxes.jl and the radiation drivers stay in
+ * Julia) and uploaded CLB_F_VAPOR_FLUX_LIQ, CLB_F_LHF, CLB_F_SHF, CLB_F_R_N, CLB_F_T_AIR and the liquid influx
+ * CLB_F_PRECIP (compute_liquid_influx :955-961):
+ *   update_infiltration_water_flux!(p, runoff, influx, Y, t, model)   runoff_model = CLB_RUNOFF_NONE (Runoff.jl:69-71),
+ *       _SURFACE (:129-148: CLB_F_IS_SATURATED = heaviside(theta_l + theta_i - nu), infiltration = (1 - is_saturated at
+ *       the top cell) max(i_c, influx), R_s) or _TOPMODEL (clb_update_runoff)
+ *   top_bc.water = infiltration + vapor_flux_liq
+ *   top_bc.heat  = R_n + lhf + shf + infiltration * volumetric_internal_energy_liq(T_air)        (:988-1002)
+ * into CLB_F_TOP_BC_W / _H.  RichardsModel (RichardsAtmosDrivenFluxBC, boundary_flux! :200-213): top_bc = infiltration.
+ * EnergyHydrology needs p.soil.{theta_l, T} (clb_update_aux) for the infiltration capacity. */
+int clb_update_atmos_driven_fluxes(clb_handle h, int32_t runoff_model);
+/* soil_boundary_fluxes!(::EnergyWaterFreeDrainage, ::BottomBoundary, ...), boundary_conditions.jl:590-608:
+ * CLB_F_BOT_BC_W = -K_1, CLB_F_BOT_BC_H = -K_1 * volumetric_internal_energy_liq(T_1) from p.soil.{K, T} of the bottom
+ * cell (clb_update_aux). */
+int clb_update_energy_water_free_drainage(clb_handle h);
 
 /* ---- SoilCO2Model: implicit CO2 / O2 diffusion ---------- */
 /* Two more independent per-column tridiagonals with lagged coefficients, on the same columns and grid as the

@@ -61,6 +61,7 @@ const CLB_HOST, CLB_DEVICE = Int32(0), Int32(1)
     F_F_MAX; F_PRECIP; F_INFILTRATION; F_R_S
     F_CO2_TOP_BC; F_CO2_BOT_BC; F_O2_TOP_BC; F_O2_BOT_BC; F_CO2_C_ATM; F_O2_C_ATM; F_CO2_DFLUXBCDY; F_O2_DFLUXBCDY
     F_SFC_W_DI; F_SFC_B; F_SFC_X
+    F_VAPOR_FLUX_LIQ; F_LHF; F_SHF; F_R_N; F_T_AIR
 end
 
 # struct clb_config (same field order and widths as the header)
@@ -347,6 +348,57 @@ function update_infiltration_water_flux!(p, runoff::Soil.Runoff.TOPMODELRunoff, 
     b.energy && get_field!(p.soil.R_ess, b.h, F_R_ESS)
     return nothing
 end
+
+const CLB_RUNOFF_NONE, CLB_RUNOFF_SURFACE, CLB_RUNOFF_TOPMODEL = Int32(0), Int32(1), Int32(2)
+runoff_id(::Soil.Runoff.NoRunoff) = CLB_RUNOFF_NONE
+runoff_id(::Soil.Runoff.SurfaceRunoff) = CLB_RUNOFF_SURFACE
+runoff_id(::Soil.Runoff.TOPMODELRunoff) = CLB_RUNOFF_TOPMODEL
+
+"""
+    soil_boundary_fluxes!(bc::AtmosDrivenFluxBC, Val((:soil,)), model, Y, p, t, b::B200Soil, depth)
+
+src/standalone/Soil/boundary_conditions.jl:901-936 with the runoff and the assembly of top_bc on the device:
+`turbulent_fluxes!` and `net_radiation!` stay the reference's (SurfaceFluxes.jl, the radiation drivers); their results,
+the liquid influx and the air temperature are uploaded, clb_update_atmos_driven_fluxes partitions the influx
+(NoRunoff / SurfaceRunoff / TOPMODELRunoff) and writes top_bc.{water, heat}; Julia's copies are refreshed.
+"""
+function soil_boundary_fluxes!(bc::Soil.AtmosDrivenFluxBC, ::Val{(:soil,)}, model::Soil.EnergyHydrology, Y, p, t,
+                               b::B200Soil, depth)
+    ClimaLand.turbulent_fluxes!(p.soil.turbulent_fluxes, bc.atmos, model, Y, p, t)
+    ClimaLand.net_radiation!(p.soil.R_n, bc.radiation, model, Y, p, t)
+    tf = p.soil.turbulent_fluxes
+    set_field!(b.h, F_PRECIP, p.drivers.P_liq); set_field!(b.h, F_T_AIR, p.drivers.T)
+    set_field!(b.h, F_VAPOR_FLUX_LIQ, tf.vapor_flux_liq); set_field!(b.h, F_LHF, tf.lhf); set_field!(b.h, F_SHF, tf.shf)
+    set_field!(b.h, F_R_N, p.soil.R_n)
+    if bc.runoff isa Soil.Runoff.TOPMODELRunoff && !b.runoff_set[]
+        r = Ref(ClbRunoffParams(bc.runoff.f_over, bc.runoff.subsurface_source.R_sb, depth))
+        check(ccall((:clb_set_runoff_params, libclb), Cint, (Ptr{Cvoid}, Ref{ClbRunoffParams}), b.h.ptr, r))
+        set_field!(b.h, F_F_MAX, bc.runoff.f_max)
+        b.runoff_set[] = true
+    end
+    check(ccall((:clb_update_atmos_driven_fluxes, libclb), Cint, (Ptr{Cvoid}, Int32), b.h.ptr, runoff_id(bc.runoff)))
+    get_field!(p.soil.top_bc.water, b.h, F_TOP_BC_W); get_field!(p.soil.top_bc.heat, b.h, F_TOP_BC_H)
+    get_field!(p.soil.infiltration, b.h, F_INFILTRATION)
+    return nothing
+end
+
+"soil_boundary_fluxes!(::EnergyWaterFreeDrainage, ::BottomBoundary, ...): boundary_conditions.jl:590-608"
+function soil_boundary_fluxes!(bc::Soil.EnergyWaterFreeDrainage, ::ClimaLand.BottomBoundary, soil::Soil.EnergyHydrology,
+                               Δz, Y, p, t, b::B200Soil)
+    check(ccall((:clb_update_energy_water_free_drainage, libclb), Cint, (Ptr{Cvoid},), b.h.ptr))
+    get_field!(p.soil.bottom_bc.water, b.h, F_BOT_BC_W); get_field!(p.soil.bottom_bc.heat, b.h, F_BOT_BC_H)
+    return nothing
+end
+
+"""
+    soil_step!(b, dt; max_iters = 3)
+
+A whole EnergyHydrology soil step on the library's resident state (clb_soil_step): update_aux! + PhaseChange, the runoff
+and the boundary fluxes selected with clb_set_option (CLB_OPT_RUNOFF_MODEL, _TOP_ATMOS_DRIVEN, _BOTTOM_EWFD), the explicit
+update and the implicit ARS111 stage; nothing crosses the ABI but the call.
+"""
+soil_step!(b::B200Soil, dt; max_iters = 3) =
+    check(ccall((:clb_soil_step, libclb), Cint, (Ptr{Cvoid}, Float64, Int32), b.h.ptr, Float64(dt), Int32(max_iters)))
 
 """
 The implicit stage of SoilCO2Model (src/standalone/Soil/Biogeochemistry/Biogeochemistry.jl:320-413, 1119-1195)

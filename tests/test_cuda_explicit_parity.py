@@ -278,3 +278,57 @@ def test_explicit_rows_respect_the_land_sea_mask():
     assert_close(out[active], C, TOL, "CO2 after the stage")
     assert np.all(np.delete(out, active, axis=0) == sentinel)
     s.close()
+
+
+# ---- the atmosphere-driven top boundary, SurfaceRunoff, EnergyWaterFreeDrainage (second half) ----
+def _atmos_forcing(ncol, seed):
+    rng = np.random.default_rng(seed)
+    return dict(precip=-rng.uniform(0, 2e-6, ncol), vapor_flux_liq=rng.normal(0, 1e-8, ncol), lhf=rng.normal(0, 50, ncol),
+                shf=rng.normal(0, 30, ncol), r_n=rng.normal(-100, 50, ncol), t_air=rng.uniform(260, 300, ncol))
+
+
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["fast", "libm"])
+@pytest.mark.parametrize("runoff_model", [0, 1, 2], ids=["norunoff", "surface", "topmodel"])
+def test_atmos_driven_top_fluxes(runoff_model, math_mode):
+    """clb_update_atmos_driven_fluxes against the oracle's soil_boundary_fluxes!(::AtmosDrivenFluxBC, ...)
+    (boundary_conditions.jl:901-936, Runoff.jl:69-71, 129-148, 234-283)"""
+    ncol = 777
+    cl, w, P, Xp, Y, a, s = _setup(ncol, 15, 21, 0, math_mode, 0)
+    F = _atmos_forcing(ncol, 5)
+    sat_cols = np.arange(0, ncol, 5)  # a saturated surface in a fifth of the columns: everything runs off there
+    Y.theta_l[sat_cols, -1] = (w["nu"] - Y.theta_i)[sat_cols, -1] + 1e-3
+    P.update_aux(Xp, Y, a)
+    s.set("y_theta_l", Y.theta_l)
+    for k, v in F.items():
+        s.set(k, v)
+    f_max = np.random.default_rng(1).uniform(0.2, 0.6, ncol)
+    s.set("f_max", f_max)
+    s.set_runoff_params(f_over=3.28, R_sb=1.484e-7, depth=50.0)
+    s.update_aux()
+    s.update_atmos_driven_fluxes(runoff_model)
+    if runoff_model == 2:
+        R = P.update_runoff(Y, F["precip"], f_max, 3.28, 1.484e-7, 50.0, X=Xp, a=a)
+        inf, sat, R_s = R.infiltration, R.is_saturated, R.R_s
+    else:
+        sat, inf, R_s = P.surface_runoff(Y, runoff_model, F["precip"], X=Xp, a=a)
+    tw, th = P.atmos_driven_top_fluxes(inf, F["vapor_flux_liq"], F["lhf"], F["shf"], F["r_n"], F["t_air"])
+    assert_close(s.get("infiltration"), inf, TOL, "infiltration")
+    assert_close(s.get("top_bc_w"), tw, TOL, "top_bc.water")
+    assert_close(s.get("top_bc_h"), th, TOL, "top_bc.heat")
+    if runoff_model > 0:
+        assert_close(s.get("is_saturated"), sat, TOL, "is_saturated")
+        assert_close(s.get("r_s"), R_s, TOL, "R_s")
+    if runoff_model == 1:
+        assert np.all(s.get("infiltration")[sat_cols] == 0.0)
+    s.close()
+
+
+@pytest.mark.parametrize("math_mode", [0, 1], ids=["fast", "libm"])
+def test_energy_water_free_drainage(math_mode):
+    cl, w, P, Xp, Y, a, s = _setup(500, 15, 22, 0, math_mode, 0)
+    s.update_aux()
+    s.update_energy_water_free_drainage()
+    bw, bh = P.energy_water_free_drainage(a)
+    assert_close(s.get("bot_bc_w"), bw, TOL, "bottom_bc.water")
+    assert_close(s.get("bot_bc_h"), bh, TOL, "bottom_bc.heat")
+    s.close()

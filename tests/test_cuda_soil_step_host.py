@@ -153,3 +153,51 @@ def test_resident_soil_step_matches_oracle(form):
         assert_close(s.get("h_grad"), P.f["h_grad"], tol, "h_grad")
         assert_close(s.get("is_saturated"), P.f["is_saturated"], tol, "is_saturated")
     s.close()
+
+
+@pytest.mark.parametrize("runoff_model", [0, 1, 2], ids=["norunoff", "surface", "topmodel"])
+def test_resident_soil_step_atmos_driven(runoff_model):
+    """clb_soil_step with the boundary fluxes of the explicit stage on the device: AtmosDrivenFluxBC top (runoff model +
+    assembly from the host's turbulent fluxes / net radiation) and EnergyWaterFreeDrainage bottom; the oracle runs
+    update_aux!, the runoff, soil_boundary_fluxes! for both boundaries, PhaseChange, the explicit update, the stage."""
+    from test_cuda_explicit_parity import _atmos_forcing
+    dt, iters, ncol = 900.0, 3, 3001
+    w, xp, forcing = _problem(ncol, 13)
+    w["topmodel"] = runoff_model == 2  # the implicit TOPMODELSubsurfaceRunoff source exists with TOPMODELRunoff only
+    if runoff_model != 2:
+        for k in ("is_saturated", "r_ss", "r_ess", "h_grad"):
+            w[k] = np.zeros_like(w[k])
+    F = _atmos_forcing(ncol, 3)
+    P, U, p = oracle_problem(w, nthreads=os.cpu_count() or 1)
+    X = P.explicit_params(**xp)
+    s = _cuda(w, xp, forcing, options={"runoff_model": runoff_model, "top_atmos_driven": 1, "bottom_ewfd": 1})
+    for k, v in F.items():
+        s.set(k, v)
+    for step in range(2):
+        a = P.new_aux()
+        P.update_aux(X, U, a)
+        dl, di = np.zeros_like(U.theta_l), np.zeros_like(U.theta_l)
+        P.phase_change(X, U, a, dl, di)
+        if runoff_model == 2:
+            R = P.update_runoff(U, F["precip"], forcing["f_max"], RUNOFF["f_over"], RUNOFF["R_sb"], RUNOFF["depth"], X=X, a=a)
+            inf = R.infiltration
+            for name, v in (("is_saturated", R.is_saturated), ("R_ss", R.R_ss), ("R_ess", R.R_ess), ("h_grad", R.h_grad)):
+                P.set(name, v)
+        else:
+            _, inf, _ = P.surface_runoff(U, runoff_model, F["precip"], X=X, a=a)
+        p.top_bc_w[...], p.top_bc_h[...] = P.atmos_driven_top_fluxes(inf, F["vapor_flux_liq"], F["lhf"], F["shf"], F["r_n"], F["t_air"])
+        p.bot_bc_w[...], p.bot_bc_h[...] = P.energy_water_free_drainage(a)
+        for name, v in (("K_lag", a.K), ("kappa_lag", a.kappa), ("theta_l_lag", a.theta_l)):
+            P.set(name, v)
+        U.theta_l += dt * dl
+        U.theta_i += dt * di
+        P.implicit_step(U, dt, iters, p=p)
+        s.soil_step(dt, iters)
+        tol = 1e-12 if step == 0 else 1e-11
+        assert_close(s.get("top_bc_w"), p.top_bc_w, tol, "top_bc.water")
+        assert_close(s.get("top_bc_h"), p.top_bc_h, tol, "top_bc.heat")
+        assert_close(s.get("bot_bc_h"), p.bot_bc_h, tol, "bottom_bc.heat")
+        assert_close(s.get("y_theta_l"), U.theta_l, tol, "theta_l")
+        assert_close(s.get("y_rho_e_int"), U.rho_e_int, tol, "rho_e_int")
+        assert_close(s.get("y_intf_e"), U.intF_e, tol, "intF_e")
+    s.close()
