@@ -109,6 +109,7 @@ def lib():
         "clb_soil_step_host": [h, d, i32, C.POINTER(i32), C.POINTER(C.c_void_p), i32,
                                C.POINTER(i32), C.POINTER(C.c_void_p), i32],
         "clb_soil_step": [h, d, i32],
+        "clb_ldiv_all": [h, C.c_uint32],
         "clb_update_atmos_driven_fluxes": [h, i32],
         "clb_update_energy_water_free_drainage": [h],
         "clb_column_integral": [h, i32, i32],

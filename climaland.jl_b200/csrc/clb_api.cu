@@ -1463,6 +1463,47 @@ int clb_ldiv(clb_handle h)
     return CLB_OK;
 }
 
+int clb_ldiv_all(clb_handle h, uint32_t blocks)
+{
+    TRY(check_handle(h));
+    if (blocks == 0 || (blocks & ~7u)) return fail(CLB_ERR_INVALID, "clb_ldiv_all: blocks must be a non-empty CLB_LDIV_* mask");
+    DeviceGuard guard(h->cfg.device);
+    if (blocks & CLB_LDIV_SOIL) {
+        TRY(require(h, {CLB_F_W11_LO, CLB_F_W11_DI, CLB_F_W11_UP, CLB_F_B_THETA_L}, "ldiv_all"));
+        TRY(alloc_fields(h, {CLB_F_X_THETA_L, CLB_F_X_INTF_W}));
+        TRY(ensure_field(h, CLB_F_B_INTF_W));
+        if (h->cfg.model == CLB_ENERGY_HYDROLOGY) {
+            TRY(require(h, {CLB_F_W21_LO, CLB_F_W21_DI, CLB_F_W21_UP, CLB_F_W22_LO, CLB_F_W22_DI, CLB_F_W22_UP, CLB_F_B_RHO_E_INT}, "ldiv_all"));
+            TRY(alloc_fields(h, {CLB_F_X_RHO_E_INT, CLB_F_X_THETA_I, CLB_F_X_INTF_E}));
+            TRY(ensure_field(h, CLB_F_B_THETA_I));
+            TRY(ensure_field(h, CLB_F_B_INTF_E));
+        }
+    }
+    if (blocks & CLB_LDIV_SOILCO2) {
+        TRY(require(h, {CLB_F_CO2_W_LO, CLB_F_CO2_W_DI, CLB_F_CO2_W_UP, CLB_F_O2_W_LO, CLB_F_O2_W_DI, CLB_F_O2_W_UP, CLB_F_CO2_B, CLB_F_O2_B},
+                    "ldiv_all (clb_soilco2_compute_jacobian and the right-hand sides first)"));
+        TRY(alloc_fields(h, {CLB_F_CO2_X, CLB_F_O2_X}));
+    }
+    if (blocks & CLB_LDIV_SURFACE) {
+        TRY(require(h, {CLB_F_SFC_W_DI, CLB_F_SFC_B}, "ldiv_all"));
+        TRY(alloc_fields(h, {CLB_F_SFC_X}));
+    }
+    TRY(ensure_work(h, 4));
+    const clb::DevView P = make_view(h);
+    double *const *F = h->field;
+    clb::LdivAllView A = {};
+    A.blocks = blocks;
+    A.co2_lo[0] = F[CLB_F_CO2_W_LO]; A.co2_di[0] = F[CLB_F_CO2_W_DI]; A.co2_up[0] = F[CLB_F_CO2_W_UP];
+    A.co2_lo[1] = F[CLB_F_O2_W_LO]; A.co2_di[1] = F[CLB_F_O2_W_DI]; A.co2_up[1] = F[CLB_F_O2_W_UP];
+    A.co2_b[0] = F[CLB_F_CO2_B]; A.co2_b[1] = F[CLB_F_O2_B]; A.co2_x[0] = F[CLB_F_CO2_X]; A.co2_x[1] = F[CLB_F_O2_X];
+    A.sfc_w = F[CLB_F_SFC_W_DI]; A.sfc_b = F[CLB_F_SFC_B]; A.sfc_x = F[CLB_F_SFC_X];
+    nvtxRangePushA("ldiv! (all blocks)");
+    clb::k_ldiv_all<<<dim3(grid_for(P.ncol), 4), kBlock, 0, h->stream>>>(P, A);
+    nvtxRangePop();
+    CUDA_TRY(cudaGetLastError());
+    return CLB_OK;
+}
+
 int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double tol, clb_stats *stats)
 {
     TRY(check_handle(h));

@@ -303,6 +303,55 @@ __global__ void __launch_bounds__(128) k_ldiv(const DevView P)
     }
 }
 
+// ldiv! of an integrated model's block-diagonal FieldMatrix in one launch (implicit_timestepping.jl:63-172): blockIdx.y =
+// 0 the soil blocks (k_ldiv), 1 / 2 the (CO2, CO2) / (O2, O2) tridiagonals, 3 the DiagonalMatrixRow block of one
+// surface variable; `blocks` = CLB_LDIV_* mask of what is present.
+struct LdivAllView {
+    const double *co2_lo[2], *co2_di[2], *co2_up[2], *co2_b[2];
+    double *co2_x[2];
+    const double *sfc_w, *sfc_b;
+    double *sfc_x;
+    unsigned blocks;
+};
+__global__ void __launch_bounds__(128) k_ldiv_all(const DevView P, const LdivAllView A)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.ncol) return;
+    const int N = P.N, part = blockIdx.y;
+    const int64_t ld = P.sl, o = P.at(0, c);
+    if (part == 0) {
+        if (!(A.blocks & 1u)) return;
+        double *cp = P.work[0] + o;
+        thomas_column(N, ld, P.w11_lo + o, P.w11_di + o, P.w11_up + o, P.b_theta_l + o, P.x_theta_l + o, cp);
+        P.x_intF_w[c] = -P.b_intF_w[c];
+        if (P.model == 1) {
+            double *b2 = P.work[1] + o;
+            const double *x1 = P.x_theta_l + o;
+            for (int i = 0; i < N; ++i) {
+                const int64_t k = (int64_t)i * ld;
+                double s = P.w21_di[k + o] * x1[k];
+                if (i > 0) s = P.w21_lo[k + o] * x1[k - ld] + s;
+                if (i < N - 1) s = s + P.w21_up[k + o] * x1[k + ld];
+                b2[k] = P.b_rho_e[k + o] - s;
+            }
+            thomas_column(N, ld, P.w22_lo + o, P.w22_di + o, P.w22_up + o, b2, P.x_rho_e + o, cp);
+            for (int i = 0; i < N; ++i) {
+                const int64_t k = P.at(i, c);
+                P.x_theta_i[k] = -P.b_theta_i[k];
+            }
+            P.x_intF_e[c] = -P.b_intF_e[c];
+        }
+    } else if (part <= 2) {
+        if (!(A.blocks & 2u)) return;
+        const int sp = part - 1;
+        thomas_column(N, ld, A.co2_lo[sp] + o, A.co2_di[sp] + o, A.co2_up[sp] + o, A.co2_b[sp] + o, A.co2_x[sp] + o,
+                      P.work[2 + sp] + o);
+    } else {
+        if (!(A.blocks & 4u)) return;
+        A.sfc_x[c] = A.sfc_b[c] / A.sfc_w[c];
+    }
+}
+
 // out[c] = sum_i field[i,c]*dz_c[i]   (column_integral_definite!, rre.jl:502-511)
 __global__ void __launch_bounds__(128) k_column_integral(const DevView P, const double *field, double *out)
 {

@@ -260,6 +260,11 @@ class SoilColumnSolver:
         """soil_boundary_fluxes!(::EnergyWaterFreeDrainage, ::BottomBoundary, ...)"""
         check(self.L.clb_update_energy_water_free_drainage(self.h))
 
+    def ldiv_all(self, soil=True, soilco2=False, surface=False):
+        """ldiv! of an integrated model's FieldMatrixWithSolver in one launch (clb_ldiv_all): the soil blocks, the SoilCO2
+        tridiagonals and the DiagonalMatrixRow block of one surface variable, whichever are present"""
+        check(self.L.clb_ldiv_all(self.h, (1 if soil else 0) | (2 if soilco2 else 0) | (4 if surface else 0)))
+
     def soil_step(self, dt, max_iters=3):
         """A whole EnergyHydrology soil step on resident state (clb_soil_step): explicit cells, the per-column sweep
         (runoff, column integrals, explicit update), the fused implicit stage -- three launches, no host transfer."""

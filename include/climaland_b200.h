@@ -157,6 +157,7 @@ typedef enum {
     CLB_F_CO2_DY, CLB_F_O2_DY,               /* implicit tendency */
     CLB_F_CO2_W_LO, CLB_F_CO2_W_DI, CLB_F_CO2_W_UP,   /* (CO2, CO2) Jacobian rows */
     CLB_F_O2_W_LO, CLB_F_O2_W_DI, CLB_F_O2_W_UP,      /* (O2, O2) Jacobian rows  */
+    CLB_F_CO2_B, CLB_F_O2_B, CLB_F_CO2_X, CLB_F_O2_X, /* right-hand side / solution of the (CO2, CO2), (O2, O2) blocks */
     CLB_F_NUM_CELL,
     /* ---- per-column fields */
     CLB_F_R_SS = CLB_F_NUM_CELL, CLB_F_R_ESS, CLB_F_H_GRAD,     /* lagged TOPMODEL */
@@ -350,6 +351,19 @@ int clb_soilco2_implicit_step(clb_handle h, double dtgamma, int32_t max_iters);
  * clb_soilco2_* for CO2 / O2, this for each surface variable (fields CLB_F_SFC_* or any three field ids of
  * one kind). */
 int clb_ldiv_diagonal(clb_handle h, int32_t w_field, int32_t b_field, int32_t x_field);
+
+/* `ldiv!(x, W, b)` of an INTEGRATED model's FieldMatrixWithSolver (implicit_timestepping.jl:63-172: the blocks
+ * initialize_jacobian builds for the variables present in Y) as ONE launch.  `blocks` says which are present:
+ *   CLB_LDIV_SOIL     (theta_l, theta_l) [+ (rho_e_int, theta_l), (rho_e_int, rho_e_int), BlockLowerTriangularSolve] and the
+ *                     -I blocks of theta_i and the flux integrals: what clb_ldiv solves (fields CLB_F_W11_* .. _X_*)
+ *   CLB_LDIV_SOILCO2  the TridiagonalMatrixRow blocks (soilco2.CO2, soilco2.CO2), (soilco2.O2, soilco2.O2)
+ *                     (CLB_F_CO2_W_*, CLB_F_O2_W_* from clb_soilco2_compute_jacobian; CLB_F_CO2_B / _O2_B -> CLB_F_CO2_X / _O2_X)
+ *   CLB_LDIV_SURFACE  the DiagonalMatrixRow block of one surface variable, canopy.energy.T (canopy_energy.jl:222-250):
+ *                     CLB_F_SFC_X = CLB_F_SFC_B / CLB_F_SFC_W_DI
+ * The blocks are independent of each other (BlockDiagonalSolve between models), so the grid's y index runs over them.
+ * The remaining explicit variables (-I blocks: x = -b) are a broadcast the caller keeps. */
+enum { CLB_LDIV_SOIL = 1, CLB_LDIV_SOILCO2 = 2, CLB_LDIV_SURFACE = 4 };
+int clb_ldiv_all(clb_handle h, uint32_t blocks);
 
 /* ---- the fused implicit stage -------------------------------------------- */
 /* One implicit ARS111 stage on the resident state Y (in: U = temp, out: new U):

@@ -54,6 +54,7 @@ const CLB_HOST, CLB_DEVICE = Int32(0), Int32(1)
     F_P_TF_DEPRESSED; F_DYE_THETA_L; F_DYE_THETA_I
     F_CO2_Y; F_O2_Y; F_CO2_D; F_O2_D; F_CO2_THETA_EFF; F_O2_THETA_EFF; F_CO2_DY; F_O2_DY
     F_CO2_W_LO; F_CO2_W_DI; F_CO2_W_UP; F_O2_W_LO; F_O2_W_DI; F_O2_W_UP
+    F_CO2_B; F_O2_B; F_CO2_X; F_O2_X
     F_R_SS; F_R_ESS; F_H_GRAD; F_THETA_BC_TOP; F_THETA_BC_BOT
     F_TOP_BC_W; F_BOT_BC_W; F_TOP_BC_H; F_BOT_BC_H; F_DFLUXBCDY; F_TOTAL_WATER
     F_Y_INTF_W; F_Y_INTF_E; F_DY_INTF_W; F_DY_INTF_E; F_B_INTF_W; F_B_INTF_E; F_X_INTF_W; F_X_INTF_E
@@ -555,6 +556,45 @@ function ldiv_diagonal!(x::Fields.Field, w::Fields.Field, rhs::Fields.Field, b::
     check(ccall((:clb_ldiv_diagonal, libclb), Cint, (Ptr{Cvoid}, Int32, Int32, Int32), b.h.ptr,
         Int32(F_SFC_W_DI), Int32(F_SFC_B), Int32(F_SFC_X)))
     get_field!(x, b.h, F_SFC_X)
+    return x
+end
+
+"""
+    ldiv_all!(x, rhs, b; canopy_T_block = nothing)
+
+`ldiv!(x, W, rhs)` of an integrated model's FieldMatrixWithSolver (src/shared_utilities/implicit_timestepping.jl:63-172)
+as ONE launch (clb_ldiv_all): the soil blocks (BlockLowerTriangularSolve(soil.ϑ_l) for EnergyHydrology), the
+(soilco2.CO2, soilco2.CO2) / (soilco2.O2, soilco2.O2) tridiagonals when `Y` has a `soilco2` component, and the
+DiagonalMatrixRow block of `canopy.energy.T` (∂Tres∂T from canopy_energy.jl:222-250, passed as `canopy_T_block`).
+The Jacobian rows are the ones clb_compute_jacobian / clb_soilco2_compute_jacobian left in the mirrors.  The other
+explicit variables keep the reference's `x = -rhs` broadcast.
+"""
+function ldiv_all!(x::Fields.FieldVector, rhs::Fields.FieldVector, b::B200Soil; canopy_T_block = nothing)
+    mask = UInt32(1)
+    set_field!(b.h, F_B_THETA_L, rhs.soil.ϑ_l); set_field!(b.h, F_B_INTF_W, rhs.soil.∫F_vol_liq_water_dt)
+    if b.energy
+        set_field!(b.h, F_B_RHO_E_INT, rhs.soil.ρe_int); set_field!(b.h, F_B_THETA_I, rhs.soil.θ_i)
+        set_field!(b.h, F_B_INTF_E, rhs.soil.∫F_e_dt)
+    end
+    if hasproperty(rhs, :soilco2)
+        mask |= UInt32(2)
+        set_field!(b.h, F_CO2_B, rhs.soilco2.CO2); set_field!(b.h, F_O2_B, rhs.soilco2.O2)
+    end
+    if !isnothing(canopy_T_block)
+        mask |= UInt32(4)
+        set_field!(b.h, F_SFC_W_DI, canopy_T_block); set_field!(b.h, F_SFC_B, rhs.canopy.energy.T)
+    end
+    check(ccall((:clb_ldiv_all, libclb), Cint, (Ptr{Cvoid}, UInt32), b.h.ptr, mask))
+    get_field!(x.soil.ϑ_l, b.h, F_X_THETA_L); get_field!(x.soil.∫F_vol_liq_water_dt, b.h, F_X_INTF_W)
+    if b.energy
+        get_field!(x.soil.ρe_int, b.h, F_X_RHO_E_INT); get_field!(x.soil.θ_i, b.h, F_X_THETA_I)
+        get_field!(x.soil.∫F_e_dt, b.h, F_X_INTF_E)
+    end
+    if hasproperty(rhs, :soilco2)
+        get_field!(x.soilco2.CO2, b.h, F_CO2_X); get_field!(x.soilco2.O2, b.h, F_O2_X)
+        x.soilco2.SOC .= .-rhs.soilco2.SOC
+    end
+    isnothing(canopy_T_block) || get_field!(x.canopy.energy.T, b.h, F_SFC_X)
     return x
 end
 

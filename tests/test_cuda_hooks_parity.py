@@ -158,3 +158,74 @@ def test_diagonal_block_solve_and_resident_vector_ops():
     with pytest.raises(cl.ClbError):
         s.ldiv_diagonal("sfc_w_di", "y_theta_l", "sfc_x")   # mixed kinds
     s.close()
+
+
+@pytest.mark.parametrize("layout", [1, 2], ids=["colfast", "levfast"])
+def test_ldiv_all_blocks_of_an_integrated_model(layout):
+    """clb_ldiv_all: the ldiv! of an integrated model's FieldMatrixWithSolver (implicit_timestepping.jl:63-172) in one
+    launch -- EnergyHydrology's blocks (BlockLowerTriangularSolve(theta_l)) against the oracle's ldiv, the SoilCO2
+    tridiagonals against scipy's banded solver on the rows clb_soilco2_compute_jacobian left in the mirrors, the canopy
+    temperature's DiagonalMatrixRow block against b / w; and block by block equal to the separate entry points."""
+    from scipy.linalg import solve_banded
+    ncol, N, dtg = 513, 15, 900.0
+    w = _workload("energy_hydrology", ncol, N, seed=19, topmodel=True)
+    rng = np.random.default_rng(3)
+    P, Y, p = oracle_problem(w)
+    s = cuda_solver(w, layout=layout)
+    P.update_implicit_cache(Y, p)
+    W = P.new_jacobian()
+    P.compute_jacobian(W, Y, p, dtg)
+    s.update_implicit_cache()
+    s.compute_jacobian(dtg)
+    b = P.new_state()
+    b.theta_l[...] = rng.normal(0, 1e-3, b.theta_l.shape)
+    b.rho_e_int[...] = rng.normal(0, 1e4, b.theta_l.shape)
+    b.theta_i[...] = rng.normal(0, 1e-3, b.theta_l.shape)
+    b.intF_w[...], b.intF_e[...] = rng.normal(0, 1.0, ncol), rng.normal(0, 1.0, ncol)
+    for k, v in (("b_theta_l", b.theta_l), ("b_rho_e_int", b.rho_e_int), ("b_theta_i", b.theta_i), ("b_intf_w", b.intF_w),
+                 ("b_intf_e", b.intF_e)):
+        s.set(k, v)
+    # SoilCO2 blocks
+    rhs = {}
+    for name in ("co2", "o2"):
+        s.set(f"{name}_y", rng.uniform(5e-5, 2e-3, (ncol, N)))
+        s.set(f"{name}_d", rng.uniform(1e-8, 2e-6, (ncol, N)))
+        s.set(f"{name}_theta_eff", rng.uniform(0.02, 0.45, (ncol, N)))
+        s.set(f"{name}_bot_bc", np.zeros(ncol))
+        s.set(f"{name}_top_bc", np.zeros(ncol))
+        rhs[name] = rng.normal(0, 1e-4, (ncol, N))
+        s.set(f"{name}_b", rhs[name])
+    s.set_co2_top_state(co2=False, o2=False)
+    s.soilco2_compute_jacobian(dtg)
+    # canopy temperature block
+    wd = dtg * (-rng.uniform(6.0, 80.0, ncol)) / (2e3 * np.maximum(rng.uniform(0, 6, ncol), 1e-16)) - 1.0
+    bs = rng.normal(0, 1.0, ncol)
+    s.set("sfc_w_di", wd)
+    s.set("sfc_b", bs)
+    s.ldiv_all(soil=True, soilco2=True, surface=True)
+    x = P.new_state()
+    P.ldiv(x, W, b)
+    assert_close(s.get("x_theta_l"), x.theta_l, TOL, "x.theta_l")
+    assert_close(s.get("x_rho_e_int"), x.rho_e_int, TOL, "x.rho_e_int")
+    assert_close(s.get("x_theta_i"), x.theta_i, TOL, "x.theta_i")
+    assert_close(s.get("x_intf_w"), x.intF_w, TOL, "x.intF_w")
+    assert_close(s.get("x_intf_e"), x.intF_e, TOL, "x.intF_e")
+    for name in ("co2", "o2"):
+        lo, di, up = s.get(f"{name}_w_lo"), s.get(f"{name}_w_di"), s.get(f"{name}_w_up")
+        got = s.get(f"{name}_x")
+        for c in range(0, ncol, 37):
+            ab = np.zeros((3, N))
+            ab[0, 1:], ab[1], ab[2, :-1] = up[c, :-1], di[c], lo[c, 1:]
+            assert_close(got[c], solve_banded((1, 1), ab, rhs[name][c]), 1e-11, f"x.{name}")
+    assert np.array_equal(s.get("sfc_x"), bs / wd)
+    # the separate entry points give the same bits
+    xs = {k: s.get(k) for k in ("x_theta_l", "x_rho_e_int", "sfc_x")}
+    s.ldiv()
+    s.ldiv_diagonal("sfc_w_di", "sfc_b", "sfc_x")
+    for k, v in xs.items():
+        assert np.array_equal(s.get(k), v), k
+    import climaland_b200 as cl
+    with pytest.raises(cl.ClbError):
+        s.L.clb_ldiv_all  # noqa: B018 (exists)
+        s.ldiv_all(soil=False, soilco2=False, surface=False)
+    s.close()
