@@ -555,12 +555,12 @@ int make_pair_maps(clb_handle h, const clb::DevView &P, int box_columns, int box
 //   octet, N = 50     8 lanes x 7 cells (56 level rows); persistent, single-buffered tiles of 4 columns (1.75 KB per
 //                     slot) with an L2 prefetch of the next tile; 8 (Richards) or 6 (EnergyHydrology) warps per SM
 template <int CLOSURE, int MODEL, int N, int PARTS, int Q, int NS, int NBUF, int BLOCK, int MINB, bool PERSISTENT,
-          bool LF = false>
+          bool LF = false, bool BCL = false>
 int launch_lanes(clb_handle h, const clb::DevView &P, double dtg, int max_iters, int64_t col0)
 {
     using Gm = clb::LaneGeom<PARTS, Q>;
     constexpr int CPW = Gm::CPW;
-    auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB, Q, LF>;
+    auto kern = clb::k_step_lanes<CLOSURE, MODEL, N, PARTS, NS, NBUF, BLOCK, MINB, Q, LF, BCL>;
     const size_t smem = clb::pair_smem_bytes<PARTS, NS, NBUF, BLOCK, Q, LF>();
     // Function attributes are per DEVICE (and per instantiation): one flag per device ordinal, so that a process
     // holding handles on several GPUs opts every one of them in to the > 48 KB of dynamic shared memory.
@@ -622,8 +622,15 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, 
 #ifndef CLB_QUAD_BLOCK
 #define CLB_QUAD_BLOCK 256  // 8 warps per SM; 128 = one warp per sub-partition (latency experiment)
 #endif
+    {
+        // RichardsModel with a MoistureStateBC top: the boundary fluxes follow the iterate (BCL instantiation)
+        if constexpr (MODEL == 0) {
+            if (h->cfg.top_bc == CLB_TOP_MOISTURE_STATE)
+                return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, CLB_QUAD_NBUF, CLB_QUAD_BLOCK_R, 1, true, false, true>(h, P, dtg, max_iters, col0);
+        }
         return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, CLB_QUAD_NBUF, (MODEL == 0) ? CLB_QUAD_BLOCK_R : CLB_QUAD_BLOCK, 1, true>(h, P, dtg, max_iters,
                                                                                                                 col0);
+    }
     else
         return launch_lanes<CLOSURE, MODEL, N, 2, 4, NS, 1, 128, CLB_QUAD_MINB, false>(h, P, dtg, max_iters, col0);
 }
@@ -694,8 +701,11 @@ bool pair_variant_applies(clb_handle h, bool octet = false)
     // octet: N = 15 / 16 / 50 as template instantiations, 17 .. 48 with the level count at run time
     if (N != 15 && N != 16 && !(octet && (N == 50 || (N >= 17 && N <= 48)))) return false;
     if (h->cfg.math_mode != CLB_MATH_FAST) return false;
-    // a MoistureStateBC top re-evaluates the boundary fluxes every iteration (rre.jl:460-468): lane-per-cell kernel
-    if (h->cfg.model == CLB_RICHARDS && h->cfg.top_bc == 1) return false;
+    // a MoistureStateBC top re-evaluates the boundary fluxes every iteration (rre.jl:460-468): the pipelined quad has an
+    // instantiation for it (BCL); the octets do not, nor does the plain quad: lane-per-cell kernel
+    if (h->cfg.model == CLB_RICHARDS && h->cfg.top_bc == 1 &&
+        (octet || h->cfg.kernel_variant == CLB_VARIANT_LANE_QUAD || h->cfg.kernel_variant == CLB_VARIANT_LANE_OCTET))
+        return false;
     // the TMA boxes of the N = 15 / 16 kernels are cut from column-fastest mirrors; the N = 50 octet also reads
     // level-fastest ones (a tile is then one contiguous piece of each field)
     if (h->cfg.layout == CLB_LAYOUT_LEVEL_FASTEST && !(octet && N == 50)) return false;
@@ -891,11 +901,13 @@ int clb_create(clb_handle *out, const clb_config *cfg)
     int layout = cfg->layout;
     // lane-per-cell kernels read level-fastest mirrors, every column-per-thread(-pair) kernel column-fastest ones
     if (layout == CLB_LAYOUT_AUTO) {
+        // (a MoistureStateBC top of RichardsModel: the pipelined quad only, see pair_variant_applies)
+        const bool live_bc = cfg->model == CLB_RICHARDS && cfg->top_bc == 1;
         const bool quad_ok = (cfg->n_levels == 15 || cfg->n_levels == 16) && cfg->math_mode == CLB_MATH_FAST &&
-                             !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
-                             (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_QUAD ||
-                              cfg->kernel_variant == CLB_VARIANT_LANE_QUAD_PIPELINED ||
-                              cfg->kernel_variant == CLB_VARIANT_LANE_OCTET);
+                             (live_bc ? (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_QUAD_PIPELINED)
+                                      : (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_QUAD ||
+                                         cfg->kernel_variant == CLB_VARIANT_LANE_QUAD_PIPELINED ||
+                                         cfg->kernel_variant == CLB_VARIANT_LANE_OCTET));
         const bool lane_per_cell = cfg->n_levels <= 31 && (cfg->kernel_variant == CLB_VARIANT_AUTO ||
                                                            cfg->kernel_variant == CLB_VARIANT_LANE_PER_CELL);
         // the N = 50 octet reads either layout; level-fastest (the reference's own) keeps a tile's 50 rows of a field
@@ -1538,8 +1550,8 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the register-column variant is built for N == 15");
     if ((variant == CLB_VARIANT_LANE_QUAD || variant == CLB_VARIANT_LANE_QUAD_PIPELINED) && !pair_variant_applies(h))
         return fail(CLB_ERR_INVALID,
-                    "clb_implicit_step: the lane-quad variants need N = 15 or 16, CLB_MATH_FAST, column-fastest mirrors and flux "
-                    "boundary conditions");
+                    "clb_implicit_step: the lane-quad variants need N = 15 or 16, CLB_MATH_FAST and column-fastest mirrors (a "
+                    "MoistureStateBC top of RichardsModel: the pipelined quad only)");
     if (variant == CLB_VARIANT_LANE_OCTET && !pair_variant_applies(h, true))
         return fail(CLB_ERR_INVALID,
                     "clb_implicit_step: the lane-octet variant needs 15 <= N <= 48 on column-fastest mirrors or N = 50, CLB_MATH_FAST and "

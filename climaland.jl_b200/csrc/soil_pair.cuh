@@ -340,8 +340,13 @@ __device__ unsigned long long g_phase_clk[16];
 #else
 #define CLB_PCS(k)
 #endif
+// BCL (RichardsModel only): the cache holds dfluxBCdY, i.e. the top boundary is a MoistureStateBC (rre.jl:460-468): the
+// boundary fluxes follow the iterate -- top: -K_N ((psi_bc + dz_top) - psi_N) / dz_top with dfluxBCdY = K_N dpsi_N / dz_top
+// on the top cell's diagonal (boundary_conditions.jl:227-267, 375-411, rre.jl:434-449); bottom: FreeDrainage -K_1, a
+// MoistureStateBC, or the lagged flux value -- the flux integral's Newton recurrence runs with them iteration by
+// iteration, and the last evaluation is left in p.soil.top_bc / bottom_bc.
 template <int CLOSURE, int MODEL, int NT, int PARTS, int NS, int NBUF, int BLOCK, int MINB, int QC = kPairQ / PARTS,
-          bool LF = false>
+          bool LF = false, bool BCL = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
     k_step_lanes(const DevView P, const PairGridT<PARTS * QC> G, const __grid_constant__ PairMaps M, double dtg,
                  int max_iters)
@@ -500,8 +505,9 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     // flux integrals (W = -I, lagged boundary fluxes): their Newton recurrence does not depend on
     // the iterate, so it runs here, off the hot loop (one lane per column stores it); placed after the wait so that
     // its dependent chain interleaves with the set-up below
+    static_assert(!BCL || MODEL == 0, "only a RichardsModel cache holds dfluxBCdY");
     double dx2_int = 0.0;
-    {
+    if (!BCL) {
         // The recurrence U <- U - (-(t + dtg T - U)) started at U = t, written out: U_1 = t + ((t + dtg T) - t), and
         // from the second iteration on U = a := t + dtg T exactly (a - U_1 is exactly representable and U_1 + (a - U_1)
         // = a), with dx = -(a - U_1) in the second iteration and -0 afterwards.  Straight-line code: as a loop with a
@@ -526,6 +532,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     // ---- set-up: transform the raw fields in place into the stage constants ------------------
     double U1[Q], U2[Q];
     double aK8 = 0.0, aC8 = 0.0, r22 = 0.0, c22_last = 0.0;  // inner face of the last cell; seam of W22
+    double psi_bc = 0.0;                                     // BCL: pressure head of this half's boundary value
+    double live_top = top_w, live_bot = bot_w, Uiw = cur.intF_w, dxw_last = 0.0;  // BCL: fluxes at the iterate, flux integral
     // The raw values of ALL of the lane's cells are loaded before the first constant is stored: the stores go to the
     // same slots (the transform is in place), so with loads and stores alternating cell by cell a load may not move
     // above the stores before it and the cells' reciprocal chains run one after the other.  (Phase clocks: set-up
@@ -548,6 +556,24 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         ClosureConst cc[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) cc[q] = pair_prepare<CLOSURE, true>(iSs[q], pa[q], pb[q], pm[q], theta_r[q], nu[q]);
+        if (BCL) {
+            // pressure head of the boundary value with the boundary CELL's parameters (boundary_conditions.jl:240-250): the
+            // top cell is slot qT of the top lane, the bottom cell slot 0 of the bottom half's outer lane
+            const int qb = half ? qT : 0;
+            double th_[1], thr_[1] = {0.0}, nu_[1] = {0.0}, irg_[1] = {0.0}, ca_[1] = {0.0}, ca2_[1] = {0.0}, cb_[1] = {0.0},
+                   cc_[1] = {0.0}, cd_[1] = {0.0}, iss_[1] = {0.0}, ks_[1] = {0.0}, K_[1], psi_[1], dp_[1];
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                if (q == qb) {
+                    thr_[0] = theta_r[q]; nu_[0] = nu[q]; irg_[0] = cc[q].inv_range; ca_[0] = cc[q].ca; ca2_[0] = cc[q].ca2;
+                    cb_[0] = cc[q].cb; cc_[0] = cc[q].cc; cd_[0] = cc[q].cd; iss_[0] = cc[q].inv_Ss; ks_[0] = K_sat[q];
+                }
+            const double tb = half ? P.theta_bc_top[col_clamped(tile_id)]
+                                   : ((P.bottom_bc == 2) ? P.theta_bc_bot[col_clamped(tile_id)] : nu_[0]);
+            th_[0] = tb;
+            fmv::closure<CLOSURE, false, 1, true>(MT, th_, thr_, nu_, irg_, ca_, ca2_, cb_, cc_, cd_, iss_, ks_, K_, psi_, dp_);
+            psi_bc = psi_[0];
+        }
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             U1[q] = theta[q];
@@ -824,13 +850,45 @@ __global__ void __launch_bounds__(BLOCK, MINB)
         // T_imp! and Wfact: face fluxes, residuals and the rows of W11 = dtgamma dT/dtheta - I
         double o1[Q], d1[Q], i1[Q], f1[Q], f2[Q], aE[Q + 1];
         double Fw_o, Fe_o = 0.0, aK_o;
+        double b0_wi = b0_w, bT_wi = bT_w, top_dflux = 0.0;  // boundary terms of this iteration
+        if (BCL) {
+            // update_implicit_boundary_fluxes (rre.jl:460-468): the boundary cell of this half -- slot qT of the top
+            // lane, slot 0 of the bottom half's outer lane
+            const int qb = half ? qT : 0;
+            double Kb = 0.0, psib = 0.0, dpb = 0.0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                if (q == qb) { Kb = Kc[q]; psib = h[q] - G.z[half][r0 + q]; dpb = dps[q]; }
+            if (half) {
+                const double fl = -Kb * ((psi_bc + P.dz_top) - psib) / P.dz_top;
+                if (top_lane) {
+                    live_top = fl;
+                    top_dflux = Kb * dpb / P.dz_top;
+                    if (qT == 0) b0_wi = -fl;
+                    else bT_wi = -fl;
+                }
+            } else if (outermost) {
+                if (P.bottom_bc == 1) live_bot = -1 * Kb;
+                else if (P.bottom_bc == 2) live_bot = -Kb * ((psib + P.dz_bot) - psi_bc) / P.dz_bot;
+                b0_wi = live_bot;
+            }
+            // the flux integral (W = -I) with the fluxes of this iterate, in the lane that stores it (the bottom
+            // half's outer lane, which owns bottom_bc; top_bc comes from the top lane of the column)
+            const double tw_ = __shfl_sync(0xffffffffu, live_top, (lane % CPW) + CPW * (pT * 2 + 1));
+            if (idx == 0) {
+                const double Tiw = -(tw_ - live_bot) - ld_Rss;
+                dxw_last = -(cur.intF_w + dtg * Tiw - Uiw);
+                Uiw -= dxw_last;
+                live_top = tw_;
+            }
+        }
         {
             // outer face of the first cell: the column boundary (zero coefficient, boundary flux)
             // or, for an inner part, the face shared with the previous part
             const double hid_o = G.hidzf[half][r0];
             const double dh0 = h[0] - h_out;
             aK_o = (MODEL == 1) ? S.template get<E_AK>(0) : (Kc[0] + K_out) * hid_o;
-            Fw_o = b0_w - aK_o * dh0;
+            Fw_o = b0_wi - aK_o * dh0;
             aE[0] = 0.0;
             if (MODEL == 1) {
                 aE[0] = (eK[0] + eK_out) * hid_o;
@@ -852,14 +910,15 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 aK_in = (Kc[q] + ((q < Q - 1) ? Kc[q + 1] : K_in)) * hid_in;
             }
             double Fw_in = -(aK_in * dh);
-            if (q + 1 == qT) Fw_in += bT_w;  // bT is zero in every lane but the top cell's
+            if (q + 1 == qT) Fw_in += bT_wi;  // bT is zero in every lane but the top cell's
             double t1;
             if (MODEL == 0) t1 = S.template get<R_T1>(q);
             else t1 = S.template get<E_T1>(q);
             f1[q] = fma(Fw_o - Fw_in, dti, t1) - U1[q];
             o1[q] = (aK_o * ((q == 0) ? dps_out : dps[q - 1])) * dti;
             i1[q] = (aK_in * dpn) * dti;
-            d1[q] = fma(-((aK_in + aK_o) * dps[q]), dti, -1.0);
+            if (BCL) d1[q] = fma(-((aK_in + aK_o) * dps[q] + ((q == qT) ? top_dflux : 0.0)), dti, -1.0);
+            else d1[q] = fma(-((aK_in + aK_o) * dps[q]), dti, -1.0);
             if (MODEL == 1) {
                 const double Tn = (q < Q - 1) ? Td[q + 1] : T_in;
                 const double eKn = (q < Q - 1) ? eK[q + 1] : eK_in;
@@ -980,6 +1039,12 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                 if (MODEL == 1 && !isfinite(U2[q])) bad += 1.0;
             }
         }
+    }
+    if (BCL && idx == 0 && col_ok) {
+        dx2_int = dxw_last * dxw_last;
+        P.out_intF_w[c] = Uiw;
+        P.top_bc_w[c] = live_top;  // the last evaluation stays in the cache, as update_implicit_boundary_fluxes leaves it
+        P.bot_bc_w[c] = live_bot;
     }
     if (col_ok) dx2_acc += dx2 + dx2_int;
     if (NBUF == 2) buf ^= 1;

@@ -40,6 +40,11 @@ CASES = [
     ("energy_hydrology", 1, 0, 0, True, 25, 38, 900.0, 2),
     ("richards", 0, 0, 0, False, 48, 9, 1800.0, 2),
     ("energy_hydrology", 0, 0, 0, True, 41, 21, 900.0, 3),
+    # MoistureStateBC top (boundary fluxes and dfluxBCdY at the iterate): Brooks-Corey, N = 16 (no pad row: the top cell
+    # is slot 0 of its lane), a lagged bottom flux value, one column more than a tile
+    ("richards", 1, 1, 1, False, 15, 90, 1800.0, 3),
+    ("richards", 0, 1, 0, True, 16, 41, 900.0, 2),
+    ("richards", 1, 1, 2, True, 16, 9, 1800.0, 3),
 ]
 
 # (kernel_variant, layout): lane-per-cell on level-fastest mirrors, register-column and generic on
@@ -83,8 +88,10 @@ def test_fused_step_matches_oracle(case, math_mode, variant):
         pytest.skip("lane-per-cell needs N <= 31")
     if variant == "register_column" and N != 15:
         pytest.skip("register-column is built for N = 15")
-    if variant.startswith("lane_quad") and (N not in (15, 16) or math_mode != 0 or (model == "richards" and top_bc == 1)):
-        pytest.skip("lane-quad is built for N = 15 / 16, fast math, flux boundary conditions, column-fastest mirrors")
+    if variant.startswith("lane_quad") and (N not in (15, 16) or math_mode != 0 or
+                                            (model == "richards" and top_bc == 1 and variant != "lane_quad_pipelined")):
+        pytest.skip("lane-quad is built for N = 15 / 16, fast math, column-fastest mirrors; a MoistureStateBC top "
+                    "(boundary fluxes at the iterate): the pipelined quad only")
     if variant.startswith("lane_octet") and (not (N in (15, 16, 50) or 17 <= N <= 48) or math_mode != 0
                                              or (model == "richards" and top_bc == 1)):
         pytest.skip("lane-octet is built for N = 15 .. 48 and 50, fast math, flux boundary conditions")
@@ -98,6 +105,10 @@ def test_fused_step_matches_oracle(case, math_mode, variant):
     assert st["iterations"] == iters and st["nan_count"] == 0
     _compare_state(s, U, model == "energy_hydrology")
     assert abs(st["dx_norm"] - nrm) <= 1e-9 * max(nrm, 1e-300)
+    if model == "richards" and top_bc == 1:
+        # update_implicit_boundary_fluxes (rre.jl:460-468) leaves its last evaluation in p.soil.top_bc / bottom_bc
+        assert_close(s.get("top_bc_w"), p.top_bc_w, 1e-11, "top_bc")
+        assert_close(s.get("bot_bc_w"), p.bot_bc_w, 1e-11, "bot_bc")
     # the step really moved the state
     assert np.max(np.abs(s.get("y_theta_l") - w["y_theta_l"])) > 0
     s.close()
