@@ -22,23 +22,58 @@ def nvcc_path():
     raise RuntimeError("nvcc not found: libclimaland_b200.so cannot be built (there is no CPU fallback)")
 
 
+def source_hash():
+    """sha256 over the sources and the flags: what the built library is a function of"""
+    import hashlib
+    hsh = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in sorted(DEPS):
+        hsh.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            hsh.update(f.read())
+    return hsh.hexdigest()
+
+
+STAMP = OUT + ".srchash"
+
+
 def stale():
+    """True when the library is missing or was built from other sources.  By CONTENT, not by mtime: a checkout or the
+    copy to a GPU box changes file times, and a rebuild there would be 2 minutes of nvcc per process -- or, with one
+    process per GPU, several of them writing the same file."""
     if not os.path.exists(OUT):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(p) > t for p in DEPS)
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
-    """Compile the library if missing or older than its sources; return its path."""
+    """Compile the library if missing or built from other sources; return its path.  Safe with several processes
+    (one per GPU): an exclusive file lock around the check and the build, output written aside and renamed."""
     if not force and not stale():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + ["-ldl"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    import fcntl
+    with open(OUT + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():  # another process built it while this one waited
+                return OUT
+            tmp = OUT + f".tmp{os.getpid()}"
+            cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES + ["-ldl"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+            os.replace(tmp, OUT)
+            with open(STAMP, "w") as f:
+                f.write(source_hash())
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return OUT
 
 
