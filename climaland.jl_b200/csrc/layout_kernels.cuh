@@ -73,8 +73,11 @@ __global__ void __launch_bounds__(256) k_relayout_many(ManyFields f, int64_t dsl
 // layout (level fastest, column stride N) for `ncol_out` columns, the remaining fields are read from it for
 // `ncol_in` columns.  One launch keeps PCIe reads and writes in flight together (two kernels on two streams do not
 // overlap reliably: the reading kernel's blocks fill the machine).  msl / msc: strides of the mirrors.
+// idx_out / idx_in (nullable): handle column -> row of the host arrays for the chunk written / read (land-sea mask
+// compaction: rows of inactive columns are never touched).
 __global__ void __launch_bounds__(256) k_relayout_dual(ManyFields f, int n_out, int64_t msl, int64_t msc, int N,
-                                                       int64_t ncol_out, int64_t ncol_in)
+                                                       int64_t ncol_out, int64_t ncol_in,
+                                                       const int64_t *__restrict__ idx_out, const int64_t *__restrict__ idx_in)
 {
     extern __shared__ double tile[];  // [N][kTileCols + 1]
     // the field is the FAST grid dimension: consecutive blocks alternate between the two directions
@@ -85,24 +88,27 @@ __global__ void __launch_bounds__(256) k_relayout_dual(ManyFields f, int n_out, 
     double *__restrict__ dst = f.dst[blockIdx.x];
     const double *__restrict__ src = f.src[blockIdx.x];
     const int64_t ssl = to_host ? msl : 1, ssc = to_host ? msc : N, dsl = to_host ? 1 : msl, dsc = to_host ? N : msc;
+    const int64_t *__restrict__ sidx = to_host ? nullptr : idx_in, *__restrict__ didx = to_host ? idx_out : nullptr;
     const int ncl = (int)min((int64_t)kTileCols, ncol - c0);
     const bool s_level_fast = ssl <= ssc, d_level_fast = dsl <= dsc;
     for (int e = threadIdx.x; e < kTileCols * N; e += blockDim.x) {
         int cl, i;
         if (s_level_fast) { cl = e / N; i = e - cl * N; } else { i = e / kTileCols; cl = e - i * kTileCols; }
-        if (cl < ncl) tile[i * (kTileCols + 1) + cl] = src[(int64_t)i * ssl + (c0 + cl) * ssc];
+        if (cl < ncl) tile[i * (kTileCols + 1) + cl] = src[(int64_t)i * ssl + (sidx ? sidx[c0 + cl] : c0 + cl) * ssc];
     }
     __syncthreads();
     for (int e = threadIdx.x; e < kTileCols * N; e += blockDim.x) {
         int cl, i;
         if (d_level_fast) { cl = e / N; i = e - cl * N; } else { i = e / kTileCols; cl = e - i * kTileCols; }
-        if (cl < ncl) dst[(int64_t)i * dsl + (c0 + cl) * dsc] = tile[i * (kTileCols + 1) + cl];
+        if (cl < ncl) dst[(int64_t)i * dsl + (didx ? didx[c0 + cl] : c0 + cl) * dsc] = tile[i * (kTileCols + 1) + cl];
     }
 }
-__global__ void __launch_bounds__(256) k_copy_many(ManyFields f, int64_t n)
+// per-column fields; sidx / didx (nullable): the caller-side index of handle column c on the source / destination side
+__global__ void __launch_bounds__(256) k_copy_many(ManyFields f, int64_t n, const int64_t *__restrict__ sidx = nullptr,
+                                                   const int64_t *__restrict__ didx = nullptr)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n) f.dst[blockIdx.y][c] = f.src[blockIdx.y][c];
+    if (c < n) f.dst[blockIdx.y][didx ? didx[c] : c] = f.src[blockIdx.y][sidx ? sidx[c] : c];
 }
 
 __global__ void __launch_bounds__(256) k_gather_cols(double *__restrict__ mirror, const double *__restrict__ src,

@@ -94,3 +94,57 @@ def test_pipelined_and_plain_routes_agree_bitwise():
         res[tag] = outs["u_theta_l"].copy()
     for tag in ("staged", "zerocopy", "boxes_per_field", "chunks7"):
         assert np.array_equal(res[tag], res["plain"]), tag
+
+
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+@pytest.mark.parametrize("whole_step", [False, True], ids=["stage", "whole_step"])
+def test_host_step_with_a_land_sea_mask(whole_step, pinned):
+    """mask_test.jl:53-61 through the host-buffer entry points: a ~1 degree lat-long domain (64 800 columns) of which 30 %
+    are land -- the handle holds the active columns only, the caller's arrays the whole domain.  Pinned arrays take the
+    chunked zero-copy route (chunks of ACTIVE columns, the host side of every access through the index), pageable ones
+    the field-by-field route: both give the compacted problem's stage (or whole step) in the active rows and leave the
+    others bit for bit."""
+    import climaland_b200 as cl
+    from climaland_b200 import workloads
+    from test_cuda_soil_step_host import RUNOFF, _oracle_step
+    ncol_total, N, dt, iters = 64800, 15, 900.0, 3
+    rng = np.random.default_rng(12)
+    active = np.sort(rng.choice(ncol_total, int(0.3 * ncol_total), replace=False)).astype(np.int64)
+    w = workloads.make_workload("energy_hydrology", ncol_total, N=N, seed=23, topmodel=True)
+    xp = workloads.make_explicit_params(w, 23)
+    forcing = dict(precip=-rng.uniform(0.0, 4e-7, ncol_total), f_max=rng.uniform(0.2, 0.6, ncol_total))
+    s = cl.SoilColumnSolver(model=cl.ENERGY_HYDROLOGY, n_columns=active.size, n_columns_total=ncol_total, z_f=w["z_f"],
+                            z_c=w["z_c"], active_columns=active, has_topmodel_source=True)
+    for k, v in {**w, **xp}.items():
+        if k.lower() in cl.FIELDS:
+            s.set(k, v)
+    s.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+    s.set("f_max", forcing["f_max"])
+    s.set_runoff_params(**RUNOFF)
+    # the compacted problem on the oracle
+    sub = {k: (v[active] if isinstance(v, np.ndarray) and v.shape[:1] == (ncol_total,) else v) for k, v in w.items()}
+    sub["ncol"] = active.size
+    P, U, p = oracle_problem(sub, nthreads=os.cpu_count() or 1)
+    if whole_step:
+        X = P.explicit_params(**{k: v[active] for k, v in xp.items()})
+        _oracle_step(P, U, p, X, {k: v[active] for k, v in forcing.items()}, dt, iters)
+        ins = {k: np.ascontiguousarray(w[k]).copy() for k in ("y_theta_l", "y_rho_e_int", "y_theta_i", "y_intf_w", "y_intf_e")}
+        ins["precip"] = forcing["precip"].copy()
+    else:
+        P.implicit_step(U, dt, iters, p=p)
+        ins = {k: np.ascontiguousarray(w[k]).copy() for k in IN_EH}
+    sentinel = -777.0
+    outs = {"y_theta_l": np.full((ncol_total, N), sentinel), "y_rho_e_int": np.full((ncol_total, N), sentinel),
+            "y_intf_w": np.full(ncol_total, sentinel), "y_intf_e": np.full(ncol_total, sentinel)}
+    if pinned:
+        ins = {k: _pin(v) for k, v in ins.items()}
+        outs = {k: _pin(v) for k, v in outs.items()}
+    if whole_step:
+        s.soil_step_host(dt, iters, ins, outs)
+    else:
+        s.implicit_step_host(dt, iters, ins, outs)
+    inactive = np.setdiff1d(np.arange(ncol_total), active)
+    for k, want in (("y_theta_l", U.theta_l), ("y_rho_e_int", U.rho_e_int), ("y_intf_w", U.intF_w), ("y_intf_e", U.intF_e)):
+        assert_close(outs[k][active], want, TOL, k[2:])
+        assert np.all(outs[k][inactive] == sentinel), k
+    s.close()

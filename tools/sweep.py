@@ -57,25 +57,36 @@ def main():
         cases.append(("energy_hydrology", 15, ncol, True, 900.0, 3))
     cases.append(("energy_hydrology", 50, 100_000, True, 900.0, 3))
     cases.append(("richards", 15, 61_206, True, 1800.0, 2))
+    # the masked variant of SURVEY 8(d): a 64 800-column lat-long domain with 30 % land -- the handle holds the active
+    # columns only (mask_test.jl:53-61), so the stage runs on 19 440 compacted columns
+    cases.append(("energy_hydrology", 15, 19_440, True, 900.0, 3))
+    # BASELINE configs[0]'s boundary conditions (MoistureStateBC top, FreeDrainage bottom): fluxes at the iterate
+    cases.append(("richards-bc", 15, 100_000, False, 1800.0, 2))
     stream = torch.cuda.Stream()
     print(f"# peak = {peak} GB/s (measured copy bandwidth); columns tiled from a {BASE}-column block")
     print(f"{'model':17s} {'N':>3s} {'columns':>9s} {'kernel':26s} {'us/stage':>10s} {'col-steps/s':>12s} {'GB/s':>8s} {'frac':>6s}  parity")
     for model, N, ncol, topm, dt, iters in cases:
         nb = min(ncol, BASE)
+        live_bc = model == "richards-bc"
+        label, model = model, model.split("-")[0]
         w = workloads.make_workload(model, nb, N=N, seed=7, topmodel=topm)
+        bc = {}
+        if live_bc:
+            w["theta_bc_top"] = w["nu"][:, -1] - np.random.default_rng(3).uniform(1e-3, 0.1, nb)
+            bc = dict(top_bc=1, bottom_bc=1)
         # parity of the base block against the oracle (test infrastructure: the checker only)
-        P, U, p = oracle_problem(w, nthreads=os.cpu_count() or 1)
+        P, U, p = oracle_problem(w, nthreads=os.cpu_count() or 1, **bc)
         P.implicit_step(U, dt, iters, p=p)
         bytes_cs = workloads.algorithmic_bytes(model, N, topmodel=topm)
         per_handle = ncol * N * (10 if model == "richards" else 17) * 8
-        if args.cases != "all" and args.cases not in f"{model}-{N}":
+        if args.cases != "all" and args.cases not in f"{label}-{N}":
             continue
         replicas = int(max(1, min(16, -(-160e6 // per_handle))))
         solvers = []
         mdl = cl.RICHARDS if model == "richards" else cl.ENERGY_HYDROLOGY
         for r in range(replicas):
             s = cl.SoilColumnSolver(model=mdl, n_columns=ncol, z_f=w["z_f"], z_c=w["z_c"], has_topmodel_source=topm,
-                                    stream=stream.cuda_stream, out_of_place=True)
+                                    stream=stream.cuda_stream, out_of_place=True, **bc)
             for k, v in w.items():
                 if k.lower() in cl.FIELDS:
                     s.set(k, tiled(np.asarray(v), ncol))
@@ -98,7 +109,7 @@ def main():
         cps = ncol / (us * 1e-6)
         gbs = cps * bytes_cs / 1e9
         name = VARIANTS.get(solvers[0].last_variant(), "?")
-        print(f"{model:17s} {N:3d} {ncol:9d} {name:26s} {us:10.1f} {cps:12.4g} {gbs:8.1f} {gbs / peak:6.3f}  {err:.1e}",
+        print(f"{label:17s} {N:3d} {ncol:9d} {name:26s} {us:10.1f} {cps:12.4g} {gbs:8.1f} {gbs / peak:6.3f}  {err:.1e}",
               flush=True)
         assert err <= 1e-10, f"parity {err}"  # a whole Newton stage; per-call parity (1e-12) is what tests/ pins
         for s in solvers:
