@@ -10,11 +10,21 @@ the shard: update_implicit_cache! + 3 x (Jacobian, implicit tendency, residual, 
 update) = ONE fused kernel launch (clb_implicit_step).
 
   value     column-steps/s with every input resident in HBM (library mirrors).
-  e2e       the same stage through the host-buffer C-ABI call (clb_implicit_step_host):
-            pinned host arrays in the reference layout; the 16 per-step inputs cross PCIe
-            (the library reads pinned arrays in place, column chunk by column chunk), the
-            fused kernel runs per chunk, the 4 outputs are written back to the host arrays;
-            all inside the timed region, one synchronising call per step.
+  e2e       the same metric through a host-buffer C-ABI call, pinned host arrays in the
+            reference layout, all transfers inside the timed region, one synchronising call
+            per step.  Two routes are timed and the faster one is the headline (the other is
+            reported under e2e.other_route):
+              clb_soil_step_host      a WHOLE soil step per call -- the state at t_n and the
+                                      forcing go up (23.5 MB), update_aux! + PhaseChange, the
+                                      TOPMODEL runoff, the explicit update and the implicit stage
+                                      run on the device per column chunk, the new state comes
+                                      back (23.0 MB); every call contains one implicit stage of
+                                      every column, the unit of the metric
+              clb_implicit_step_host  the implicit stage alone: its 16 per-step inputs (state +
+                                      lagged cache, 55.8 MB) up, the 4 outputs (15.7 MB) back
+  config    besides the workload: the whole RESIDENT soil step (clb_soil_step, 2 launches)
+            and ONE ~1 degree domain sharded over the ranks (strong scaling), both timed in
+            the same run with CUDA events.
   roofline  algorithmic bytes (2008 B per column-step) / kernel time against the
             measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline / --impl reference: the CPU oracle (our C restatement of the reference path;
