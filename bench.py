@@ -176,6 +176,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(use), "window": "timed region" if use is inside else "warm-up + timed region"}
 
 
+def bind_to_gpu_cpus(index):
+    """Pin this process to the CPUs NVML names as local to GPU `index`, BEFORE any pinned host buffer exists: the host
+    arrays of the e2e legs are then first touched -- and so placed -- on the GPU's own NUMA node.  (On a two-socket
+    node the H2D rate of a pinned buffer on the far socket is 12-23 GB/s against 55 GB/s, profiles/r2.)  A no-op where
+    NVML or the affinity call is unavailable, or on a host that exposes one node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(hnd, words)
+        cpus = {64 * i + b for i, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
@@ -204,6 +224,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="CLB_VARIANT_* (0 = the library's choice)")
     ap.add_argument("--layout", type=int, default=0, help="CLB_LAYOUT_* (0 = the library's choice)")
+    ap.add_argument("--host-route", type=int, default=0, help="CLB_OPT_HOST_ROUTE of the e2e legs (0 = the library's choice)")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the GPU's local CPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -219,6 +241,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    if not args.no_bind:
+        bind_to_gpu_cpus(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -344,6 +369,10 @@ def main():
             s_.set(k_, w_[k_])
 
     # ---- end to end through the host-buffer call ------------------------------------------
+    if args.host_route:
+        for s_ in solvers:
+            s_.set_option("host_route", args.host_route)
+
     def pinned(a):
         tns = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
         tns.numpy()[...] = a
@@ -471,6 +500,8 @@ def main():
             "balance": {"water_before": balance0[0], "water_after": balance1[0], "intF_w_after": balance1[1]},
         }
         if world == 1 and not args.no_cpu_baseline:
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)  # the CPU baseline runs on every host core again
             v, ms, cores, n = run_oracle(steps=1000, warmup=1, budget_s=12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
                                     "sample": f"{n} steps of the full {NCOL}-column workload (oracle/soil_oracle.c, OpenMP over columns)"}

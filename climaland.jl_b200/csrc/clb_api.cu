@@ -1018,7 +1018,7 @@ int clb_set_option(clb_handle h, int32_t option, int64_t value)
         h->co2_top_state[1] = value != 0;
         return CLB_OK;
     case CLB_OPT_HOST_ROUTE:
-        if (value < 0 || value > 2) return fail(CLB_ERR_INVALID, "clb_set_option: CLB_OPT_HOST_ROUTE takes 0, 1 or 2");
+        if (value < 0 || value > 3) return fail(CLB_ERR_INVALID, "clb_set_option: CLB_OPT_HOST_ROUTE takes 0 .. 3");
         h->host_route = (int)value;
         return CLB_OK;
     case CLB_OPT_HOST_CHUNKS:

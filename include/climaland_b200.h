@@ -96,9 +96,11 @@ enum { CLB_LAYOUT_AUTO = 0,
 enum { CLB_OPT_OUT_OF_PLACE = 1,        /* fused stage reads Y (= temp) and writes the U fields */
        CLB_OPT_CO2_TOP_STATE = 2,       /* SoilCO2Model: the top BC of CO2 is AtmosCO2StateBC (value CLB_F_CO2_C_ATM) */
        CLB_OPT_O2_TOP_STATE = 3,        /* ... of O2 is AtmosO2StateBC (value CLB_F_O2_C_ATM); 0 = flux values */
-       CLB_OPT_HOST_ROUTE = 4,          /* clb_implicit_step_host: 0 = the library's choice (zero-copy for pinned caller
-                                           arrays, staged copies for pageable ones), 1 = staged copies always,
-                                           2 = field by field (clb_set_field / clb_implicit_step / clb_get_field) */
+       CLB_OPT_HOST_ROUTE = 4,          /* clb_implicit_step_host / clb_soil_step_host: 0 = the library's choice (pinned
+                                           caller arrays: zero-copy kernels or the copy engines, whichever this host
+                                           favours -- measured once per device; pageable ones: staged copies),
+                                           1 = copy engines + device staging always, 2 = field by field (clb_set_field /
+                                           the step / clb_get_field), 3 = zero-copy kernels for pinned arrays */
        CLB_OPT_HOST_CHUNKS = 5,         /* column chunks of the pipelined host route (0 = default, 4) */
        CLB_OPT_TILE_BOXES = 6,          /* lane kernels: 0 = two TMA boxes of the arena per tile where the mirrors are
                                            equally spaced, 1 = one box per field always (same results, bit for bit) */
@@ -398,9 +400,10 @@ int clb_implicit_step_host(clb_handle h, double dtgamma, int32_t max_iters,
  * in_fields: whatever changed on the host since the last call -- normally Y (CLB_F_Y_THETA_L, _Y_RHO_E_INT,
  * _Y_THETA_I, _Y_INTF_W, _Y_INTF_E), CLB_F_PRECIP and the heat / bottom boundary fluxes; the lagged cache (K, kappa,
  * theta_l, is_saturated, R_ss, R_ess, h_grad) is computed on the device and never crosses PCIe.  out_fields: the new
- * state (the Y fields, or the U fields with CLB_OPT_OUT_OF_PLACE).  Pinned host arrays are read and written in place
- * column chunk by column chunk, chunk k's transfers overlapping chunk k-1's kernels; pageable arrays take the
- * field-by-field route (same results).  Needs clb_set_explicit_params, clb_set_runoff_params, the explicit-stage
+ * state (the Y fields, or the U fields with CLB_OPT_OUT_OF_PLACE).  The columns are cut into chunks whose transfers
+ * overlap the neighbouring chunks' kernels: pinned host arrays are read and written in place by the relayout kernels
+ * or moved by the copy engines through a device staging area (CLB_OPT_HOST_ROUTE; by default whichever this host
+ * favours), pageable ones go through the staging area (same results, bit for bit).  Needs clb_set_explicit_params, clb_set_runoff_params, the explicit-stage
  * parameter fields and CLB_F_F_MAX.  Synchronous. */
 int clb_soil_step_host(clb_handle h, double dt, int32_t max_iters,
                        const int32_t *in_fields, const double *const *in_ptrs, int32_t n_in,

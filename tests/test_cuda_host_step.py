@@ -85,14 +85,15 @@ def test_host_step_repeated_calls(pinned):
 
 
 def test_pipelined_and_plain_routes_agree_bitwise():
-    """CLB_OPT_HOST_ROUTE = 2 forces the field-by-field route, 1 the staged route for pinned arrays, CLB_OPT_TILE_BOXES
+    """CLB_OPT_HOST_ROUTE = 2 forces the field-by-field route, 1 the copy engines + staging, 3 the zero-copy kernels (0: the
+    library's choice between those two, by what the host favours), CLB_OPT_TILE_BOXES
     = 1 the lane kernel's one-box-per-field tile requests, CLB_OPT_HOST_CHUNKS another chunking: same bits."""
     res = {}
-    for tag, opt in (("zerocopy", {}), ("staged", {"host_route": 1}), ("plain", {"host_route": 2}),
+    for tag, opt in (("auto", {}), ("zerocopy", {"host_route": 3}), ("staged", {"host_route": 1}), ("plain", {"host_route": 2}),
                      ("boxes_per_field", {"tile_boxes": 1}), ("chunks7", {"host_chunks": 7})):
         _, outs, _, _ = _run("energy_hydrology", 20000, True, pinned=True, options=opt)
         res[tag] = outs["u_theta_l"].copy()
-    for tag in ("staged", "zerocopy", "boxes_per_field", "chunks7"):
+    for tag in ("auto", "staged", "zerocopy", "boxes_per_field", "chunks7"):
         assert np.array_equal(res[tag], res["plain"]), tag
 
 

@@ -108,11 +108,11 @@ def test_soil_step_host_time_loop():
 
 def test_soil_step_host_routes_agree_bitwise():
     res = {}
-    for tag, opt, pinned in (("chunked", {}, True), ("plain", {"host_route": 2}, True), ("pageable", {}, False),
-                             ("chunks7", {"host_chunks": 7}, True)):
+    for tag, opt, pinned in (("auto", {}, True), ("zerocopy", {"host_route": 3}, True), ("copy_engines", {"host_route": 1}, True),
+                             ("plain", {"host_route": 2}, True), ("pageable", {}, False), ("chunks7", {"host_chunks": 7}, True)):
         _, outs, _, _ = _run(20000, pinned, options=opt)
         res[tag] = {k: v.copy() for k, v in outs.items()}
-    for tag in ("chunked", "pageable", "chunks7"):
+    for tag in ("auto", "zerocopy", "copy_engines", "pageable", "chunks7"):
         for k in res["plain"]:
             assert np.array_equal(res[tag][k], res["plain"][k]), (tag, k)
 
