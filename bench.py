@@ -310,6 +310,7 @@ def main():
     if world == 1:
         shard_solvers = solvers  # the whole domain on one GPU: the loop above
         ms_shard = ms_step
+        ms_shard_whole = None  # = the whole resident step below
     else:
         w_full = make_inputs(seed=7)
         w_shard = parallel.shard_workload(w_full, world, rank)
@@ -329,6 +330,31 @@ def main():
         t = torch.tensor([es0.elapsed_time(es1)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_shard = float(t.item()) / args.steps
+        # ... and the WHOLE resident soil step of the shard (clb_soil_step, 2 launches)
+        rng_s = np.random.default_rng(11 + rank)
+        xp_s = workloads.make_explicit_params(w_shard, 7)
+        for s_ in shard_solvers:
+            for k_, v_ in xp_s.items():
+                s_.set(k_, v_)
+            s_.set_explicit_params(**workloads.EXPLICIT_SCALARS)
+            s_.set("f_max", rng_s.uniform(0.2, 0.6, hi - lo))
+            s_.set("precip", -rng_s.uniform(0, 4e-7, hi - lo))
+            s_.set_runoff_params(f_over=3.28, R_sb=1.484e-7, depth=50.0)
+            s_.set_option("out_of_place", 0)
+        n_ws = 200
+        with torch.cuda.stream(stream):
+            for k in range(n_rep):
+                shard_solvers[k].soil_step(DT, MAX_ITERS)
+            barrier()
+            es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            es0.record(stream)
+            for k in range(n_ws):
+                shard_solvers[k % n_rep].soil_step(DT, MAX_ITERS)
+            es1.record(stream)
+            barrier()
+        t = torch.tensor([es0.elapsed_time(es1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_shard_whole = float(t.item()) / n_ws
         for s_ in shard_solvers:
             s_.close()
 
@@ -484,6 +510,9 @@ def main():
                                        "sharded_1deg": {"columns_per_gpu": hi - lo, "ms_per_step": ms_shard,
                                                         "column_steps_per_s": NCOL / (ms_shard * 1e-3),
                                                         "sypd_1deg_sharded_implicit_stage_only": DT / (ms_shard * 1e-3) / 365.0,
+                                                        "ms_per_whole_soil_step": ms_shard_whole if ms_shard_whole else ms_whole,
+                                                        "sypd_1deg_sharded_whole_soil_step":
+                                                            DT / ((ms_shard_whole if ms_shard_whole else ms_whole) * 1e-3) / 365.0,
                                                         "speedup_vs_this_run_1gpu_whole_domain": ms_step / ms_shard,
                                                         "field_sets": n_rep, "scaling": "strong",
                                                         "note": "ONE 61 206-column domain cut into contiguous column blocks, "

@@ -451,7 +451,10 @@ __global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : C
         };
         // (Programmatic dependent launch of this kernel and an early release of the implicit stage behind it were
         // measured: 130.8 against 127.3 us per whole step -- the stage's blocks, which need a whole SM's shared memory,
-        // get in the way of this grid's last wave -- and not kept.)
+        // get in the way of this grid's last wave -- and not kept.  So were PERSISTENT blocks walking over the tiles, to
+        // fill the tables and wait for them once per block instead of once per tile (that barrier holds 12 % of the
+        // stall samples): 147.3 us -- without a second staging buffer, which does not fit, every tile's HBM latency is
+        // then exposed to its block instead of being covered by the next block the hardware schedules.)
         cpa(0, P.nu); cpa(1, P.theta_r); cpa(2, P.K_sat); cpa(3, P.S_s); cpa(4, P.hcm_a); cpa(5, P.hcm_b); cpa(6, P.hcm_m);
         cpa(7, P.Y_theta_l); cpa(8, P.Y_theta_i); cpa(9, P.rho_c_ds); cpa(10, P.Y_rho_e);
         if (AUX) {
