@@ -24,6 +24,7 @@
 #include "soil_pair.cuh"
 #include "soil_explicit.cuh"
 #include "soil_co2.cuh"
+#include "soil_co2_lanes.cuh"
 
 namespace {
 
