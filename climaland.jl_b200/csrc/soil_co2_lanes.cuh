@@ -25,8 +25,11 @@
 
 namespace clb {
 
+#ifndef CLB_CO2_MINB
+#define CLB_CO2_MINB 5  // <= 102 registers, 5 blocks per SM: 26.8 us at ~1 degree against 28.8 (4 blocks), 28.0 (6), 35.2 (8: spills)
+#endif
 template <int PARTS, int Q>
-__global__ void __launch_bounds__(128) k_co2_lanes(const DevView P, const Co2View V, double dtg, int max_iters)
+__global__ void __launch_bounds__(128, (Q <= 4) ? CLB_CO2_MINB : 1) k_co2_lanes(const DevView P, const Co2View V, double dtg, int max_iters)
 {
     using Gm = LaneGeom<PARTS, Q>;
     constexpr int CPW = Gm::CPW, NR = Gm::NR;

@@ -330,24 +330,55 @@ constexpr int kExplicitStage = 17;  // per-cell inputs of k_explicit_cells_unifo
 
 namespace xbf {
 
+// The constants of the table-driven log / exp in CONSTANT memory: an FP64 instruction takes one operand straight from
+// a constant bank, but a 64-bit literal that is not a bank operand costs two moves (IMAD.MOV / UMOV of its halves)
+// EVERY time it is used -- with one cell per thread nothing amortises them (the lane kernels use a literal for W = 4
+// chains): ncu's opcode mix of this kernel had 230 such moves among 1 811 instructions per warp.
+__constant__ double c_xm[12] = {mtab::kLn2, mtab::kExpScale, -mtab::kLn2NHi, -mtab::kLn2NLo, mtab::kExpC2, mtab::kExpC3,
+                                mtab::kExpC4, mtab::kExpC5, 0.33333333333333333, 0.2, -0.16666666666666667,
+                                4503601774854144.0};
+
 // tlog / texp with the tables in SHARED memory (2.5 KB per block, filled by its 128 threads): a look-up through L1
 // from global memory stalls the warp on the long scoreboard (ncu: 3.8 stall cycles per issued instruction, the
-// largest item), from shared memory it is a ~25-cycle access
+// largest item), from shared memory it is a ~25-cycle access.  Operation by operation fmv::log_tab<1> / exp_tab<1>
+// (same values); only where the constants come from differs.
 struct Tab {
     fmv::MathTab MT;
     __device__ __forceinline__ double log(double x) const
     {
-        const double xv[1] = {x};
-        double r[1];
-        fmv::log_tab<1>(MT, xv, r);
-        return r[0];
+        const int hx = __double2hiint(x);
+        const int tmp = hx - mtab::kLogOffHi;
+        const int k = tmp >> 20;
+        const double2 e = MT.logt[(tmp >> 13) & (mtab::kLogN - 1)];
+        const double z = __hiloint2double(hx - (tmp & 0xfff00000), __double2loint(x));
+        const double dk = __hiloint2double(0x43300000, k ^ 0x80000000) - c_xm[11];
+        double r = fma(z, e.x, -1.0);
+        const double w = fma(dk, c_xm[0], e.y);
+        const double r2 = r * r;
+        double p01 = fma(r, c_xm[8], -0.5);
+        double p23 = fma(r, c_xm[9], -0.25);
+        p23 = fma(r2, c_xm[10], p23);
+        p01 = fma(r2, p23, p01);
+        r = fma(r2, p01, r);
+        return w + r;
     }
     __device__ __forceinline__ double exp(double x) const
     {
-        const double xv[1] = {x};
-        double r[1];
-        fmv::exp_tab<1>(MT, xv, r);
-        return r[0];
+        const double MAGIC = 6755399441055744.0;
+        double t = fma(x, c_xm[1], MAGIC);
+        const int k = __double2loint(t);
+        t = t - MAGIC;
+        const double tb = MT.expt[k & (mtab::kExpN - 1)];
+        double r = fma(t, c_xm[2], x);
+        r = fma(t, c_xm[3], r);
+        const double r2 = r * r;
+        double q23 = fma(r, c_xm[5], c_xm[4]);
+        const double q45 = fma(r, c_xm[7], c_xm[6]);
+        q23 = fma(r2, q45, q23);
+        r = fma(r2, q23, r);
+        r = fma(tb, r, tb);
+        const int kc = min(max(k >> 6, -1021), 1022);
+        return __hiloint2double(__double2hiint(r) + (kc << 20), __double2loint(r));
     }
 };
 
