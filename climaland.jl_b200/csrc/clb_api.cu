@@ -699,8 +699,8 @@ int launch_octet_n(clb_handle h, const clb::DevView &P, double dtg, int max_iter
 bool pair_variant_applies(clb_handle h, bool octet = false)
 {
     const int N = h->cfg.n_levels;
-    // octet: N = 15 / 16 / 50 as template instantiations, 17 .. 48 with the level count at run time
-    if (N != 15 && N != 16 && !(octet && (N == 50 || (N >= 17 && N <= 48)))) return false;
+    // octet: N = 15 / 16 / 50 as template instantiations, 17 .. 64 with the level count at run time
+    if (N != 15 && N != 16 && !(octet && N >= 17 && N <= 64)) return false;
     if (h->cfg.math_mode != CLB_MATH_FAST) return false;
     // a MoistureStateBC top re-evaluates the boundary fluxes every iteration (rre.jl:460-468): the pipelined quad has an
     // instantiation for it (BCL); the octets do not, nor does the plain quad: lane-per-cell kernel
@@ -916,11 +916,11 @@ int clb_create(clb_handle *out, const clb_config *cfg)
         const bool octet50 = cfg->n_levels == 50 && cfg->math_mode == CLB_MATH_FAST &&
                              !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
                              (cfg->kernel_variant == CLB_VARIANT_AUTO || cfg->kernel_variant == CLB_VARIANT_LANE_OCTET);
-        // 17 <= N <= 48: the octet with the level count at run time reads column-fastest mirrors; it is the choice
+        // 17 <= N <= 64 (other than 50): the octet with the level count at run time reads column-fastest mirrors; it is the choice
         // while a field stays below 80 MB (beyond that its tiles fall out of the TLB, see clb_implicit_step).  Measured
         // at 1e5 columns (tools/time_other_n.py): faster than the lane-per-cell / generic kernels at every N
         const int64_t ld0 = (cfg->n_columns + 31) / 32 * 32;
-        const bool octet_rt = cfg->n_levels >= 17 && cfg->n_levels <= 48 && cfg->math_mode == CLB_MATH_FAST &&
+        const bool octet_rt = cfg->n_levels >= 17 && cfg->n_levels <= 64 && cfg->n_levels != 50 && cfg->math_mode == CLB_MATH_FAST &&
                               !(cfg->model == CLB_RICHARDS && cfg->top_bc == 1) &&
                               (cfg->kernel_variant == CLB_VARIANT_LANE_OCTET ||
                                (cfg->kernel_variant == CLB_VARIANT_AUTO && ld0 * cfg->n_levels * 8 <= ((int64_t)80 << 20)));
@@ -1534,7 +1534,7 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
         if (pair_variant_applies(h))
             variant = CLB_VARIANT_LANE_QUAD_PIPELINED;
         else if (pair_variant_applies(h, true) && (level_fast || (int64_t)h->ld * N * 8 <= (int64_t)80 << 20))
-            // N = 50 (and 17 .. 48 on column-fastest mirrors).  A tile of the octet touches all 50 level rows of every field at once.  In level-fastest mirrors
+            // N = 50 (and 17 .. 64 on column-fastest mirrors).  A tile of the octet touches all 50 level rows of every field at once.  In level-fastest mirrors
             // (what CLB_LAYOUT_AUTO picks for N = 50) they are contiguous.  In column-fastest mirrors they lie
             // ld * 8 bytes apart and, as the fields grow, the tile's ~550 pages fall out of the TLB (measured against
             // the generic kernel, tools/n50_crossover.py: 2.1x faster at 1e5 columns, equal at ~2.2e5 = 88 MB per
@@ -1555,7 +1555,7 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
                     "MoistureStateBC top of RichardsModel: the pipelined quad only)");
     if (variant == CLB_VARIANT_LANE_OCTET && !pair_variant_applies(h, true))
         return fail(CLB_ERR_INVALID,
-                    "clb_implicit_step: the lane-octet variant needs 15 <= N <= 48 on column-fastest mirrors or N = 50, CLB_MATH_FAST and "
+                    "clb_implicit_step: the lane-octet variant needs 15 <= N <= 64 on column-fastest mirrors or N = 50, CLB_MATH_FAST and "
                     "flux boundary conditions");
     if (variant == CLB_VARIANT_LANE_PER_CELL && N > 31)
         return fail(CLB_ERR_INVALID, "clb_implicit_step: the lane-per-cell variant needs N <= 31");
@@ -1596,7 +1596,9 @@ int clb_implicit_step(clb_handle h, double dtgamma, int32_t max_iters, double to
             else if (N <= 24) TRY((launch_octet_rt_q<3>(h, P, dtgamma, max_iters)));
             else if (N <= 32) TRY((launch_octet_rt_q<4>(h, P, dtgamma, max_iters)));
             else if (N <= 40) TRY((launch_octet_rt_q<5>(h, P, dtgamma, max_iters)));
-            else TRY((launch_octet_rt_q<6>(h, P, dtgamma, max_iters)));
+            else if (N <= 48) TRY((launch_octet_rt_q<6>(h, P, dtgamma, max_iters)));
+            else if (N <= 56) TRY((launch_octet_rt_q<7>(h, P, dtgamma, max_iters)));
+            else TRY((launch_octet_rt_q<8>(h, P, dtgamma, max_iters)));
 #endif
         } else if (variant == CLB_VARIANT_LANE_PER_CELL) {
             const int cpw = (N <= 15) ? 2 : 1;  // columns per warp (one lane of each segment is a ghost)

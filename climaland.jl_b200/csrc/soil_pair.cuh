@@ -1,6 +1,6 @@
 // soil_pair.cuh -- the lane kernels of the fused implicit stage: a column is split over 2 * PARTS lanes of a warp
 // (PARTS = 1 lane pair, 2 lane QUAD -- the bench kernel, N = 15 / 16 -- , 4 lane OCTET, N = 15 / 16 / 50 compiled in
-// and 17 .. 48 read at run time), Q cells per lane, 32 / (2 PARTS) columns per warp.
+// and 17 .. 64 read at run time), Q cells per lane, 32 / (2 PARTS) columns per warp.
 //
 // The lanes of a column form two halves: the "bottom" half holds the levels from the bottom boundary up to the seam,
 // the "top" half the levels from the top boundary down to the seam (NR = 2 PARTS Q level rows; rows >= N are pads at

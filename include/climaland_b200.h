@@ -85,7 +85,7 @@ enum { CLB_VARIANT_AUTO = 0,
                                            CLB_MATH_FAST, flux BCs, column-fastest mirrors               */
        CLB_VARIANT_LANE_QUAD_PIPELINED = 5, /* the same as a persistent kernel whose warps prefetch their next
                                            tile (double-buffered shared memory)                          */
-       CLB_VARIANT_LANE_OCTET = 6       /* eight lanes per column, Q cells each: 15 <= N <= 48 (Q = ceil(N / 8);
+       CLB_VARIANT_LANE_OCTET = 6       /* eight lanes per column, Q cells each: 15 <= N <= 64 (Q = ceil(N / 8);
                                            N = 15 / 16 compiled in, the others read at run time) on column-fastest
                                            mirrors, N = 50 (Q = 7) on either layout; otherwise as the quad */ };
 /* layout of the library's per-cell mirrors (0 = let the library choose) */

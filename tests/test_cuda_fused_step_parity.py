@@ -40,6 +40,12 @@ CASES = [
     ("energy_hydrology", 1, 0, 0, True, 25, 38, 900.0, 2),
     ("richards", 0, 0, 0, False, 48, 9, 1800.0, 2),
     ("energy_hydrology", 0, 0, 0, True, 41, 21, 900.0, 3),
+    # 49 .. 64 levels (other than the compiled N = 50): Q = 7 / 8 cells per lane, single-buffered tiles
+    ("richards", 0, 0, 0, True, 56, 37, 1800.0, 2),
+    ("energy_hydrology", 0, 0, 0, True, 49, 29, 900.0, 3),
+    ("richards", 1, 0, 1, False, 57, 21, 1800.0, 2),
+    ("energy_hydrology", 1, 0, 0, True, 64, 13, 900.0, 3),
+    ("energy_hydrology", 0, 0, 0, False, 60, 50, 900.0, 2),
     # MoistureStateBC top (boundary fluxes and dfluxBCdY at the iterate): Brooks-Corey, N = 16 (no pad row: the top cell
     # is slot 0 of its lane), a lagged bottom flux value, one column more than a tile
     ("richards", 1, 1, 1, False, 15, 90, 1800.0, 3),
@@ -92,9 +98,9 @@ def test_fused_step_matches_oracle(case, math_mode, variant):
                                             (model == "richards" and top_bc == 1 and variant != "lane_quad_pipelined")):
         pytest.skip("lane-quad is built for N = 15 / 16, fast math, column-fastest mirrors; a MoistureStateBC top "
                     "(boundary fluxes at the iterate): the pipelined quad only")
-    if variant.startswith("lane_octet") and (not (N in (15, 16, 50) or 17 <= N <= 48) or math_mode != 0
+    if variant.startswith("lane_octet") and (not (15 <= N <= 64) or math_mode != 0
                                              or (model == "richards" and top_bc == 1)):
-        pytest.skip("lane-octet is built for N = 15 .. 48 and 50, fast math, flux boundary conditions")
+        pytest.skip("lane-octet is built for N = 15 .. 64, fast math, flux boundary conditions")
     if variant == "lane_octet_lf" and N != 50:
         pytest.skip("only the N = 50 octet reads level-fastest mirrors")
     w = _setup(case)
