@@ -615,7 +615,10 @@ int launch_quad(clb_handle h, const clb::DevView &P, double dtg, int max_iters, 
 #ifndef CLB_QUAD_NBUF
 #define CLB_QUAD_NBUF 2
 #endif
-    constexpr int NS = (MODEL == 1) ? ((PIPELINED && CLB_QUAD_NBUF == 2) ? 14 : CLB_QUAD_NS) : 11;
+#ifndef CLB_QUAD_NS_R
+#define CLB_QUAD_NS_R 11  // RichardsModel: all 11 stage constants in shared memory (9 = the raw fields' slots only, 2 in registers)
+#endif
+    constexpr int NS = (MODEL == 1) ? ((PIPELINED && CLB_QUAD_NBUF == 2) ? 14 : CLB_QUAD_NS) : (PIPELINED ? CLB_QUAD_NS_R : 11);
     if constexpr (PIPELINED)
 #ifndef CLB_QUAD_BLOCK_R
 #define CLB_QUAD_BLOCK_R 256
