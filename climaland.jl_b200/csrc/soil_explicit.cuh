@@ -351,7 +351,7 @@ struct Tab {
         const int k = tmp >> 20;
         const double2 e = MT.logt[(tmp >> 13) & (mtab::kLogN - 1)];
         const double z = __hiloint2double(hx - (tmp & 0xfff00000), __double2loint(x));
-        const double dk = __hiloint2double(0x43300000, k ^ 0x80000000) - c_xm[11];
+        const double dk = __int2double_rn(k);
         double r = fma(z, e.x, -1.0);
         const double w = fma(dk, c_xm[0], e.y);
         const double r2 = r * r;
