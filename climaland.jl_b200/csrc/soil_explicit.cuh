@@ -474,11 +474,11 @@ __global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : C
     // HBM round trips per cell (ncu: long_scoreboard 3.2 stall cycles per issued instruction, the largest item).  A
     // thread only reads what it staged itself: no block barrier.
     {
+        // every field is there (explicit_ready / clb_soil_step require them) except m of a Brooks-Corey handle: the
+        // pointers are not tested one by one (17 uniform null checks were 54 instructions per thread)
         auto cpa = [&](int slot, const double *src) {
-            if (src) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + (size_t)slot * nt);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + q) : "memory");
-            }
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + (size_t)slot * nt);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + q) : "memory");
         };
         // (Programmatic dependent launch of this kernel and an early release of the implicit stage behind it were
         // measured: 130.8 against 127.3 us per whole step -- the stage's blocks, which need a whole SM's shared memory,
@@ -486,7 +486,8 @@ __global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : C
         // fill the tables and wait for them once per block instead of once per tile (that barrier holds 12 % of the
         // stall samples): 147.3 us -- without a second staging buffer, which does not fit, every tile's HBM latency is
         // then exposed to its block instead of being covered by the next block the hardware schedules.)
-        cpa(0, P.nu); cpa(1, P.theta_r); cpa(2, P.K_sat); cpa(3, P.S_s); cpa(4, P.hcm_a); cpa(5, P.hcm_b); cpa(6, P.hcm_m);
+        cpa(0, P.nu); cpa(1, P.theta_r); cpa(2, P.K_sat); cpa(3, P.S_s); cpa(4, P.hcm_a); cpa(5, P.hcm_b);
+        if (CLOSURE == kVanGenuchten) cpa(6, P.hcm_m);
         cpa(7, P.Y_theta_l); cpa(8, P.Y_theta_i); cpa(9, P.rho_c_ds); cpa(10, P.Y_rho_e);
         if (AUX) {
             cpa(11, X.nu_ss_om); cpa(12, X.nu_ss_quartz); cpa(13, X.nu_ss_gravel); cpa(14, X.kappa_sat_unfrozen);
@@ -499,6 +500,9 @@ __global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : C
         // 148 / 296 / 592 blocks ahead, one lane per 128-byte line: 128.9 / 130.5 / 134.1 against 127.5 us per whole soil
         // step -- the wait of a fresh block is not what the prefetch can remove, and its 17 requests per line cost more.)
     }
+    // not unrolled: all but the first 128 threads of a block only fall through (unrolled, the loop was 85 instructions
+    // for every thread)
+#pragma unroll 1
     for (int t = threadIdx.x; t < mtab::kLogN; t += blockDim.x) fmv::math_tab_fill(tab_sm, t);
     const xbf::Tab M{fmv::MathTab{reinterpret_cast<const double2 *>(tab_sm),
                                   reinterpret_cast<const double *>(tab_sm + mtab::kLogN * 16)}};
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : C
     auto in = [&](int slot) { return stage[(size_t)slot * nt]; };
     HydroCell cell;
     cell.nu = in(0); cell.theta_r = in(1); cell.K_sat = in(2); cell.S_s = in(3); cell.a = in(4); cell.b = in(5);
-    cell.m = P.hcm_m ? in(6) : 0.0;
+    cell.m = (CLOSURE == kVanGenuchten) ? in(6) : 0.0;
     const double th = in(7), thi = in(8);
     const double rcds = in(9);
     const bool any_ice = __any_sync(kFull, thi != 0.0);
