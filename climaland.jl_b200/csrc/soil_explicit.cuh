@@ -30,6 +30,10 @@ namespace clb {
 // scalars of EnergyHydrologyParameters (energy_hydrology.jl:150-160) + LandParameters T_freeze, grav
 struct ExplicitConst {
     double Omega, gamma, gammaT_ref, alpha, beta, T_freeze, grav;
+    // quotients of launch constants, divided on the host (make_explicit_view: the same IEEE quotient, i.e. the same bits):
+    // in k_explicit_cells_uniform every `/` of two constants was an inlined IEEE division per THREAD -- four of them on
+    // a cell's path, 155 of the kernel's ~3 200 issue cycles (tools/sass_cost_lines.py)
+    double rho_l_over_rho_i = 0.0, rho_i_over_rho_l = 0.0, LH_f0_over_grav = 0.0;
 };
 
 // per-cell fields only the explicit stage touches
@@ -324,8 +328,9 @@ struct RunoffView {
 //     general path once instead of both paths one after the other;
 //   * saturated cells run the unsaturated formulas on finite garbage and select, as the lane kernels' closure does;
 //   * the logarithm of T / T_f (series log: it needs relative accuracy near 1) only where some lane is below T_f.
-// Every value is the one the kernel above produces (same formulas, same functions, same rounding sequence) except
-// kappa_sat of an ice-free cell in a warp with ice, exp(log k_u) instead of k_u (<= 2^-52 relative).
+// Every value is the one the kernel above produces (same formulas and functions) up to the last bit or two: kappa_sat
+// of an ice-free cell in a warp with ice is exp(log k_u) instead of k_u (<= 2^-52 relative), and the series of the
+// table-driven log / exp are summed in Horner order here (xbf::Tab).
 constexpr int kExplicitStage = 17;  // per-cell inputs of k_explicit_cells_uniform staged in shared memory
 
 namespace xbf {
@@ -340,8 +345,8 @@ __constant__ double c_xm[12] = {mtab::kLn2, mtab::kExpScale, -mtab::kLn2NHi, -mt
 
 // tlog / texp with the tables in SHARED memory (2.5 KB per block, filled by its 128 threads): a look-up through L1
 // from global memory stalls the warp on the long scoreboard (ncu: 3.8 stall cycles per issued instruction, the
-// largest item), from shared memory it is a ~25-cycle access.  Operation by operation fmv::log_tab<1> / exp_tab<1>
-// (same values); only where the constants come from differs.
+// largest item), from shared memory it is a ~25-cycle access.  The algorithms of fmv::log_tab<1> / exp_tab<1>
+// with the constants from constant memory and the series in Horner form (values within an ulp of theirs).
 struct Tab {
     fmv::MathTab MT;
     __device__ __forceinline__ double log(double x) const
@@ -355,10 +360,14 @@ struct Tab {
         double r = fma(z, e.x, -1.0);
         const double w = fma(dk, c_xm[0], e.y);
         const double r2 = r * r;
-        double p01 = fma(r, c_xm[8], -0.5);
-        double p23 = fma(r, c_xm[9], -0.25);
-        p23 = fma(r2, c_xm[10], p23);
-        p01 = fma(r2, p23, p01);
+        // Horner in r (the lane kernels' Estrin form needs a second constant in a register per pair of coefficients --
+        // one LDC each here, where a thread holds one cell -- and two more DFMAs with three live register operands):
+        // the same series, rounded in another order (both within the 2^-56 max(1, |log x|) of tests/test_cuda_math.py);
+        // static issue cost of the whole kernel -1.7 %, whole soil step 125.15 -> 124.4 us
+        double p01 = fma(r, c_xm[10], c_xm[9]);
+        p01 = fma(r, p01, -0.25);
+        p01 = fma(r, p01, c_xm[8]);
+        p01 = fma(r, p01, -0.5);
         r = fma(r2, p01, r);
         return w + r;
     }
@@ -372,9 +381,9 @@ struct Tab {
         double r = fma(t, c_xm[2], x);
         r = fma(t, c_xm[3], r);
         const double r2 = r * r;
-        double q23 = fma(r, c_xm[5], c_xm[4]);
-        const double q45 = fma(r, c_xm[7], c_xm[6]);
-        q23 = fma(r2, q45, q23);
+        double q23 = fma(r, c_xm[7], c_xm[6]);  // Horner, as in log above
+        q23 = fma(r, q23, c_xm[5]);
+        q23 = fma(r, q23, c_xm[4]);
         r = fma(r2, q23, r);
         r = fma(tb, r, tb);
         const int kc = min(max(k >> 6, -1021), 1022);
@@ -591,7 +600,7 @@ __global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : C
         const double f_i = fm::div(thi, theta_l + thi - cell.theta_r);
         const double imp = any_ice ? M.exp((-X.k.Omega * f_i) * 2.302585092994045684) : 1.0;  // 10^0 = exp(0) = 1 exactly
         const double visc = M.exp(X.k.gamma * (T - X.k.gammaT_ref));
-        Tf_aux = xbf::Tf_depressed<CLOSURE>(M, cell, inv_m, inv_n, theta_l, thi, E.rho_l / E.rho_i, X.k, E.LH_f0, psi_w0_aux);
+        Tf_aux = xbf::Tf_depressed<CLOSURE>(M, cell, inv_m, inv_n, theta_l, thi, X.k.rho_l_over_rho_i, X.k, E.LH_f0, psi_w0_aux);
         if (live) {
             X.p_theta_l[q] = theta_l;
             X.p_kappa[q] = kappa;
@@ -610,23 +619,23 @@ __global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : C
         const double tau = fm::div(3.0 * volumetric_heat_capacity(theta_l, thi, rcds, E) * (dz * dz), kappa);
         double psi_w0 = psi_w0_aux, Tf = Tf_aux;
         if (!AUX || any_ice)  // without ice the density ratio does not enter theta_tot: the value of update_aux!
-            Tf = xbf::Tf_depressed<CLOSURE>(M, cell, inv_m, inv_n, theta_l, thi, E.rho_i / E.rho_l, X.k, E.LH_f0, psi_w0);
+            Tf = xbf::Tf_depressed<CLOSURE>(M, cell, inv_m, inv_n, theta_l, thi, X.k.rho_i_over_rho_l, X.k, E.LH_f0, psi_w0);
         const bool below = (Tf - T) > kEps;  // heaviside(Tf - T)
         double psi_T = 0.0;
-        if (__any_sync(kFull, below)) psi_T = below ? E.LH_f0 / X.k.grav * fm::log(fm::div(T, Tf)) : 0.0;
+        if (__any_sync(kFull, below)) psi_T = below ? X.k.LH_f0_over_grav * fm::log(fm::div(T, Tf)) : 0.0;
         const double theta_star =
             xbf::inverse_matric_potential<CLOSURE>(M, cell, psi_w0 + psi_T) * (cell.nu - cell.theta_r) + cell.theta_r;
         const double s = fm::div(theta_l - theta_star, tau);
         if (live) {
             if (X.apply_dt != 0.0) {
                 P.Y_theta_l[q] = __dadd_rn(th, __dmul_rn(X.apply_dt, -s));
-                P.Y_theta_i[q] = __dadd_rn(thi, __dmul_rn(X.apply_dt, (E.rho_l / E.rho_i) * s));
+                P.Y_theta_i[q] = __dadd_rn(thi, __dmul_rn(X.apply_dt, X.k.rho_l_over_rho_i * s));
             } else if (X.assign_source) {
                 X.dYe_theta_l[q] = -s;
-                X.dYe_theta_i[q] = (E.rho_l / E.rho_i) * s;
+                X.dYe_theta_i[q] = X.k.rho_l_over_rho_i * s;
             } else {
                 X.dYe_theta_l[q] += -s;
-                X.dYe_theta_i[q] += (E.rho_l / E.rho_i) * s;
+                X.dYe_theta_i[q] += X.k.rho_l_over_rho_i * s;
             }
         }
     }
