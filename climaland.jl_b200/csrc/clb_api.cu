@@ -294,6 +294,8 @@ clb::DevView make_view(clb_handle h)
     if (h->grid_set) {
         P.dz_top = h->dz_c[N - 1] / 2.0;
         P.dz_bot = h->dz_c[0] / 2.0;
+        P.inv_dz_top = 1.0 / P.dz_top;
+        P.inv_dz_bot = 1.0 / P.dz_bot;
     }
     double *const *F = h->field;
     P.nu = F[CLB_F_NU]; P.theta_r = F[CLB_F_THETA_R]; P.K_sat = F[CLB_F_K_SAT]; P.S_s = F[CLB_F_S_S];

@@ -23,6 +23,7 @@ struct DevView {
     // grid (device arrays, length N; inv_dz_f[i] belongs to the face between cells i-1 and i, i = 1..N-1)
     const double *z_c, *dz_c, *inv_dz_c, *inv_dz_f;
     double dz_top, dz_bot;  // Domains.get_dz top / bottom half-cell, Domains.jl:935-949
+    double inv_dz_top, inv_dz_bot;  // 1 / dz_top, 1 / dz_bot divided on the host (correctly rounded): fm::div_by
     // parameters and lagged cache
     const double *nu, *theta_r, *K_sat, *S_s, *hcm_a, *hcm_b, *hcm_m, *rho_c_ds;
     const double *K_lag, *kappa_lag, *theta_l_lag, *is_sat;

@@ -863,16 +863,16 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             for (int q = 0; q < Q; ++q)
                 if (q == qb) { Kb = Kc[q]; psib = h[q] - G.z[half][r0 + q]; dpb = dps[q]; }
             if (half) {
-                const double fl = -Kb * ((psi_bc + P.dz_top) - psib) / P.dz_top;
+                const double fl = fm::div_by(-Kb * ((psi_bc + P.dz_top) - psib), P.dz_top, P.inv_dz_top);
                 if (top_lane) {
                     live_top = fl;
-                    top_dflux = Kb * dpb / P.dz_top;
+                    top_dflux = fm::div_by(Kb * dpb, P.dz_top, P.inv_dz_top);
                     if (qT == 0) b0_wi = -fl;
                     else bT_wi = -fl;
                 }
             } else if (outermost) {
                 if (P.bottom_bc == 1) live_bot = -1 * Kb;
-                else if (P.bottom_bc == 2) live_bot = -Kb * ((psib + P.dz_bot) - psi_bc) / P.dz_bot;
+                else if (P.bottom_bc == 2) live_bot = fm::div_by(-Kb * ((psib + P.dz_bot) - psi_bc), P.dz_bot, P.inv_dz_bot);
                 b0_wi = live_bot;
             }
             // the flux integral (W = -I) with the fluxes of this iterate, in the lane that stores it (the bottom
