@@ -301,11 +301,16 @@ __host__ __device__ constexpr size_t pair_smem_bytes()
 // Per-column scalars of a tile, fetched one tile ahead into registers.
 struct ColScalars {
     double Rss, hg, top_w, bot_w, Ress, top_h, bot_h, intF_w, intF_e;
+    double theta_bc;  // BCL: the boundary value of this lane's half (MoistureStateBC), else unused
 };
-template <int MODEL>
-__device__ __forceinline__ ColScalars load_col_scalars(const DevView &P, int64_t cs)
+template <int MODEL, bool BCL = false>
+__device__ __forceinline__ ColScalars load_col_scalars(const DevView &P, int64_t cs, int half = 0)
 {
     ColScalars v;
+    v.theta_bc = 0.0;
+    // fetched a tile ahead with the other per-column scalars: read where it is used (the set-up), it was one exposed
+    // HBM round trip per tile
+    if (BCL) v.theta_bc = half ? P.theta_bc_top[cs] : ((P.bottom_bc == 2) ? P.theta_bc_bot[cs] : 0.0);
     v.Rss = P.R_ss[cs];
     v.hg = P.h_grad[cs];
     v.top_w = P.top_bc_w[cs];
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     if (!has_tile) return;  // whole warp
     request_tile(warp0, 0, 2);
     if (NBUF == 2 && warp0 + nwarps < ntiles) request_tile(warp0 + nwarps, 1, 3);  // untouched buffer: no proxy fence needed
-    ColScalars nxt = load_col_scalars<MODEL>(P, col_clamped(warp0));
+    ColScalars nxt = load_col_scalars<MODEL, BCL>(P, col_clamped(warp0), half);
 
     double dx2_acc = 0.0, bad = 0.0;
     CLB_PC_DECL
@@ -571,8 +576,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
                     thr_[0] = theta_r[q]; nu_[0] = nu[q]; irg_[0] = cc[q].inv_range; ca_[0] = cc[q].ca; ca2_[0] = cc[q].ca2;
                     cb_[0] = cc[q].cb; cc_[0] = cc[q].cc; cd_[0] = cc[q].cd; iss_[0] = cc[q].inv_Ss; ks_[0] = K_sat[q];
                 }
-            const double tb = half ? P.theta_bc_top[col_clamped(tile_id)]
-                                   : ((P.bottom_bc == 2) ? P.theta_bc_bot[col_clamped(tile_id)] : nu_[0]);
+            const double tb = (half || P.bottom_bc == 2) ? cur.theta_bc : nu_[0];
             th_[0] = tb;
             fmv::closure<CLOSURE, false, 1, true>(MT, th_, thr_, nu_, irg_, ca_, ca2_, cb_, cc_, cd_, iss_, ks_, K_, psi_, dp_);
             psi_bc = psi_[0];
@@ -718,7 +722,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     // next tile's boxes were requested when the tile before this one finished its Newton loop, below.)
     if (NBUF == 2) {
         const int64_t tn = tile_id + nwarps;
-        if (tn < ntiles) nxt = load_col_scalars<MODEL>(P, col_clamped(tn));
+        if (tn < ntiles) nxt = load_col_scalars<MODEL, BCL>(P, col_clamped(tn), half);
     }
 
     CLB_PC(2)  // set-up
@@ -1024,7 +1028,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             CLB_PC(11)  // of the request: __syncwarp + proxy fence
             request_tile(tr, buf, 3);
-            if (NBUF == 1) nxt = load_col_scalars<MODEL>(P, col_clamped(tr));
+            if (NBUF == 1) nxt = load_col_scalars<MODEL, BCL>(P, col_clamped(tr), half);
         }
     }
 
