@@ -653,6 +653,12 @@ int launch_quad_n(clb_handle h, const clb::DevView &P, double dtg, int max_iters
               : launch_quad<1, 0, N, PIPELINED>(h, P, dtg, max_iters, col0);
 }
 
+#ifndef CLB_OCTET_BLOCK_EH1
+// threads per block of the single-buffered EnergyHydrology octets on column-fastest mirrors with up to 7 cells per lane
+// (18 slots of 56 rows x 4 columns per warp: seven warps fill the 227 KB; the level-fastest tiles' padded rows and
+// Q = 8 leave room for six): N = 49 / 56 at 1e5 columns 590 / 619 -> 559 / 585 us
+#define CLB_OCTET_BLOCK_EH1 224
+#endif
 template <int CLOSURE, int MODEL, int N>
 int launch_octet(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
 {
@@ -661,7 +667,7 @@ int launch_octet(clb_handle h, const clb::DevView &P, double dtg, int max_iters)
         return launch_lanes<CLOSURE, MODEL, N, 4, 2, NS, 2, 512, 1, true>(h, P, dtg, max_iters, 0);
     } else if constexpr (MODEL == 1) {
         if (h->sc != 1) return launch_lanes<CLOSURE, MODEL, N, 4, 7, 18, 1, 192, 1, true, true>(h, P, dtg, max_iters, 0);
-        return launch_lanes<CLOSURE, MODEL, N, 4, 7, 18, 1, 192, 1, true>(h, P, dtg, max_iters, 0);
+        return launch_lanes<CLOSURE, MODEL, N, 4, 7, 18, 1, CLB_OCTET_BLOCK_EH1, 1, true>(h, P, dtg, max_iters, 0);
     } else {
         if (h->sc != 1) return launch_lanes<CLOSURE, MODEL, N, 4, 7, 11, 1, 256, 1, true, true>(h, P, dtg, max_iters, 0);
         return launch_lanes<CLOSURE, MODEL, N, 4, 7, 11, 1, 256, 1, true>(h, P, dtg, max_iters, 0);
@@ -679,7 +685,7 @@ int launch_octet_rt(clb_handle h, const clb::DevView &P, double dtg, int max_ite
     // 182 us, EnergyHydrology N = 20: 190 against 244 us
     if constexpr (MODEL == 1 && Q <= 4) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 14, 2, 192, 1, true>(h, P, dtg, max_iters, 0);
     else if constexpr (MODEL == 0 && Q <= 5) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 11, 2, 256, 1, true>(h, P, dtg, max_iters, 0);
-    else if constexpr (MODEL == 1) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 18, 1, 192, 1, true>(h, P, dtg, max_iters, 0);
+    else if constexpr (MODEL == 1) return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 18, 1, (Q <= 7) ? CLB_OCTET_BLOCK_EH1 : 192, 1, true>(h, P, dtg, max_iters, 0);
     else return launch_lanes<CLOSURE, MODEL, 0, 4, Q, 11, 1, 256, 1, true>(h, P, dtg, max_iters, 0);
 }
 
