@@ -811,6 +811,7 @@ __global__ void k_test_math(int kind, const double *x, const double *y, double *
     case 3: r = clb::fm::exp(x[k]); break;
     case 4: r = clb::fm::sqrt(x[k]); break;
     case 5: r = clb::fm::rcp_seed(x[k]); break;
+    case 8: r = clb::fm::div_by(x[k], y[k], 1.0 / y[k]); break;  // the reciprocal divided as the host does (IEEE)
     default: r = NAN;
     }
     out[k] = r;

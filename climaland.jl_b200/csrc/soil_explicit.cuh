@@ -33,7 +33,7 @@ struct ExplicitConst {
     // quotients of launch constants, divided on the host (make_explicit_view: the same IEEE quotient, i.e. the same bits):
     // in k_explicit_cells_uniform every `/` of two constants was an inlined IEEE division per THREAD -- four of them on
     // a cell's path, 155 of the kernel's ~3 200 issue cycles (tools/sass_cost_lines.py)
-    double rho_l_over_rho_i = 0.0, rho_i_over_rho_l = 0.0, LH_f0_over_grav = 0.0;
+    double rho_l_over_rho_i = 0.0, rho_i_over_rho_l = 0.0, LH_f0_over_grav = 0.0, inv_LH_f0 = 0.0;
 };
 
 // per-cell fields only the explicit stage touches
@@ -427,7 +427,7 @@ __device__ __forceinline__ double Tf_depressed(const Tab &M, const HydroCell &p,
     const double lo = p.theta_r + kSqrtEps;
     const double S = fm::div(fmax(theta_tot, lo) - p.theta_r, fmax(p.nu, lo) - p.theta_r);
     psi_w0 = matric_potential<CLOSURE>(M, p, inv_m, inv_n, S);
-    return fmax(k.T_freeze * M.exp((k.grav * psi_w0) * fm::rcp(LH_f0)), 1.0);  // |g psi / LH| ~ 1e-3: an ulp of it is nothing
+    return fmax(k.T_freeze * M.exp((k.grav * psi_w0) * k.inv_LH_f0), 1.0);  // |g psi / LH| ~ 1e-3: an ulp of it is nothing
 }
 
 }  // namespace xbf

@@ -62,7 +62,8 @@ __device__ __forceinline__ double div_by(double a, double b, double inv_b)
 {
     const double q = a * inv_b;
     const double rem = fma(-b, q, a);
-    return fma(rem, inv_b, q);
+    const double r = fma(rem, inv_b, q);
+    return (fabs(q) <= 1.7976931348623157e308) ? r : q;  // an infinite (or NaN) quotient has no residual: inf - inf
 }
 
 // sqrt(x) for normal finite x > 0; sqrt(0) = 0.

@@ -254,14 +254,14 @@ __global__ void __launch_bounds__(128, CLB_WARP_MIN_BLOCKS) k_step_warp(const De
                 if (P.bottom_bc == 1)
                     qb = -1 * K;
                 else if (P.bottom_bc == 2)
-                    qb = -K * ((psi + P.dz_bot) - psi_bc) / P.dz_bot;
+                    qb = fm::div_by(-K * ((psi + P.dz_bot) - psi_bc), P.dz_bot, P.inv_dz_bot);
                 else
                     qb = bot_w;
                 qb = rot_above<SEG>(qb, l);
                 if (col_ok && is_ghost) qadd_w = qb;
                 if (col_ok && is_top) {
-                    qadd_w = -K * ((psi_bc + P.dz_top) - psi) / P.dz_top;
-                    top_dflux = K * dps / P.dz_top;
+                    qadd_w = fm::div_by(-K * ((psi_bc + P.dz_top) - psi), P.dz_top, P.inv_dz_top);
+                    top_dflux = fm::div_by(K * dps, P.dz_top, P.inv_dz_top);
                 }
                 top_w = __shfl_sync(kFull, qadd_w, N - 1, SEG);
                 bot_w = __shfl_sync(kFull, qadd_w, G, SEG);

@@ -43,6 +43,14 @@ def test_rcp_and_div():
     print("rcp seed max rel err: 2^%.1f" % np.log2(np.max(np.abs(seed * x - 1.0))))
 
 
+def test_div_by_is_the_ieee_quotient():
+    """fm::div_by (division by a launch constant through its host-divided reciprocal): the bits of a / b"""
+    a = np.concatenate([_samples(1e-20, 1e20, seed=11), -_samples(1e-9, 1e3, seed=12), [0.0, 0.3, 1.0, 7.0, np.inf]])
+    b = np.concatenate([_samples(1e-3, 1e2, seed=13), _samples(1e-3, 1e2, seed=14), [0.025, 0.3, 3.0, 0.7, 0.025]])
+    q = _run(8, a, b)
+    assert np.array_equal(q, a / b)
+
+
 def test_log():
     x = np.concatenate([_samples(1e-300, 1e300), _samples(1e-9, 1.0, seed=3), 1.0 - _samples(1e-16, 0.5, seed=4),
                         1.0 + _samples(1e-16, 0.5, seed=5), [1.0, 0.5, 2.0]])
