@@ -33,7 +33,7 @@ struct ExplicitConst {
     // quotients of launch constants, divided on the host (make_explicit_view: the same IEEE quotient, i.e. the same bits):
     // in k_explicit_cells_uniform every `/` of two constants was an inlined IEEE division per THREAD -- four of them on
     // a cell's path, 155 of the kernel's ~3 200 issue cycles (tools/sass_cost_lines.py)
-    double rho_l_over_rho_i = 0.0, rho_i_over_rho_l = 0.0, LH_f0_over_grav = 0.0, inv_LH_f0 = 0.0;
+    double rho_l_over_rho_i = 0.0, rho_i_over_rho_l = 0.0, LH_f0_over_grav = 0.0, inv_LH_f0 = 0.0, inv_rho_l = 0.0;
 };
 
 // per-cell fields only the explicit stage touches
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(SWEEP ? 32 * COLS : 128, SWEEP ? 32 / COLS : C
             term[0] = s_all * dz;
             term[TS] = s_liq * dz;
             term[2 * TS] = s_liq * volumetric_internal_energy_liq(T, E) * dz;
-            term[3 * TS] = (th + thi * E.rho_i / E.rho_l) * dz;
+            term[3 * TS] = (th + fm::div_by(thi * E.rho_i, E.rho_l, X.k.inv_rho_l)) * dz;  // the bits of (thi rho_i) / rho_l
             term[4 * TS] = rho_e * dz;
         }
         if (live) R.is_sat[q] = s_liq;
