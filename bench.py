@@ -506,7 +506,7 @@ def main():
                                        "ms_per_whole_soil_step": ms_whole,
                                        "whole_soil_step": "clb_soil_step: update_aux! + PhaseChange, TOPMODEL runoff + column "
                                                           "integrals + explicit update, fused implicit stage on resident "
-                                                          "mirrors (3 launches, no host transfer)",
+                                                          "mirrors (2 launches, no host transfer)",
                                        "sharded_1deg": {"columns_per_gpu": hi - lo, "ms_per_step": ms_shard,
                                                         "column_steps_per_s": NCOL / (ms_shard * 1e-3),
                                                         "sypd_1deg_sharded_implicit_stage_only": DT / (ms_shard * 1e-3) / 365.0,

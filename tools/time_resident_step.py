@@ -54,7 +54,7 @@ def time_it(fn, label, launches):
 
 
 time_it(step, "call by call", 8)
-time_it(lambda s: s.soil_step(dt, 3), "clb_soil_step", 3)
+time_it(lambda s: s.soil_step(dt, 3), "clb_soil_step", 2)
 for s in ss:
     s.set_option("explicit_kernel", 1)
 time_it(lambda s: s.soil_step(dt, 3), "clb_soil_step with the per-cell explicit kernel", 3)
