@@ -155,6 +155,40 @@ def test_resident_soil_step_matches_oracle(form):
     s.close()
 
 
+@pytest.mark.parametrize("N", [4, 10, 16, 25, 32])
+def test_resident_soil_step_other_level_counts(N):
+    """clb_soil_step on column-fastest mirrors at level counts other than the bench's 15: the ONE-launch explicit stage
+    (a block is 16 columns x N levels, rounded up to whole warps; the last block of 1 237 columns is ragged) in front of
+    whichever stage kernel CLB_VARIANT_AUTO picks for that N"""
+    import climaland_b200  # noqa: F401
+    from climaland_b200 import workloads
+    dt, iters, ncol, seed = 900.0, 3, 1237, 21
+    w = workloads.make_workload("energy_hydrology", ncol, N=N, seed=seed, topmodel=True)
+    xp = workloads.make_explicit_params(w, seed)
+    rng = np.random.default_rng(seed + 100)
+    forcing = dict(precip=-rng.uniform(0.0, 4e-7, ncol), f_max=rng.uniform(0.2, 0.6, ncol))
+    sat = rng.random(ncol) < 0.35
+    w["y_theta_l"][sat, :2] = (w["nu"] - w["y_theta_i"])[sat, :2] + 1e-3
+    P, U, p = oracle_problem(w, nthreads=os.cpu_count() or 1)
+    X = P.explicit_params(**xp)
+    s = _cuda(w, xp, forcing)
+    s.set("precip", forcing["precip"])
+    a = P.new_aux()
+    P.update_aux(X, U, a)
+    _oracle_step(P, U, p, X, forcing, dt, iters)
+    s.soil_step(dt, iters)
+    assert_close(s.get("y_theta_l"), U.theta_l, 1e-12, "theta_l")
+    assert_close(s.get("y_theta_i"), U.theta_i, 1e-12, "theta_i", floor_rel=1e-3)
+    assert_close(s.get("y_rho_e_int"), U.rho_e_int, 1e-12, "rho_e_int")
+    for dev, name in (("p_t", "T"), ("kappa_lag", "kappa"), ("k_lag", "K"), ("total_water", "total_water"),
+                      ("total_energy", "total_energy")):
+        assert_close(s.get(dev), getattr(a, name), 1e-12, name)
+    assert_close(s.get("r_ss"), P.f["R_ss"], 1e-12, "R_ss")
+    assert_close(s.get("h_grad"), P.f["h_grad"], 1e-12, "h_grad")
+    assert_close(s.get("is_saturated"), P.f["is_saturated"], 1e-12, "is_saturated")
+    s.close()
+
+
 @pytest.mark.parametrize("runoff_model", [0, 1, 2], ids=["norunoff", "surface", "topmodel"])
 def test_resident_soil_step_atmos_driven(runoff_model):
     """clb_soil_step with the boundary fluxes of the explicit stage on the device: AtmosDrivenFluxBC top (runoff model +
