@@ -272,6 +272,90 @@ __device__ __forceinline__ void thomas_column(int N, int64_t ld /* level stride 
     }
 }
 
+// The same sweep for N <= NT with the column in registers: every load of the column is issued before the first use (in
+// the loop above a level's loads wait for the level before: they may alias its stores, and the recurrence is a chain of
+// IEEE divisions), c' and d' never touch memory.  Same expressions in the same order: the same bits.  r: b in, x out.
+template <int NT>
+__device__ __forceinline__ void thomas_regs(int N, int64_t ld, const double *__restrict__ lo, const double *__restrict__ di,
+                                            const double *__restrict__ up, double (&r)[NT])
+{
+    double l[NT], d[NT], u[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const int64_t k = (int64_t)((i < N) ? i : 0) * ld;
+        l[i] = __ldg(lo + k);
+        d[i] = __ldg(di + k);
+        u[i] = __ldg(up + k);
+    }
+    double den = 1.0 / d[0];
+    double cprev = u[0] * den, xprev = r[0] * den;
+    u[0] = cprev;
+    r[0] = xprev;
+#pragma unroll
+    for (int i = 1; i < NT; ++i) {
+        if (i < N) {
+            den = 1.0 / (d[i] - l[i] * cprev);
+            cprev = u[i] * den;
+            xprev = (r[i] - l[i] * xprev) * den;
+            u[i] = cprev;
+            r[i] = xprev;
+        }
+    }
+#pragma unroll
+    for (int i = NT - 2; i >= 0; --i) {
+        if (i < N - 1) {
+            xprev = r[i] - u[i] * xprev;
+            r[i] = xprev;
+        }
+    }
+}
+
+// the soil blocks of ldiv! for one column with N <= NT levels, in registers (see thomas_regs); values as ldiv_soil_column
+template <int NT>
+__device__ __forceinline__ void ldiv_soil_regs(const DevView &P, int64_t c)
+{
+    const int N = P.N;
+    const int64_t ld = P.sl, o = P.at(0, c);
+    auto lev = [&](int i) { return (int64_t)((i < N) ? i : 0) * ld + o; };
+    double x1[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) x1[i] = __ldg(P.b_theta_l + lev(i));
+    thomas_regs<NT>(N, ld, P.w11_lo + o, P.w11_di + o, P.w11_up + o, x1);
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+        if (i < N) P.x_theta_l[lev(i)] = x1[i];
+    P.x_intF_w[c] = -P.b_intF_w[c];
+    if (P.model == 1) {
+        double b2[NT], nb[NT];
+        {
+            double wl[NT], wd[NT], wu[NT];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                wl[i] = __ldg(P.w21_lo + lev(i));
+                wd[i] = __ldg(P.w21_di + lev(i));
+                wu[i] = __ldg(P.w21_up + lev(i));
+                b2[i] = __ldg(P.b_rho_e + lev(i));
+                nb[i] = __ldg(P.b_theta_i + lev(i));
+            }
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                double s = wd[i] * x1[i];
+                if (i > 0) s = wl[i] * x1[i - 1] + s;
+                if (i < N - 1 && i < NT - 1) s = s + wu[i] * x1[(i < NT - 1) ? i + 1 : i];
+                b2[i] = b2[i] - s;
+            }
+        }
+        thomas_regs<NT>(N, ld, P.w22_lo + o, P.w22_di + o, P.w22_up + o, b2);
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+            if (i < N) {
+                P.x_rho_e[lev(i)] = b2[i];
+                P.x_theta_i[lev(i)] = -nb[i];
+            }
+        P.x_intF_e[c] = -P.b_intF_e[c];
+    }
+}
+
 // ldiv!: implicit_timestepping.jl:160-171.  Richards: BlockDiagonalSolve.  EH:
 // BlockLowerTriangularSolve(theta_l): W11 x1 = b1; b2' = b2 - W21 x1; W22 x2 = b2'.
 // x = -b for the -I blocks (theta_i and the two flux integrals).
@@ -280,6 +364,10 @@ __global__ void __launch_bounds__(128) k_ldiv(const DevView P)
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.ncol) return;
     const int N = P.N;
+    if (N <= 16) {  // warp-uniform
+        ldiv_soil_regs<16>(P, c);
+        return;
+    }
     const int64_t ld = P.sl, o = P.at(0, c);
     double *cp = P.work[0] + o;
     thomas_column(N, ld, P.w11_lo + o, P.w11_di + o, P.w11_up + o, P.b_theta_l + o, P.x_theta_l + o, cp);
@@ -321,6 +409,10 @@ __global__ void __launch_bounds__(128) k_ldiv_all(const DevView P, const LdivAll
     const int64_t ld = P.sl, o = P.at(0, c);
     if (part == 0) {
         if (!(A.blocks & 1u)) return;
+        if (N <= 16) {
+            ldiv_soil_regs<16>(P, c);
+            return;
+        }
         double *cp = P.work[0] + o;
         thomas_column(N, ld, P.w11_lo + o, P.w11_di + o, P.w11_up + o, P.b_theta_l + o, P.x_theta_l + o, cp);
         P.x_intF_w[c] = -P.b_intF_w[c];
@@ -344,6 +436,16 @@ __global__ void __launch_bounds__(128) k_ldiv_all(const DevView P, const LdivAll
     } else if (part <= 2) {
         if (!(A.blocks & 2u)) return;
         const int sp = part - 1;
+        if (N <= 16) {
+            double r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __ldg(A.co2_b[sp] + o + (int64_t)((i < N) ? i : 0) * ld);
+            thomas_regs<16>(N, ld, A.co2_lo[sp] + o, A.co2_di[sp] + o, A.co2_up[sp] + o, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < N) A.co2_x[sp][o + (int64_t)i * ld] = r[i];
+            return;
+        }
         thomas_column(N, ld, A.co2_lo[sp] + o, A.co2_di[sp] + o, A.co2_up[sp] + o, A.co2_b[sp] + o, A.co2_x[sp] + o,
                       P.work[2 + sp] + o);
     } else {
