@@ -90,13 +90,33 @@ __global__ void __launch_bounds__(128) k_update_boundary_fluxes(const DevView P)
 // InterpolateC2F = mean of the two centres, GradientC2F = centre difference over the
 // centre spacing, DivergenceF2C(SetValue) = face-flux difference over the cell thickness
 // (test/standalone/Soil/soiltest.jl:357-406).  Implicit source: Runoff/Runoff.jl:321-359.
-__global__ void __launch_bounds__(128) k_imp_tendency(const DevView P)
+// NT > 0 (N <= NT): the column's K, psi (T, kappa, is_saturated) in registers, every load issued before the first use --
+// in the rolling form (NT = 0) a level's loads wait behind the stores of the level before, which they may alias: one
+// HBM round trip per level.  Same expressions in the same order either way.
+template <int NT>
+__device__ __forceinline__ void imp_tendency_column(const DevView &P, const int64_t c)
 {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.ncol) return;
     const int N = P.N;
     const bool eh = (P.model == 1);
     const double *Kf = eh ? P.K_lag : P.p_K;
+    constexpr int NA = NT > 0 ? NT : 1;
+    double Kr[NA], pr[NA], Tr[NA], kr[NA], sr[NA];
+    if (NT > 0) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int64_t k = P.at((i < N) ? i : 0, c);
+            Kr[i] = __ldg(Kf + k);
+            pr[i] = __ldg(P.p_psi + k);
+            Tr[i] = eh ? __ldg(P.p_T + k) : 0.0;
+            kr[i] = eh ? __ldg(P.kappa_lag + k) : 0.0;
+            sr[i] = P.topmodel ? __ldg(P.is_sat + k) : 0.0;
+        }
+    }
+    auto ld_K = [&](int i, int64_t k) { return NT > 0 ? Kr[NT > 0 ? i : 0] : Kf[k]; };
+    auto ld_psi = [&](int i, int64_t k) { return NT > 0 ? pr[NT > 0 ? i : 0] : P.p_psi[k]; };
+    auto ld_T = [&](int i, int64_t k) { return NT > 0 ? Tr[NT > 0 ? i : 0] : P.p_T[k]; };
+    auto ld_kap = [&](int i, int64_t k) { return NT > 0 ? kr[NT > 0 ? i : 0] : P.kappa_lag[k]; };
+    auto ld_sat = [&](int i, int64_t k) { return NT > 0 ? sr[NT > 0 ? i : 0] : P.is_sat[k]; };
     const double top_w = P.top_bc_w[c], bot_w = P.bot_bc_w[c];
     double dintw = -(top_w - bot_w), dinte = 0.0;
     double top_h = 0.0, bot_h = 0.0;
@@ -119,29 +139,32 @@ __global__ void __launch_bounds__(128) k_imp_tendency(const DevView P)
     if (eh) P.dY_intF_e[c] = dinte;
 
     const int64_t k00 = P.at(0, c);
-    double K0 = Kf[k00], h0 = P.p_psi[k00] + P.z_c[0];
+    double K0 = ld_K(0, k00), h0 = ld_psi(0, k00) + P.z_c[0];
     double T0 = 0.0, eK0 = 0.0, kap0 = 0.0;
     if (eh) {
-        T0 = P.p_T[k00];
+        T0 = ld_T(0, k00);
         eK0 = volumetric_internal_energy_liq(T0, P.earth) * K0;
-        kap0 = P.kappa_lag[k00];
+        kap0 = ld_kap(0, k00);
     }
     double qw_lo = bot_w, qe_lo = bot_h;
-    for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int i = 0; i < (NT > 0 ? NT : N); ++i) {
+        if (NT > 0 && i >= N) break;
         const int64_t k = P.at(i, c);
         double qw_hi, qe_hi = 0.0;
         double K1 = 0, h1 = 0, T1 = 0, eK1 = 0, kap1 = 0;
         if (i < N - 1) {
             const int64_t k1 = k + P.sl;
-            const double idzf = P.inv_dz_f[i + 1];
-            K1 = Kf[k1];
-            h1 = P.p_psi[k1] + P.z_c[i + 1];
+            const int i1 = (NT > 0 && i + 1 >= NT) ? i : i + 1;  // (never taken: i < N - 1 <= NT - 1; keeps the index in bounds)
+            const double idzf = __ldg(P.inv_dz_f + i + 1);
+            K1 = ld_K(i1, k1);
+            h1 = ld_psi(i1, k1) + __ldg(P.z_c + i + 1);
             const double grad_h = (h1 - h0) * idzf;
             qw_hi = -((K0 + K1) / 2.0) * grad_h;
             if (eh) {
-                T1 = P.p_T[k1];
+                T1 = ld_T(i1, k1);
                 eK1 = volumetric_internal_energy_liq(T1, P.earth) * K1;
-                kap1 = P.kappa_lag[k1];
+                kap1 = ld_kap(i1, k1);
                 const double grad_T = (T1 - T0) * idzf;
                 qe_hi = -((kap0 + kap1) / 2.0) * grad_T - ((eK0 + eK1) / 2.0) * grad_h;
             }
@@ -149,11 +172,11 @@ __global__ void __launch_bounds__(128) k_imp_tendency(const DevView P)
             qw_hi = top_w;
             qe_hi = top_h;
         }
-        const double idzc = P.inv_dz_c[i];
+        const double idzc = __ldg(P.inv_dz_c + i);
         double tw = -((qw_hi - qw_lo) * idzc);
         double sat = 0.0;
         if (P.topmodel) {
-            sat = P.is_sat[k];
+            sat = ld_sat(i, k);
             tw -= src_w * sat;
         }
         P.dY_theta_l[k] = tw;
@@ -167,6 +190,14 @@ __global__ void __launch_bounds__(128) k_imp_tendency(const DevView P)
         qe_lo = qe_hi;
         K0 = K1; h0 = h1; T0 = T1; eK0 = eK1; kap0 = kap1;
     }
+}
+
+__global__ void __launch_bounds__(128) k_imp_tendency(const DevView P)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.ncol) return;
+    if (P.N <= 16) imp_tendency_column<16>(P, c);  // warp-uniform
+    else imp_tendency_column<0>(P, c);
 }
 
 // One tridiagonal row of  W = -dtgamma * (D . Diag(interp(-A)) . G . Diag(coef)) - I
